@@ -1,0 +1,678 @@
+// Fused multi-slot embedding gather (+ linear term + FM + dnn_input assembly) and its backward.
+//
+// Replaces, in ONE pass over the batch, what the reference does with 52 nn.Embedding calls,
+// four torch.cat's and the FM element-wise ops (reference models/basemodel.py:354-380,63-92;
+// inputs.py:126-138; layers/interaction.py:26-34).  HBM-bound: per sample it reads the X row
+// (C floats), F rows of D floats, F linear weights and writes the [F*D + n_dense] block once.
+//
+// Work decomposition: one warp per sample (grid-stride).  A row of D floats is moved by
+// LPR = D/4 lanes, each with one 128-bit load/store, so a warp moves 32/LPR rows per step.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxSmemSlots = 256;  // slot metadata staged in shared memory up to this many fields
+
+__device__ __forceinline__ int64_t decode_id(float xv, int vocab, int32_t* err_flag) {
+    // fp32 -> int64 by truncation, exactly like `.long()` (reference basemodel.py:369)
+    int64_t id = (int64_t)xv;
+    if (id < 0 || id >= (int64_t)vocab) {
+        if (err_flag) atomicOr(err_flag, 1);
+        id = 0;
+    }
+    return id;
+}
+
+struct GatherArgs {
+    const float* X;
+    int64_t ldx;
+    int64_t B;
+    int n_emb, D;
+    const float* const* emb_tables;
+    const int32_t* emb_cols;
+    const int32_t* emb_vocab;
+    int n_lin;
+    const float* const* lin_tables;
+    const int32_t* lin_cols;
+    const int32_t* lin_vocab;
+    int n_dense;
+    const int32_t* dense_cols;
+    int n_lin_dense;
+    const int32_t* lin_dense_cols;
+    const float* lin_dense_w;
+    float* blk;
+    int64_t ld_blk;
+    float* lin;
+    float* fm;
+    int32_t* err_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward, vector path: D % 4 == 0 and D/4 a power of two <= 32
+// ---------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
+    constexpr int RPW = 32 / LPR;  // rows per warp step
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // stage slot metadata (table pointer, column, vocab) in shared memory
+    const float** s_tab = reinterpret_cast<const float**>(smem_raw);
+    int32_t* s_col = reinterpret_cast<int32_t*>(s_tab + a.n_emb);
+    int32_t* s_voc = s_col + a.n_emb;
+    for (int i = threadIdx.x; i < a.n_emb; i += blockDim.x) {
+        s_tab[i] = a.emb_tables[i];
+        s_col[i] = a.emb_cols[i];
+        s_voc[i] = a.emb_vocab[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int rslot = lane / LPR;
+    const int D = a.D;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    for (int64_t b = warp0; b < a.B; b += nwarps) {
+        const float* xrow = a.X + b * a.ldx;
+        float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+        float q = 0.f;
+        for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
+            const int f = f0 + rslot;
+            if (f < a.n_emb) {
+                const int64_t id = decode_id(__ldg(xrow + s_col[f]), s_voc[f], a.err_flag);
+                const float4 v = ld_stream4(s_tab[f] + id * D + sub * 4);
+                if (a.blk) st_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4, v);
+                S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+                q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        }
+        float fmv = 0.f;
+        if (a.fm) {
+            // sum S over the lanes that hold the same quad of d (stride LPR), q over all lanes
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
+                S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
+                S.z += __shfl_xor_sync(0xffffffffu, S.z, o);
+                S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
+            }
+            float t = S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w;
+#pragma unroll
+            for (int o = 1; o < LPR; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            q = warp_sum(q);
+            fmv = 0.5f * (t - q);
+        }
+        // linear term: sparse weights + dense dot; dense copy into the block
+        float lp = 0.f;
+        for (int f = lane; f < a.n_lin; f += 32) {
+            const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+            lp += __ldg(a.lin_tables[f] + id);
+        }
+        for (int k = lane; k < a.n_lin_dense; k += 32)
+            lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
+        if (a.blk) {
+            float* drow = a.blk + b * a.ld_blk + (int64_t)a.n_emb * D;
+            for (int k = lane; k < a.n_dense; k += 32) drow[k] = __ldg(xrow + a.dense_cols[k]);
+        }
+        if (a.lin) {
+            lp = warp_sum(lp);
+            if (lane == 0) a.lin[b] = lp;
+        }
+        if (a.fm && lane == 0) a.fm[b] = fmv;
+    }
+}
+
+// forward, generic path: any D (scalar loads); FM is computed by fm_fwd_kernel afterwards
+__global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int D = a.D;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp0; b < a.B; b += nwarps) {
+        const float* xrow = a.X + b * a.ldx;
+        if (a.blk) {
+            const int total = a.n_emb * D;
+            for (int i = lane; i < total; i += 32) {
+                const int f = i / D, d = i - f * D;
+                const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], a.err_flag);
+                a.blk[b * a.ld_blk + i] = __ldg(a.emb_tables[f] + id * D + d);
+            }
+            float* drow = a.blk + b * a.ld_blk + (int64_t)total;
+            for (int k = lane; k < a.n_dense; k += 32) drow[k] = __ldg(xrow + a.dense_cols[k]);
+        }
+        float lp = 0.f;
+        for (int f = lane; f < a.n_lin; f += 32) {
+            const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+            lp += __ldg(a.lin_tables[f] + id);
+        }
+        for (int k = lane; k < a.n_lin_dense; k += 32)
+            lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
+        if (a.lin) {
+            lp = warp_sum(lp);
+            if (lane == 0) a.lin[b] = lp;
+        }
+    }
+}
+
+// FM over an assembled block: one warp per sample, lanes over d
+__global__ void __launch_bounds__(256) fm_fwd_kernel(const float* __restrict__ blk, int64_t ld,
+                                                     int64_t B, int F, int D, float* fm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        const float* row = blk + b * ld;
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            float s = 0.f, q = 0.f;
+            for (int f = 0; f < F; ++f) {
+                const float v = row[f * D + d];
+                s += v;
+                q += v * v;
+            }
+            acc += s * s - q;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) fm[b] = 0.5f * acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) fm_bwd_kernel(const float* __restrict__ blk, int64_t ld,
+                                                     int64_t B, int F, int D,
+                                                     const float* __restrict__ g, float* d_blk,
+                                                     int64_t ld_d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        const float* row = blk + b * ld;
+        float* drow = d_blk + b * ld_d;
+        const float gb = g[b];
+        for (int d = lane; d < D; d += 32) {
+            float s = 0.f;
+            for (int f = 0; f < F; ++f) s += row[f * D + d];
+            for (int f = 0; f < F; ++f) drow[f * D + d] += gb * (s - row[f * D + d]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct ScatterArgs {
+    const float* X;
+    int64_t ldx;
+    int64_t B;
+    int n_emb, D;
+    float* const* emb_out;         // dense: grad tables [V,D]; rowwise: row-grad buffers [B,D]
+    const int32_t* emb_cols;       // dense: X column; rowwise: plan column
+    const int32_t* emb_vocab;
+    int n_lin;
+    float* const* lin_out;
+    const int32_t* lin_cols;
+    const int32_t* lin_vocab;
+    const float* blk;
+    int64_t ld_blk;
+    const float* d_blk;
+    int64_t ld_dblk;
+    const float* g_fm;
+    const float* g_lin;
+    // rowwise only
+    int n_plan;
+    const int32_t* inv;
+    const int32_t* cnt;
+};
+
+// One warp per sample.  Pass 1 recomputes S = sum_f E (only when the FM branch is live), pass 2
+// forms r[b,f,:] = d_blk + g_fm (S - E) and adds it to its destination row: dense mode ->
+// red.global.add.v4.f32 into [V,D]; rowwise mode -> plain store when the id is unique in the
+// batch (cnt == 1), vector reduction otherwise.
+template <int LPR, bool ROWWISE>
+__global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int rslot = lane / LPR;
+    const int D = a.D;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    for (int64_t b = warp0; b < a.B; b += nwarps) {
+        const float* xrow = a.X ? a.X + b * a.ldx : nullptr;
+        float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gfm = 0.f;
+        if (a.g_fm) {
+            gfm = __ldg(a.g_fm + b);
+            for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
+                const int f = f0 + rslot;
+                if (f < a.n_emb) {
+                    const float4 v = ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
+                    S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+                }
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
+                S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
+                S.z += __shfl_xor_sync(0xffffffffu, S.z, o);
+                S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
+            }
+        }
+        for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
+            const int f = f0 + rslot;
+            if (f < a.n_emb) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.d_blk) r = ld_stream4(a.d_blk + b * a.ld_dblk + (int64_t)f * D + sub * 4);
+                if (a.g_fm) {
+                    const float4 v = ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
+                    r.x += gfm * (S.x - v.x);
+                    r.y += gfm * (S.y - v.y);
+                    r.z += gfm * (S.z - v.z);
+                    r.w += gfm * (S.w - v.w);
+                }
+                if (ROWWISE) {
+                    const int pc = a.emb_cols[f];
+                    const int u = __ldg(a.inv + b * a.n_plan + pc);
+                    const int c = __ldg(a.cnt + (int64_t)pc * a.B + u);
+                    float* dst = a.emb_out[f] + (int64_t)u * D + sub * 4;
+                    if (c == 1) st_stream4(dst, r);
+                    else red_add4(dst, r);
+                } else {
+                    const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], nullptr);
+                    red_add4(a.emb_out[f] + id * D + sub * 4, r);
+                }
+            }
+        }
+        if (a.g_lin) {
+            const float gl = __ldg(a.g_lin + b);
+            for (int f = lane; f < a.n_lin; f += 32) {
+                if (ROWWISE) {
+                    const int pc = a.lin_cols[f];
+                    const int u = __ldg(a.inv + b * a.n_plan + pc);
+                    const int c = __ldg(a.cnt + (int64_t)pc * a.B + u);
+                    if (c == 1) a.lin_out[f][u] = gl;
+                    else atomicAdd(a.lin_out[f] + u, gl);
+                } else {
+                    const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], nullptr);
+                    atomicAdd(a.lin_out[f] + id, gl);
+                }
+            }
+        }
+    }
+}
+
+// generic (any D) backward: scalar atomics
+template <bool ROWWISE>
+__global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int D = a.D;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp0; b < a.B; b += nwarps) {
+        const float* xrow = a.X ? a.X + b * a.ldx : nullptr;
+        const float gfm = a.g_fm ? a.g_fm[b] : 0.f;
+        const int total = a.n_emb * D;
+        for (int i = lane; i < total; i += 32) {
+            const int f = i / D, d = i - f * D;
+            float r = a.d_blk ? a.d_blk[b * a.ld_dblk + i] : 0.f;
+            if (a.g_fm) {
+                float s = 0.f;
+                for (int f2 = 0; f2 < a.n_emb; ++f2) s += a.blk[b * a.ld_blk + f2 * D + d];
+                r += gfm * (s - a.blk[b * a.ld_blk + i]);
+            }
+            if (ROWWISE) {
+                const int pc = a.emb_cols[f];
+                const int u = a.inv[b * a.n_plan + pc];
+                atomicAdd(a.emb_out[f] + (int64_t)u * D + d, r);
+            } else {
+                const int64_t id = decode_id(xrow[a.emb_cols[f]], a.emb_vocab[f], nullptr);
+                atomicAdd(a.emb_out[f] + id * D + d, r);
+            }
+        }
+        if (a.g_lin) {
+            const float gl = a.g_lin[b];
+            for (int f = lane; f < a.n_lin; f += 32) {
+                if (ROWWISE) {
+                    const int u = a.inv[b * a.n_plan + a.lin_cols[f]];
+                    atomicAdd(a.lin_out[f] + u, gl);
+                } else {
+                    const int64_t id = decode_id(xrow[a.lin_cols[f]], a.lin_vocab[f], nullptr);
+                    atomicAdd(a.lin_out[f] + id, gl);
+                }
+            }
+        }
+    }
+}
+
+// rowwise prep: zero every destination row that will not be written by exactly one plain store
+// (cnt == 0: padding beyond n_uniq; cnt > 1: accumulated with reductions).  force_all zeroes
+// everything (generic path uses atomics only).
+__global__ void __launch_bounds__(256) rowgrad_prep_kernel(int64_t B, const int32_t* __restrict__ cnt,
+                                                           int n_emb, int D, float* const* emb_out,
+                                                           const int32_t* emb_plan, int n_lin,
+                                                           float* const* lin_out,
+                                                           const int32_t* lin_plan, int force_all) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int D4 = (D % 4 == 0) ? D / 4 : 0;
+    if (D4) {
+        const int64_t total = (int64_t)n_emb * B * D4;
+        for (int64_t i = tid; i < total; i += nthreads) {
+            const int sub = (int)(i % D4);
+            const int64_t u = (i / D4) % B;
+            const int f = (int)(i / ((int64_t)D4 * B));
+            if (force_all || __ldg(cnt + (int64_t)emb_plan[f] * B + u) != 1)
+                *reinterpret_cast<float4*>(emb_out[f] + u * D + sub * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        const int64_t total = (int64_t)n_emb * B * D;
+        for (int64_t i = tid; i < total; i += nthreads) {
+            const int d = (int)(i % D);
+            const int64_t u = (i / D) % B;
+            const int f = (int)(i / ((int64_t)D * B));
+            if (force_all || cnt[(int64_t)emb_plan[f] * B + u] != 1) emb_out[f][u * D + d] = 0.f;
+        }
+    }
+    const int64_t total_l = (int64_t)n_lin * B;
+    for (int64_t i = tid; i < total_l; i += nthreads) {
+        const int64_t u = i % B;
+        const int f = (int)(i / B);
+        if (force_all || __ldg(cnt + (int64_t)lin_plan[f] * B + u) != 1) lin_out[f][u] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unique plan (hash based, per id column)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restrict__ X, int64_t ldx,
+                                                          int64_t B, int n_cols,
+                                                          const int32_t* __restrict__ cols,
+                                                          const int32_t* __restrict__ vocab,
+                                                          int32_t* keys, int32_t* vals, int64_t H,
+                                                          int32_t* n_uniq, int32_t* uniq,
+                                                          int32_t* inv, int32_t* err_flag) {
+    const int64_t total = B * n_cols;
+    const uint32_t mask = (uint32_t)(H - 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % n_cols);
+        const int64_t b = i / n_cols;
+        const int32_t key = (int32_t)decode_id(__ldg(X + b * ldx + cols[c]), vocab[c], err_flag);
+        int32_t* kc = keys + (int64_t)c * H;
+        uint32_t slot = mix32((uint32_t)key) & mask;
+        while (true) {
+            int32_t k = __ldcg(kc + slot);
+            if (k == -1) {
+                const int32_t old = atomicCAS(kc + slot, -1, key);
+                if (old == -1) {  // this thread inserted the key: hand out the next unique index
+                    const int32_t u = atomicAdd(n_uniq + c, 1);
+                    vals[(int64_t)c * H + slot] = u;
+                    uniq[(int64_t)c * B + u] = key;
+                    break;
+                }
+                k = old;
+            }
+            if (k == key) break;
+            slot = (slot + 1) & mask;
+        }
+        inv[i] = (int32_t)slot;  // replaced by the unique index in plan_finalize_kernel
+    }
+}
+
+__global__ void __launch_bounds__(256) plan_finalize_kernel(int64_t B, int n_cols,
+                                                            const int32_t* __restrict__ vals,
+                                                            int64_t H, int32_t* inv, int32_t* cnt) {
+    const int64_t total = B * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % n_cols);
+        const int32_t u = vals[(int64_t)c * H + inv[i]];
+        inv[i] = u;
+        atomicAdd(cnt + (int64_t)c * B + u, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) lin_dense_wgrad_kernel(const float* __restrict__ X,
+                                                              int64_t ldx, int64_t B, int n,
+                                                              const int32_t* __restrict__ cols,
+                                                              const float* __restrict__ g, float* dw) {
+    // thread k of each group of n accumulates column k over a strided set of samples
+    extern __shared__ float s_acc[];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_acc[k] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        float acc = 0.f;
+        if (k < n) {
+            const int c = cols[k];
+            for (int64_t b = warp0; b < B; b += nwarps) acc += __ldg(g + b) * __ldg(X + b * ldx + c);
+            atomicAdd(&s_acc[k], acc);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(dw + k, s_acc[k]);
+}
+
+int lpr_for_dim(int D) {
+    if (D % 4 != 0) return 0;
+    const int l = D / 4;
+    if (l < 1 || l > 32 || (l & (l - 1)) != 0) return 0;
+    return l;
+}
+
+unsigned sample_grid(int64_t B, int warps_per_block, int blocks_per_sm) {
+    int64_t want = ceil_div64(B, warps_per_block);
+    int64_t cap = (int64_t)ctr_sm_count() * blocks_per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (unsigned)want;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+                              const float* const* emb_tables, const int32_t* emb_cols,
+                              const int32_t* emb_vocab, int n_lin, const float* const* lin_tables,
+                              const int32_t* lin_cols, const int32_t* lin_vocab, int n_dense,
+                              const int32_t* dense_cols, int n_lin_dense,
+                              const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
+                              int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
+                              void* stream) {
+    CTR_ARG(X && B >= 0 && ldx >= 0, "ctr_gather_fwd: X/B/ldx invalid");
+    CTR_ARG(n_emb >= 0 && n_lin >= 0 && n_dense >= 0 && n_lin_dense >= 0, "ctr_gather_fwd: negative count");
+    CTR_ARG(n_emb == 0 || (D > 0 && emb_tables && emb_cols && emb_vocab), "ctr_gather_fwd: embedding slot arrays missing");
+    CTR_ARG(n_lin == 0 || (lin_tables && lin_cols && lin_vocab), "ctr_gather_fwd: linear slot arrays missing");
+    CTR_ARG(n_dense == 0 || dense_cols, "ctr_gather_fwd: dense_cols missing");
+    CTR_ARG(n_lin_dense == 0 || (lin_dense_cols && lin_dense_w), "ctr_gather_fwd: linear dense arrays missing");
+    CTR_ARG(!blk || ld_blk >= (int64_t)n_emb * D + n_dense, "ctr_gather_fwd: ld_blk too small");
+    if (B == 0) return 0;
+    GatherArgs a{X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols,
+                 lin_vocab, n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk,
+                 lin, fm, err_flag};
+    cudaStream_t st = as_stream(stream);
+    const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
+    const bool vec_ok = lpr > 0 && n_emb <= kMaxSmemSlots &&
+                        (!blk || ((ld_blk % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk) & 15) == 0)));
+    const unsigned grid = sample_grid(B, 8, 8);
+    if (vec_ok) {
+        const size_t smem = (size_t)n_emb * (sizeof(void*) + 8);
+        switch (lpr) {
+            case 1: gather_fwd_vec_kernel<1><<<grid, 256, smem, st>>>(a); break;
+            case 2: gather_fwd_vec_kernel<2><<<grid, 256, smem, st>>>(a); break;
+            case 4: gather_fwd_vec_kernel<4><<<grid, 256, smem, st>>>(a); break;
+            case 8: gather_fwd_vec_kernel<8><<<grid, 256, smem, st>>>(a); break;
+            case 16: gather_fwd_vec_kernel<16><<<grid, 256, smem, st>>>(a); break;
+            default: gather_fwd_vec_kernel<32><<<grid, 256, smem, st>>>(a); break;
+        }
+        CTR_LAUNCH_OK("gather_fwd_vec_kernel");
+    } else {
+        CTR_ARG(blk || !fm || n_emb == 0, "ctr_gather_fwd: FM on the generic path needs blk");
+        gather_fwd_generic_kernel<<<grid, 256, 0, st>>>(a);
+        CTR_LAUNCH_OK("gather_fwd_generic_kernel");
+        if (fm) {
+            if (n_emb > 0) {
+                fm_fwd_kernel<<<grid, 256, 0, st>>>(blk, ld_blk, B, n_emb, D, fm);
+                CTR_LAUNCH_OK("fm_fwd_kernel");
+            } else {
+                CTR_CUDA(cudaMemsetAsync(fm, 0, sizeof(float) * B, st));
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int ctr_fm_fwd(const float* blk, int64_t ld, int64_t B, int F, int D, float* fm,
+                          void* stream) {
+    CTR_ARG(blk && fm && F > 0 && D > 0 && ld >= (int64_t)F * D, "ctr_fm_fwd: bad arguments");
+    if (B == 0) return 0;
+    fm_fwd_kernel<<<sample_grid(B, 8, 8), 256, 0, as_stream(stream)>>>(blk, ld, B, F, D, fm);
+    CTR_LAUNCH_OK("fm_fwd_kernel");
+    return 0;
+}
+
+extern "C" int ctr_fm_bwd(const float* blk, int64_t ld, int64_t B, int F, int D, const float* g,
+                          float* d_blk, int64_t ld_d, void* stream) {
+    CTR_ARG(blk && g && d_blk && F > 0 && D > 0, "ctr_fm_bwd: bad arguments");
+    if (B == 0) return 0;
+    fm_bwd_kernel<<<sample_grid(B, 8, 8), 256, 0, as_stream(stream)>>>(blk, ld, B, F, D, g, d_blk, ld_d);
+    CTR_LAUNCH_OK("fm_bwd_kernel");
+    return 0;
+}
+
+static int launch_scatter(ScatterArgs& a, bool rowwise, cudaStream_t st) {
+    const int lpr = (a.n_emb > 0) ? lpr_for_dim(a.D) : 1;
+    const bool aligned =
+        (!a.blk || (a.ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.blk) & 15) == 0)) &&
+        (!a.d_blk || (a.ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.d_blk) & 15) == 0));
+    const unsigned grid = sample_grid(a.B, 8, 8);
+    if (lpr > 0 && aligned) {
+#define LAUNCH_SC(L)                                                                     \
+    if (rowwise) scatter_bwd_vec_kernel<L, true><<<grid, 256, 0, st>>>(a);               \
+    else scatter_bwd_vec_kernel<L, false><<<grid, 256, 0, st>>>(a);
+        switch (lpr) {
+            case 1: LAUNCH_SC(1) break;
+            case 2: LAUNCH_SC(2) break;
+            case 4: LAUNCH_SC(4) break;
+            case 8: LAUNCH_SC(8) break;
+            case 16: LAUNCH_SC(16) break;
+            default: LAUNCH_SC(32) break;
+        }
+#undef LAUNCH_SC
+        CTR_LAUNCH_OK("scatter_bwd_vec_kernel");
+        return 1;
+    }
+    if (rowwise) scatter_bwd_generic_kernel<true><<<grid, 256, 0, st>>>(a);
+    else scatter_bwd_generic_kernel<false><<<grid, 256, 0, st>>>(a);
+    CTR_LAUNCH_OK("scatter_bwd_generic_kernel");
+    return 2;
+}
+
+extern "C" int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+                                     float* const* emb_grads, const int32_t* emb_cols,
+                                     const int32_t* emb_vocab, int n_lin, float* const* lin_grads,
+                                     const int32_t* lin_cols, const int32_t* lin_vocab,
+                                     const float* blk, int64_t ld_blk, const float* d_blk,
+                                     int64_t ld_dblk, const float* g_fm, const float* g_lin,
+                                     void* stream) {
+    CTR_ARG(X && B >= 0, "ctr_scatter_bwd_dense: X/B invalid");
+    CTR_ARG(n_emb == 0 || (D > 0 && emb_grads && emb_cols && emb_vocab), "ctr_scatter_bwd_dense: embedding arrays missing");
+    CTR_ARG(n_lin == 0 || !g_lin || (lin_grads && lin_cols && lin_vocab), "ctr_scatter_bwd_dense: linear arrays missing");
+    CTR_ARG(!g_fm || blk, "ctr_scatter_bwd_dense: FM gradient needs blk");
+    if (B == 0) return 0;
+    ScatterArgs a{X, ldx, B, n_emb, D, emb_grads, emb_cols, emb_vocab, g_lin ? n_lin : 0, lin_grads,
+                  lin_cols, lin_vocab, blk, ld_blk, d_blk, ld_dblk, g_fm, g_lin, 0, nullptr, nullptr};
+    if (!d_blk && !g_fm) a.n_emb = 0;
+    const int r = launch_scatter(a, false, as_stream(stream));
+    return r < 0 ? r : (r > 2 ? r : 0);
+}
+
+extern "C" int64_t ctr_unique_plan_hash_slots(int64_t B) {
+    int64_t h = 64;
+    while (h < 2 * B) h <<= 1;
+    return h;
+}
+
+extern "C" int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_cols,
+                               const int32_t* cols, const int32_t* vocab, int32_t* hash_keys,
+                               int32_t* hash_vals, int64_t H, int32_t* n_uniq, int32_t* uniq,
+                               int32_t* inv, int32_t* cnt, int32_t* err_flag, void* stream) {
+    CTR_ARG(X && cols && vocab && hash_keys && hash_vals && n_uniq && uniq && inv && cnt,
+            "ctr_unique_plan: null argument");
+    CTR_ARG(n_cols > 0 && B >= 0, "ctr_unique_plan: bad sizes");
+    CTR_ARG(H >= 2 * B && (H & (H - 1)) == 0, "ctr_unique_plan: H must be a power of two >= 2B");
+    if (B == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    CTR_CUDA(cudaMemsetAsync(hash_keys, 0xFF, sizeof(int32_t) * H * n_cols, st));
+    CTR_CUDA(cudaMemsetAsync(n_uniq, 0, sizeof(int32_t) * n_cols, st));
+    CTR_CUDA(cudaMemsetAsync(uniq, 0, sizeof(int32_t) * B * n_cols, st));
+    CTR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * B * n_cols, st));
+    int64_t blocks = ceil_div64(B * n_cols, 256);
+    const int64_t cap = (int64_t)ctr_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    plan_insert_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, B, n_cols, cols, vocab, hash_keys,
+                                                         hash_vals, H, n_uniq, uniq, inv, err_flag);
+    CTR_LAUNCH_OK("plan_insert_kernel");
+    plan_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, n_cols, hash_vals, H, inv, cnt);
+    CTR_LAUNCH_OK("plan_finalize_kernel");
+    return 0;
+}
+
+extern "C" int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv,
+                                       const int32_t* cnt, const int32_t* n_uniq, int n_emb, int D,
+                                       float* const* emb_rowgrad, const int32_t* emb_plan_col,
+                                       int n_lin, float* const* lin_rowgrad,
+                                       const int32_t* lin_plan_col, const float* blk, int64_t ld_blk,
+                                       const float* d_blk, int64_t ld_dblk, const float* g_fm,
+                                       const float* g_lin, void* stream) {
+    (void)n_uniq;
+    CTR_ARG(inv && cnt && n_plan_cols > 0 && B >= 0, "ctr_scatter_bwd_rowwise: plan missing");
+    CTR_ARG(n_emb == 0 || (D > 0 && emb_rowgrad && emb_plan_col), "ctr_scatter_bwd_rowwise: embedding arrays missing");
+    CTR_ARG(n_lin == 0 || (lin_rowgrad && lin_plan_col), "ctr_scatter_bwd_rowwise: linear arrays missing");
+    CTR_ARG(!g_fm || blk, "ctr_scatter_bwd_rowwise: FM gradient needs blk");
+    if (B == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    ScatterArgs a{nullptr, 0, B, n_emb, D, emb_rowgrad, emb_plan_col, nullptr, n_lin, lin_rowgrad,
+                  lin_plan_col, nullptr, blk, ld_blk, d_blk, ld_dblk, g_fm, g_lin, n_plan_cols, inv, cnt};
+    const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
+    const bool aligned =
+        (!blk || (ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(blk) & 15) == 0)) &&
+        (!d_blk || (ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(d_blk) & 15) == 0));
+    const int force_all = (lpr > 0 && aligned) ? 0 : 1;
+    {
+        int64_t work = (int64_t)n_emb * B * (D % 4 == 0 ? D / 4 : D);
+        if ((int64_t)n_lin * B > work) work = (int64_t)n_lin * B;
+        int64_t blocks = ceil_div64(work, 256);
+        const int64_t cap = (int64_t)ctr_sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        rowgrad_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, cnt, n_emb, D, emb_rowgrad,
+                                                              emb_plan_col, n_lin, lin_rowgrad,
+                                                              lin_plan_col, force_all);
+        CTR_LAUNCH_OK("rowgrad_prep_kernel");
+    }
+    // the sparse linear rows still need a value when the linear branch received no gradient
+    const int r = launch_scatter(a, true, st);
+    return r < 0 ? r : (r > 2 ? r : 0);
+}
+
+extern "C" int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n,
+                                   const int32_t* cols, const float* g, float* dw, void* stream) {
+    CTR_ARG(X && cols && g && dw && n > 0 && B >= 0, "ctr_lin_dense_wgrad: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n, st));
+    if (B == 0) return 0;
+    lin_dense_wgrad_kernel<<<sample_grid(B, 8 * 64, 2), 256, sizeof(float) * n, st>>>(X, ldx, B, n, cols, g, dw);
+    CTR_LAUNCH_OK("lin_dense_wgrad_kernel");
+    return 0;
+}

@@ -1,0 +1,712 @@
+"""autograd wrappers over the C ABI (include/ctr_b200.h).
+
+Every function here launches hand-written sm_100a kernels from libctr_b200.so on torch's
+current CUDA stream; torch only owns the memory and the autograd graph.  There is no CPU or
+stock-torch fallback: a non-CUDA tensor raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT_CODES = {"linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("deepctr_torch_b200: %s must be a CUDA tensor — the hot path runs only on "
+                           "the GPU kernels of libctr_b200.so (no CPU fallback)" % what)
+    if t.dtype != torch.float32:
+        raise TypeError("deepctr_torch_b200: %s must be float32, got %s" % (what, t.dtype))
+
+
+def _rowmajor(t):
+    """Return t if its last dim is unit-stride (2-D), else a contiguous copy."""
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
+def _round4(n):
+    return (n + 3) // 4 * 4
+
+
+def act_code(name):
+    if isinstance(name, str) and name.lower() in ACT_CODES:
+        return ACT_CODES[name.lower()]
+    raise NotImplementedError("activation %r is not implemented by the CUDA tower "
+                              "(available: %s)" % (name, sorted(ACT_CODES)))
+
+
+# ----------------------------------------------------------------------------------------------
+# fused input: gather + linear + FM + dnn_input assembly
+# ----------------------------------------------------------------------------------------------
+class GatherPlan:
+    """Device-side slot metadata for one model (built once, refreshed if storages move).
+
+    emb / lin: lists of (parameter, X column, vocab, plan column) per field; dense_cols: X columns
+    copied behind the embedding block; lin_dense_cols: X columns of Linear's dense weight."""
+
+    def __init__(self, emb_slots, lin_slots, dense_cols, lin_dense_cols, dim, device):
+        self.device = torch.device(device)
+        self.emb_params = [s[0] for s in emb_slots]
+        self.lin_params = [s[0] for s in lin_slots]
+        self.n_emb, self.n_lin = len(emb_slots), len(lin_slots)
+        self.D = int(dim) if self.n_emb else 0
+        self.n_dense, self.n_lin_dense = len(dense_cols), len(lin_dense_cols)
+        self.width = self.n_emb * self.D + self.n_dense
+        self.ld = _round4(max(self.width, 1))
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.emb_cols = torch.tensor([s[1] for s in emb_slots], **i32)
+        self.emb_vocab = torch.tensor([s[2] for s in emb_slots], **i32)
+        self.lin_cols = torch.tensor([s[1] for s in lin_slots], **i32)
+        self.lin_vocab = torch.tensor([s[2] for s in lin_slots], **i32)
+        self.dense_cols = torch.tensor(list(dense_cols), **i32)
+        self.lin_dense_cols = torch.tensor(list(lin_dense_cols), **i32)
+        # the unique plan is per distinct id column of X
+        plan_cols = []
+        for s in list(emb_slots) + list(lin_slots):
+            if s[1] not in plan_cols:
+                plan_cols.append(s[1])
+        self.plan_cols_host = plan_cols
+        vocab_of = {}
+        for s in list(emb_slots) + list(lin_slots):
+            vocab_of[s[1]] = max(vocab_of.get(s[1], 0), s[2])
+        self.plan_cols = torch.tensor(plan_cols, **i32)
+        self.plan_vocab = torch.tensor([vocab_of[c] for c in plan_cols], **i32)
+        self.emb_plan_col = torch.tensor([plan_cols.index(s[1]) for s in emb_slots], **i32)
+        self.lin_plan_col = torch.tensor([plan_cols.index(s[1]) for s in lin_slots], **i32)
+        self.err_flag = torch.zeros(1, **i32)
+        self._ptr_key = None
+        self._emb_ptrs = self._lin_ptrs = None
+        self._ws = {}
+
+    def table_ptrs(self):
+        key = tuple(p.data_ptr() for p in self.emb_params) + tuple(p.data_ptr() for p in self.lin_params)
+        if key != self._ptr_key:
+            i64 = dict(dtype=torch.int64, device=self.device)
+            self._emb_ptrs = torch.tensor(list(key[:self.n_emb]), **i64)
+            self._lin_ptrs = torch.tensor(list(key[self.n_emb:]), **i64)
+            self._ptr_key = key
+        return self._emb_ptrs, self._lin_ptrs
+
+    def workspace(self, B):
+        """Buffers of the row-wise backward for batch size B (cached)."""
+        ws = self._ws.get(B)
+        if ws is None:
+            n = len(self.plan_cols_host)
+            H = int(_lib.load().ctr_unique_plan_hash_slots(B))
+            i32 = dict(dtype=torch.int32, device=self.device)
+            ws = {"H": H, "keys": torch.empty(n * H, **i32), "vals": torch.empty(n * H, **i32),
+                  "n_uniq": torch.empty(n, **i32), "uniq": torch.empty(n, B, **i32),
+                  "inv": torch.empty(B, n, **i32), "cnt": torch.empty(n, B, **i32)}
+            self._ws = {B: ws}
+        return ws
+
+    def check_ids(self):
+        """Raise IndexError (like nn.Embedding on CPU) if any id was out of range.  Synchronises."""
+        if int(self.err_flag.item()) != 0:
+            self.err_flag.zero_()
+            raise IndexError("index out of range in self (sparse feature id outside [0, vocabulary_size))")
+
+
+class _FusedInput(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, plan, lin_dense_w, want_blk, want_fm, grad_mode, *tables):
+        _require_cuda(X, "X")
+        X = _rowmajor(X)
+        B = X.shape[0]
+        dev = X.device
+        emb_ptrs, lin_ptrs = plan.table_ptrs()
+        blk = torch.empty(B, plan.ld, device=dev, dtype=torch.float32) if want_blk else None
+        lin =torch.empty(B, device=dev, dtype=torch.float32)
+        fm = torch.empty(B, device=dev, dtype=torch.float32) if want_fm else None
+        n_emb = plan.n_emb if (want_blk or want_fm) else 0
+        _lib.call("ctr_gather_fwd", _ptr(X), X.stride(0), B,
+                  n_emb, plan.D, _ptr(emb_ptrs), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
+                  plan.n_lin, _ptr(lin_ptrs), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
+                  plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
+                  plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
+                  _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
+                  _stream())
+        ctx.plan, ctx.grad_mode = plan, grad_mode
+        ctx.want_blk, ctx.want_fm = want_blk, want_fm
+        ctx.has_ldw = lin_dense_w is not None
+        ctx.n_tables = len(tables)
+        ctx.save_for_backward(X, blk if blk is not None else X.new_empty(0))
+        outs = (blk if blk is not None else X.new_empty(0), lin, fm if fm is not None else X.new_empty(0))
+        if blk is None:
+            ctx.mark_non_differentiable(outs[0])
+        if fm is None:
+            ctx.mark_non_differentiable(outs[2])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_blk, d_lin, d_fm):
+        plan = ctx.plan
+        X, blk = ctx.saved_tensors
+        B = X.shape[0]
+        dev = X.device
+        if blk.numel() == 0:
+            blk = None
+        if not ctx.want_blk:
+            d_blk = None
+        if not ctx.want_fm:
+            d_fm = None
+        if d_blk is not None:
+            d_blk = _rowmajor(d_blk)
+            if d_blk.stride(0) % 4 != 0 or d_blk.data_ptr() % 16 != 0:
+                tmp = torch.empty(B, plan.ld, device=dev, dtype=torch.float32)
+                tmp[:, :d_blk.shape[1]].copy_(d_blk)
+                d_blk = tmp
+        d_lin = d_lin.contiguous() if d_lin is not None else torch.zeros(B, device=dev)
+        d_fm = d_fm.contiguous() if d_fm is not None else None
+        emb_live = plan.n_emb > 0 and (d_blk is not None or d_fm is not None)
+        n_emb = plan.n_emb if emb_live else 0
+        i64 = dict(dtype=torch.int64, device=dev)
+        grads_emb, grads_lin = [], []
+        if ctx.grad_mode == "dense":
+            grads_emb = [torch.zeros_like(p) for p in plan.emb_params] if emb_live else [None] * plan.n_emb
+            grads_lin = [torch.zeros_like(p) for p in plan.lin_params]
+            eg = torch.tensor([g.data_ptr() for g in grads_emb], **i64) if emb_live else None
+            lg = torch.tensor([g.data_ptr() for g in grads_lin], **i64)
+            _lib.call("ctr_scatter_bwd_dense", _ptr(X), X.stride(0), B,
+                      n_emb, plan.D, _ptr(eg), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
+                      plan.n_lin, _ptr(lg), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
+                      _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
+                      _ptr(d_fm), _ptr(d_lin), _stream())
+        else:  # row-wise: (unique ids, summed row grads) per table, returned as sparse COO
+            ws = plan.workspace(B)
+            n_plan = len(plan.plan_cols_host)
+            _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, n_plan, _ptr(plan.plan_cols),
+                      _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]), ws["H"],
+                      _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                      _ptr(plan.err_flag), _stream())
+            rg_emb = torch.empty(max(n_emb, 1), B, max(plan.D, 1), device=dev, dtype=torch.float32)
+            rg_lin = torch.empty(max(plan.n_lin, 1), B, device=dev, dtype=torch.float32)
+            eg = torch.tensor([rg_emb[f].data_ptr() for f in range(n_emb)], **i64) if n_emb else None
+            lg = torch.tensor([rg_lin[f].data_ptr() for f in range(plan.n_lin)], **i64) if plan.n_lin else None
+            _lib.call("ctr_scatter_bwd_rowwise", B, n_plan, _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                      _ptr(ws["n_uniq"]), n_emb, plan.D, _ptr(eg), _ptr(plan.emb_plan_col),
+                      plan.n_lin, _ptr(lg), _ptr(plan.lin_plan_col),
+                      _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
+                      _ptr(d_fm), _ptr(d_lin), _stream())
+            uniq = ws["uniq"].to(torch.int64)
+            emb_pc = plan.emb_plan_col.tolist() if not hasattr(plan, "_emb_pc") else plan._emb_pc
+            lin_pc = plan.lin_plan_col.tolist() if not hasattr(plan, "_lin_pc") else plan._lin_pc
+            plan._emb_pc, plan._lin_pc = emb_pc, lin_pc
+            for f, p in enumerate(plan.emb_params):
+                if not emb_live:
+                    grads_emb.append(None)
+                    continue
+                grads_emb.append(torch.sparse_coo_tensor(uniq[emb_pc[f]].unsqueeze(0), rg_emb[f],
+                                                         size=p.shape, check_invariants=False))
+            for f, p in enumerate(plan.lin_params):
+                grads_lin.append(torch.sparse_coo_tensor(uniq[lin_pc[f]].unsqueeze(0),
+                                                         rg_lin[f].unsqueeze(1), size=p.shape,
+                                                         check_invariants=False))
+        d_ldw = None
+        if ctx.has_ldw:
+            d_ldw = torch.empty(plan.n_lin_dense, 1, device=dev, dtype=torch.float32)
+            _lib.call("ctr_lin_dense_wgrad", _ptr(X), X.stride(0), B, plan.n_lin_dense,
+                      _ptr(plan.lin_dense_cols), _ptr(d_lin), _ptr(d_ldw), _stream())
+        # a table shared by several fields appears several times in `tables`; autograd sums them
+        return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
+
+
+def fused_input(X, plan, lin_dense_w, want_blk=True, want_fm=False, grad_mode="dense"):
+    """(blk [B, ld] | None, lin [B], fm [B] | None) — see ctr_gather_fwd in include/ctr_b200.h."""
+    tables = tuple(plan.emb_params) + tuple(plan.lin_params)
+    blk, lin, fm = _FusedInput.apply(X, plan, lin_dense_w, want_blk, want_fm, grad_mode, *tables)
+    return (blk if want_blk else None), lin, (fm if want_fm else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# FM on an assembled block (generic composition; the fused gather computes FM itself)
+# ----------------------------------------------------------------------------------------------
+class _FM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E):
+        _require_cuda(E, "FM input")
+        B, F, D = E.shape
+        E2 = E.reshape(B, F * D)
+        E2 = _rowmajor(E2)
+        out = torch.empty(B, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_fm_fwd", _ptr(E2), E2.stride(0), B, F, D, _ptr(out), _stream())
+        ctx.save_for_backward(E2)
+        ctx.shape = (B, F, D)
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (E2,) = ctx.saved_tensors
+        B, F, D = ctx.shape
+        dE = torch.zeros(B, F * D, device=E2.device, dtype=torch.float32)
+        gg = g.reshape(B).contiguous()
+        _lib.call("ctr_fm_bwd", _ptr(E2), E2.stride(0), B, F, D, _ptr(gg), _ptr(dE), F * D, _stream())
+        return dE.view(B, F, D)
+
+
+def fm(E):
+    return _FM.apply(E)
+
+
+# ----------------------------------------------------------------------------------------------
+# dense tower
+# ----------------------------------------------------------------------------------------------
+class _DnnLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, bias, act, w_kn):
+        """w_kn: W is stored [K, N] (CrossNetMix factors) instead of nn.Linear's [N, K]."""
+        _require_cuda(x, "DNN input")
+        x = _rowmajor(x)
+        B, K = x.shape
+        Wc = W if W.is_contiguous() else W.contiguous()
+        N = Wc.shape[1] if w_kn else Wc.shape[0]
+        swn, swk = (1, N) if w_kn else (K, 1)
+        y = torch.empty(B, N, device=x.device, dtype=torch.float32)
+        _lib.call("ctr_dnn_layer_fwd", _ptr(x), x.stride(0), _ptr(Wc), swn, swk, _ptr(bias),
+                  _ptr(y), N, B, K, N, act, _stream())
+        ctx.act, ctx.w_kn, ctx.has_bias = act, w_kn, bias is not None
+        ctx.save_for_backward(x, Wc, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wc, y = ctx.saved_tensors
+        B, K = x.shape
+        N = y.shape[1]
+        dy = _rowmajor(dy)
+        swn, swk = (1, N) if ctx.w_kn else (K, 1)
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ldx = _round4(K)
+        dx_full = torch.empty(B, ldx, device=x.device, dtype=torch.float32) if need_dx else None
+        dW = torch.empty_like(Wc) if need_dw else None
+        db = torch.empty(N, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        _lib.call("ctr_dnn_layer_bwd", _ptr(x), x.stride(0), _ptr(Wc), swn, swk, _ptr(y), N,
+                  _ptr(dy), dy.stride(0), _ptr(dx_full), ldx, 0, _ptr(dW), swn, swk, _ptr(db),
+                  B, K, N, ctx.act, _stream())
+        dx = dx_full[:, :K] if need_dx else None
+        return dx, dW, db, None, None
+
+
+def dnn_layer(x, W, bias, act="relu", w_kn=False):
+    return _DnnLayer.apply(x, W, bias, act_code(act) if isinstance(act, str) else int(act), w_kn)
+
+
+class _RowDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, w):
+        _require_cuda(H, "row-dot input")
+        H = _rowmajor(H)
+        B, N = H.shape
+        wv = w.reshape(-1).contiguous()
+        out = torch.empty(B, device=H.device, dtype=torch.float32)
+        _lib.call("ctr_rowdot_fwd", _ptr(H), H.stride(0), _ptr(wv), B, N, _ptr(out), 0, _stream())
+        ctx.save_for_backward(H, wv)
+        ctx.wshape = w.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H, wv = ctx.saved_tensors
+        B, N = H.shape
+        g = g.contiguous()
+        ld = _round4(N)
+        dH = torch.empty(B, ld, device=H.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(N, device=H.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _lib.call("ctr_rowdot_bwd", _ptr(H), H.stride(0), _ptr(wv), _ptr(g), B, N, _ptr(dH), ld, 0,
+                  _ptr(dw), _stream())
+        return (dH[:, :N] if dH is not None else None), (dw.view(ctx.wshape) if dw is not None else None)
+
+
+def rowdot(H, w):
+    """[B] = H[B,N] @ w (the bias-free 1-unit Linear heads)."""
+    return _RowDot.apply(H, w)
+
+
+class _Predict(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bias, binary, *terms):
+        terms = [t.reshape(-1).contiguous() for t in terms]
+        _require_cuda(terms[0], "logit term")
+        B = terms[0].shape[0]
+        y = torch.empty(B, device=terms[0].device, dtype=torch.float32)
+        arr = (ctypes.c_void_p * len(terms))(*[t.data_ptr() for t in terms])
+        _lib.call("ctr_predict_fwd", arr, len(terms), _ptr(bias), B, 1 if binary else 0, None,
+                  _ptr(y), _stream())
+        ctx.binary, ctx.n_terms, ctx.has_bias = binary, len(terms), bias is not None
+        ctx.save_for_backward(y)
+        return y.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        B = y.shape[0]
+        dy = dy.reshape(-1).contiguous()
+        dlogit = torch.empty(B, device=y.device, dtype=torch.float32)
+        dbias = torch.empty(1, device=y.device, dtype=torch.float32) if ctx.has_bias else None
+        _lib.call("ctr_predict_bwd", _ptr(y), _ptr(dy), B, 1 if ctx.binary else 0, _ptr(dlogit),
+                  _ptr(dbias), _stream())
+        return (dbias, None) + (dlogit,) * ctx.n_terms
+
+
+def predict(terms, bias, binary=True):
+    """y[B,1] = sigmoid(sum(terms) + bias) — PredictionLayer (reference layers/core.py:154-160)."""
+    if len(terms) > 8:
+        raise ValueError("at most 8 logit terms")
+    return _Predict.apply(bias, binary, *terms)
+
+
+# ----------------------------------------------------------------------------------------------
+# CIN
+# ----------------------------------------------------------------------------------------------
+class _CIN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, act, split_half, layer_size, *params):
+        """E [B,M,D] (any batch stride); params = (W0, b0, W1, b1, ...) with W [N, H*M, 1]."""
+        _require_cuda(E, "CIN input")
+        B, M, D = E.shape
+        if E.stride(2) != 1 or E.stride(1) != D:
+            E = E.contiguous()
+        dev = E.device
+        n_layers = len(layer_size)
+        plan = []
+        H = M
+        total = 0
+        for k, N in enumerate(layer_size):
+            last = k == n_layers - 1
+            if split_half:
+                n_hidden, dstart = (0, 0) if last else (N // 2, N // 2)
+            else:
+                n_hidden, dstart = N, 0
+            plan.append((H, N, n_hidden, dstart, total))
+            total += N - dstart
+            H = n_hidden
+        out = torch.empty(B, total, device=dev, dtype=torch.float32)
+        Ys = []
+        xp, sxp = E, E.stride(0)
+        for k, (Hk, N, n_hidden, dstart, off) in enumerate(plan):
+            W = params[2 * k].reshape(N, Hk * M)
+            W = W if W.is_contiguous() else W.contiguous()
+            b = params[2 * k + 1]
+            Y = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+            _lib.call("ctr_cin_layer_fwd", _ptr(xp), sxp, Hk, _ptr(E), E.stride(0), M, D, _ptr(W),
+                      _ptr(b), N, dstart, act, _ptr(Y), _vp(out.data_ptr() + 4 * off), total, B,
+                      _stream())
+            Ys.append(Y)
+            xp, sxp = Y, N * D
+        ctx.plan, ctx.act, ctx.dims = plan, act, (B, M, D, total)
+        ctx.save_for_backward(E, *Ys, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, M, D, total = ctx.dims
+        plan = ctx.plan
+        L = len(plan)
+        saved = ctx.saved_tensors
+        E, Ys, params = saved[0], saved[1:1 + L], saved[1 + L:]
+        dev = E.device
+        dout = _rowmajor(dout)
+        dE = torch.zeros(B, M, D, device=dev, dtype=torch.float32)
+        grads = [None] * (2 * L)
+        dYh, sdyh = None, 0
+        for k in range(L - 1, -1, -1):
+            Hk, N, n_hidden, dstart, off = plan[k]
+            W = params[2 * k].reshape(N, Hk * M)
+            W = W if W.is_contiguous() else W.contiguous()
+            first = k == 0
+            xp = E if first else Ys[k - 1]
+            sxp = E.stride(0) if first else plan[k - 1][1] * D
+            dZ = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+            dW = torch.empty(N, Hk * M, device=dev, dtype=torch.float32)
+            db = torch.empty(N, device=dev, dtype=torch.float32)
+            dXp = None if first else torch.empty(B, Hk, D, device=dev, dtype=torch.float32)
+            _lib.call("ctr_cin_layer_bwd", _ptr(xp), sxp, Hk, _ptr(E), E.stride(0), M, D, _ptr(W), N,
+                      n_hidden if k < L - 1 else 0, dstart, ctx.act, _ptr(Ys[k]), _ptr(dYh), sdyh,
+                      _vp(dout.data_ptr() + 4 * off), dout.stride(0), _ptr(dZ), _ptr(dW), _ptr(db),
+                      _ptr(dXp), Hk * D, _ptr(dE), M * D, B, _stream())
+            grads[2 * k] = dW.view(params[2 * k].shape)
+            grads[2 * k + 1] = db
+            dYh, sdyh = dXp, Hk * D
+        return (dE, None, None, None) + tuple(grads)
+
+
+def cin(E, layer_size, split_half, act, params):
+    return _CIN.apply(E, act_code(act), bool(split_half), tuple(int(s) for s in layer_size), *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# CrossNet
+# ----------------------------------------------------------------------------------------------
+class _CrossVector(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernels, bias):
+        _require_cuda(x, "CrossNet input")
+        x = _rowmajor(x)
+        B, n = x.shape
+        L = kernels.shape[0]
+        kv = kernels.reshape(L, n).contiguous()
+        bv = bias.reshape(L, n).contiguous()
+        out = torch.empty(B, n, device=x.device, dtype=torch.float32)
+        s = torch.empty(B, max(L, 1), device=x.device, dtype=torch.float32)
+        _lib.call("ctr_cross_vector_fwd", _ptr(x), x.stride(0), _ptr(kv), _ptr(bv), L, n, _ptr(out), n,
+                  _ptr(s), B, _stream())
+        ctx.save_for_backward(x, kv, bv, s)
+        ctx.shapes = (kernels.shape, bias.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, kv, bv, s = ctx.saved_tensors
+        B, n = x.shape
+        L = kv.shape[0]
+        dout = _rowmajor(dout)
+        ld = _round4(n)
+        dx = torch.empty(B, ld, device=x.device, dtype=torch.float32)
+        dk = torch.empty(L, n, device=x.device, dtype=torch.float32)
+        db = torch.empty(L, n, device=x.device, dtype=torch.float32)
+        _lib.call("ctr_cross_vector_bwd", _ptr(x), x.stride(0), _ptr(kv), _ptr(bv), L, n, _ptr(s),
+                  _ptr(dout), dout.stride(0), _ptr(dx), ld, 0, _ptr(dk), _ptr(db), B, _stream())
+        return dx[:, :n], dk.view(ctx.shapes[0]), db.view(ctx.shapes[1])
+
+
+class _CrossMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernels, bias):
+        _require_cuda(x, "CrossNet input")
+        x = _rowmajor(x)
+        B, n = x.shape
+        L = kernels.shape[0]
+        W = kernels.contiguous()
+        bv = bias.reshape(L, n).contiguous()
+        xs, Us = [x], []
+        for l in range(L):
+            U = torch.empty(B, n, device=x.device, dtype=torch.float32)
+            nxt = torch.empty(B, n, device=x.device, dtype=torch.float32)
+            _lib.call("ctr_cross_matrix_layer_fwd", _ptr(x), x.stride(0), _ptr(xs[-1]), xs[-1].stride(0),
+                      _ptr(W[l]), _ptr(bv[l]), n, _ptr(U), n, _ptr(nxt), n, B, _stream())
+            xs.append(nxt)
+            Us.append(U)
+        ctx.L = L
+        ctx.bshape = bias.shape
+        ctx.save_for_backward(W, *xs[:-1], *Us)
+        return xs[-1] if L > 0 else x.clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = ctx.L
+        saved = ctx.saved_tensors
+        W, xs, Us = saved[0], saved[1:1 + L], saved[1 + L:]
+        x0 = xs[0] if L else None
+        if L == 0:
+            return dout, torch.zeros_like(W), None
+        B, n = x0.shape
+        dev = x0.device
+        g = _rowmajor(dout)
+        dx0 = torch.zeros(B, n, device=dev, dtype=torch.float32)
+        dW = torch.empty(L, n, n, device=dev, dtype=torch.float32)
+        db = torch.empty(L, n, device=dev, dtype=torch.float32)
+        dU = torch.empty(B, n, device=dev, dtype=torch.float32)
+        for l in range(L - 1, -1, -1):
+            gprev = torch.empty(B, n, device=dev, dtype=torch.float32)
+            _lib.call("ctr_cross_matrix_layer_bwd", _ptr(x0), x0.stride(0), _ptr(xs[l]), xs[l].stride(0),
+                      _ptr(W[l]), _ptr(Us[l]), n, _ptr(g), g.stride(0), n, _ptr(dU), n, _ptr(dx0), n,
+                      _ptr(dW[l]), _ptr(db[l]), _ptr(gprev), n, B, _stream())
+            g = gprev
+        dx0 += g                      # x_0 is also the x_l of layer 0
+        return dx0, dW, db.view(ctx.bshape)
+
+
+def crossnet(x, kernels, bias, parameterization="vector"):
+    if parameterization == "vector":
+        return _CrossVector.apply(x, kernels, bias)
+    if parameterization == "matrix":
+        return _CrossMatrix.apply(x, kernels, bias)
+    raise ValueError("parameterization should be 'vector' or 'matrix'")
+
+
+class _CrossMixCombine(torch.autograd.Function):
+    """x_{l+1} = sum_e softmax(gate)_e * x0 (.) (uv_e + bias) + x_l  (one layer)."""
+
+    @staticmethod
+    def forward(ctx, x0, xl, uv, gate, bias):
+        E, B, n = uv.shape
+        x0, xl = _rowmajor(x0), _rowmajor(xl)
+        uv, gate = uv.contiguous(), gate.contiguous()
+        bv = bias.reshape(n).contiguous()
+        out = torch.empty(B, n, device=x0.device, dtype=torch.float32)
+        _lib.call("ctr_cross_mix_fwd", _ptr(x0), x0.stride(0), _ptr(xl), xl.stride(0), _ptr(uv), n,
+                  _ptr(gate), _ptr(bv), E, n, _ptr(out), n, B, _stream())
+        ctx.save_for_backward(x0, uv, gate, bv)
+        ctx.bshape = bias.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, uv, gate, bv = ctx.saved_tensors
+        E, B, n = uv.shape
+        g = _rowmajor(g)
+        duv = torch.empty_like(uv)
+        dgate = torch.empty_like(gate)
+        dx0 = torch.zeros(B, n, device=x0.device, dtype=torch.float32)
+        dbias = torch.empty(n, device=x0.device, dtype=torch.float32)
+        _lib.call("ctr_cross_mix_bwd", _ptr(x0), x0.stride(0), _ptr(uv), n, _ptr(gate), _ptr(bv), _ptr(g),
+                  g.stride(0), E, n, _ptr(duv), _ptr(dgate), _ptr(dx0), n, _ptr(dbias), B, _stream())
+        return dx0, g, duv, dgate, dbias.view(ctx.bshape)
+
+
+def cross_mix_combine(x0, xl, uv, gate, bias):
+    return _CrossMixCombine.apply(x0, xl, uv, gate, bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# FiBiNET pieces
+# ----------------------------------------------------------------------------------------------
+class _SENET(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, W1, W2):
+        _require_cuda(E, "SENET input")
+        B, F, D = E.shape
+        if E.stride(2) != 1 or E.stride(1) != D:
+            E = E.contiguous()
+        W1c, W2c = W1.contiguous(), W2.contiguous()
+        R = W1c.shape[0]
+        V = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_senet_fwd", _ptr(E), E.stride(0), F, D, _ptr(W1c), _ptr(W2c), R, _ptr(V), F * D, B,
+                  _stream())
+        ctx.save_for_backward(E, W1c, W2c)
+        return V
+
+    @staticmethod
+    def backward(ctx, dV):
+        E, W1c, W2c = ctx.saved_tensors
+        B, F, D = E.shape
+        R = W1c.shape[0]
+        dV = dV.contiguous()
+        dE = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        dW1, dW2 = torch.empty_like(W1c), torch.empty_like(W2c)
+        _lib.call("ctr_senet_bwd", _ptr(E), E.stride(0), F, D, _ptr(W1c), _ptr(W2c), R, _ptr(dV), F * D,
+                  _ptr(dE), F * D, 0, _ptr(dW1), _ptr(dW2), B, _stream())
+        return dE, dW1, dW2
+
+
+def senet(E, W1, W2):
+    return _SENET.apply(E, W1, W2)
+
+
+BILINEAR_SEL = {"all": 0, "each": 1, "interaction": 2}
+
+
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, W, wsel):
+        """E [B,F,D]; W [n_w, D, D] stacked weights; returns [B, P, D]."""
+        _require_cuda(E, "bilinear input")
+        B, F, D = E.shape
+        if E.stride(2) != 1 or E.stride(1) != D:
+            E = E.contiguous()
+        Wc = W.contiguous()
+        P = F * (F - 1) // 2
+        out = torch.empty(B, P, D, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_bilinear_fwd", _ptr(E), E.stride(0), F, D, _ptr(Wc), wsel, _ptr(out), P * D, B,
+                  _stream())
+        ctx.wsel = wsel
+        ctx.save_for_backward(E, Wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        E, Wc = ctx.saved_tensors
+        B, F, D = E.shape
+        P = F * (F - 1) // 2
+        dout = dout.contiguous()
+        dE = torch.zeros(B, F, D, device=E.device, dtype=torch.float32)
+        dW = torch.empty_like(Wc)
+        _lib.call("ctr_bilinear_bwd", _ptr(E), E.stride(0), F, D, _ptr(Wc), ctx.wsel, _ptr(dout), P * D,
+                  _ptr(dE), F * D, _ptr(dW), B, _stream())
+        return dE, dW, None
+
+
+def bilinear(E, W, bilinear_type):
+    return _Bilinear.apply(E, W, BILINEAR_SEL[bilinear_type])
+
+
+# ----------------------------------------------------------------------------------------------
+# VarLen pooled lookup and the whole-table L2 term
+# ----------------------------------------------------------------------------------------------
+POOL_MODES = {"sum": 0, "mean": 1, "max": 2}
+
+
+class _VarlenPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, table, col, T, len_col, mode, err_flag):
+        _require_cuda(X, "X")
+        X = _rowmajor(X)
+        B = X.shape[0]
+        V, D = table.shape
+        out = torch.empty(B, D, device=X.device, dtype=torch.float32)
+        _lib.call("ctr_varlen_pool_fwd", _ptr(X), X.stride(0), B, col, T, len_col, _ptr(table), V, D,
+                  mode, _ptr(out), D, _ptr(err_flag), _stream())
+        ctx.args = (col, T, len_col, mode)
+        ctx.save_for_backward(X, table)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        X, table = ctx.saved_tensors
+        col, T, len_col, mode = ctx.args
+        V, D = table.shape
+        dout = dout.contiguous()
+        dtable = torch.zeros_like(table)
+        _lib.call("ctr_varlen_pool_bwd", _ptr(X), X.stride(0), X.shape[0], col, T, len_col, _ptr(table),
+                  V, D, mode, _ptr(dout), D, _ptr(dtable), _stream())
+        return None, dtable, None, None, None, None, None
+
+
+def varlen_pool(X, table, col, maxlen, len_col, combiner, err_flag):
+    if combiner not in POOL_MODES:
+        raise ValueError("parameter mode should in [sum, mean, max]")
+    return _VarlenPool.apply(X, table, int(col), int(maxlen), -1 if len_col is None else int(len_col),
+                             POOL_MODES[combiner], err_flag)
+
+
+class _SumSq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale, *weights):
+        dev = weights[0].device
+        out = torch.zeros(1, device=dev, dtype=torch.float32)
+        for w in weights:
+            _require_cuda(w, "regularised weight")
+            wc = w if w.is_contiguous() else w.contiguous()
+            _lib.call("ctr_sumsq_acc", _ptr(wc), wc.numel(), float(scale), _ptr(out), _stream())
+        ctx.scale = float(scale)
+        ctx.save_for_backward(*weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # d/dw (scale * sum w^2) = 2*scale*w — elementwise scaling of parameters already resident
+        return (None,) + tuple(w * (2.0 * ctx.scale * g) for w in ctx.saved_tensors)
+
+
+def l2_penalty(weights, scale):
+    """scale * sum_w sum(w^2) via the streaming sum-of-squares kernel (basemodel.py:412-428)."""
+    weights = [w for w in weights if w.numel() > 0]
+    if not weights or scale == 0:
+        return None
+    return _SumSq.apply(scale, *weights)

@@ -1,0 +1,260 @@
+/*
+ * ctr_b200.h — C ABI of libctr_b200.so: the B200 (sm_100a) CTR embedding + interaction hot path.
+ *
+ * The reference (shenweichen/DeepCTR-Torch) has NO native/FFI layer: its hot path is Python over
+ * stock torch ops.  Each entry point below therefore cites the reference *Python* code whose
+ * arithmetic it replaces (paths relative to the reference root, v0.2.9).  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add to bind them.
+ *
+ * Conventions
+ *  - every tensor is caller-owned, device-resident, contiguous along its last axis, fp32 unless
+ *    stated; `ld*` = leading dimension in ELEMENTS; `stream` is a cudaStream_t passed as void*.
+ *  - the library never allocates, frees or synchronises; launches are asynchronous on `stream`.
+ *  - return value: 0 = OK, <0 = argument error, >0 = cudaError_t.  `ctr_last_error()` returns a
+ *    thread-local message for the last non-zero return on this thread.
+ *  - ids travel as fp32 inside X (reference models/basemodel.py:242,369) and are decoded by
+ *    truncation exactly like `.long()`.  Out-of-range ids set bit 0 of `*err_flag` (the reference
+ *    raises IndexError on CPU); the row is then read from id 0 so no memory is touched out of bounds.
+ *  - "pointer arrays" (`const float* const*`) are DEVICE arrays of device pointers.
+ */
+#ifndef CTR_B200_H_
+#define CTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         ctr_version(void);            /* ABI version, currently 1 */
+const char* ctr_last_error(void);
+
+/* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
+enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3 };
+
+/* ---- a4+a5+a6+a7: fused multi-slot gather + linear term + FM + dnn_input assembly --------
+ * replaces: BaseModel.input_from_feature_columns  models/basemodel.py:354-380
+ *           Linear.forward                        models/basemodel.py:63-92
+ *           combined_dnn_input                    inputs.py:126-138
+ *           FM.forward                            layers/interaction.py:26-34
+ * blk[b, f*D + d] = emb_tables[f][id(b,f), d]        f < n_emb  (the [B,F,D] embedding block)
+ * blk[b, n_emb*D + k] = X[b, dense_cols[k]]          k < n_dense
+ * lin[b] = sum_f lin_tables[f][id(b,f)] + sum_k X[b, lin_dense_cols[k]] * lin_dense_w[k]
+ * fm[b]  = 0.5 * sum_d ((sum_f E)^2 - sum_f E^2)     (only if fm != NULL)
+ * Any of {blk, lin, fm} may be NULL (branch switched off).  D is the (uniform) embedding dim.
+ */
+int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B,
+                   int n_emb, int D, const float* const* emb_tables, const int32_t* emb_cols,
+                   const int32_t* emb_vocab,
+                   int n_lin, const float* const* lin_tables, const int32_t* lin_cols,
+                   const int32_t* lin_vocab,
+                   int n_dense, const int32_t* dense_cols,
+                   int n_lin_dense, const int32_t* lin_dense_cols, const float* lin_dense_w,
+                   float* blk, int64_t ld_blk, float* lin, float* fm,
+                   int32_t* err_flag, void* stream);
+
+/* FM on an already assembled block (used when pooled VarLen fields were added to it).
+ * replaces FM.forward layers/interaction.py:26-34.  E = blk viewed as [B, F, D], row stride ld. */
+int ctr_fm_fwd(const float* blk, int64_t ld, int64_t B, int F, int D, float* fm, void* stream);
+/* d_blk[b,f,:] += g[b] * (S[b,:] - E[b,f,:])  (accumulates into d_blk) */
+int ctr_fm_bwd(const float* blk, int64_t ld, int64_t B, int F, int D, const float* g,
+               float* d_blk, int64_t ld_d, void* stream);
+
+/* ---- backward of the gather ("embedding_dense_backward" x 52 in the reference) -----------
+ * replaces: autograd of nn.Embedding (aten::embedding_dense_backward) reached from
+ *           models/basemodel.py:261, plus FM backward and the dense part of Linear.
+ * Row gradient of field f for sample b:
+ *     r[b,f,:] = d_blk[b, f*D:(f+1)*D]  (+ g_fm[b] * (S[b,:] - E[b,f,:]) if g_fm != NULL)
+ *     linear:    rl[b,f] = g_lin[b]
+ *
+ * (1) dense-compat mode: atomically accumulate rows into caller-zeroed dense [V,D] / [V,1]
+ *     gradient tables (what the reference's sparse=False nn.Embedding produces).
+ */
+int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B,
+                          int n_emb, int D, float* const* emb_grads, const int32_t* emb_cols,
+                          const int32_t* emb_vocab,
+                          int n_lin, float* const* lin_grads, const int32_t* lin_cols,
+                          const int32_t* lin_vocab,
+                          const float* blk, int64_t ld_blk,
+                          const float* d_blk, int64_t ld_dblk,
+                          const float* g_fm, const float* g_lin, void* stream);
+
+/* (2) row-wise mode (B200-native): per id column a duplicate-free list of touched rows.
+ *   ctr_unique_plan  : for each of n_cols id columns builds, with an open-addressing hash table
+ *                      of H (power of two >= 2B) slots per column,
+ *                        uniq[c*B + u]   = u-th distinct id of column c      (u < n_uniq[c])
+ *                        inv [b*n_cols+c] = u such that uniq[c*B+u] == id(b,c)
+ *                        cnt [c*B + u]   = multiplicity of that id in the batch
+ *                      hash_keys/hash_vals: int32 [n_cols*H] scratch, n_uniq: int32 [n_cols];
+ *                      all three are (re)initialised inside.  Entries u >= n_uniq[c] get
+ *                      uniq = 0, cnt = 0.
+ *   ctr_scatter_bwd_rowwise: emb_rowgrad[f] is a [B, D] buffer, lin_rowgrad[f] a [B] buffer;
+ *                      row u of field f receives the summed gradient of uniq id u of the plan
+ *                      column emb_plan_col[f]; rows u >= n_uniq are zero-filled so that
+ *                      (uniq, rowgrad) is always a valid padded sparse-COO pair of length B.
+ */
+int64_t ctr_unique_plan_hash_slots(int64_t B);
+int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
+                    const int32_t* vocab, int32_t* hash_keys, int32_t* hash_vals, int64_t H,
+                    int32_t* n_uniq, int32_t* uniq, int32_t* inv, int32_t* cnt,
+                    int32_t* err_flag, void* stream);
+int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv, const int32_t* cnt,
+                            const int32_t* n_uniq,
+                            int n_emb, int D, float* const* emb_rowgrad, const int32_t* emb_plan_col,
+                            int n_lin, float* const* lin_rowgrad, const int32_t* lin_plan_col,
+                            const float* blk, int64_t ld_blk,
+                            const float* d_blk, int64_t ld_dblk,
+                            const float* g_fm, const float* g_lin, void* stream);
+
+/* gradient of Linear's dense weight: dw[k] = sum_b g[b] * X[b, cols[k]]   (basemodel.py:88-90) */
+int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n, const int32_t* cols,
+                        const float* g, float* dw, void* stream);
+
+/* ---- a8: DNN tower (reference layers/core.py:120-134: Linear(+bias) -> activation) -------
+ * The weight is addressed as W(n,k) = W[n*swn + k*swk] so that both nn.Linear weights
+ * ([N,K] row-major: swn = K, swk = 1) and the [K,N] factors of CrossNetMix (swn = 1, swk = N)
+ * are consumed in place.  bias may be NULL.
+ * fwd : Y[B,N] = act(X[B,K] @ W^T + bias[N])
+ * bwd : dZ = dY (.) act'(Y)  applied on the fly;
+ *       dX[B,K] (+)= dZ @ W           (dX may be NULL; accumulate_dx != 0 adds into dX)
+ *       dW(n,k)  = sum_b dZ[b,n] X[b,k]  stored at dW[n*sdwn + k*sdwk] (one of them == 1),
+ *       db[N]    = colsum(dZ)          (dW / db may be NULL)
+ */
+int ctr_dnn_layer_fwd(const float* X, int64_t ldx, const float* W, int64_t swn, int64_t swk,
+                      const float* bias, float* Y, int64_t ldy, int64_t B, int K, int N, int act,
+                      void* stream);
+int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, int64_t swn, int64_t swk,
+                      const float* Y, int64_t ldy, const float* dY, int64_t lddy,
+                      float* dX, int64_t lddx, int accumulate_dx,
+                      float* dW, int64_t sdwn, int64_t sdwk, float* db,
+                      int64_t B, int K, int N, int act, void* stream);
+
+/* generic fp32 GEMM used by the layer kernels and exposed for composition:
+ *   C[m,n] (+)= sum_k A[m*sam + k*sak] * Bm[n*sbn + k*sbk]      (any strides, in elements) */
+int ctr_sgemm(int64_t M, int64_t N, int64_t K,
+              const float* A, int64_t sam, int64_t sak,
+              const float* Bm, int64_t sbn, int64_t sbk,
+              float* C, int64_t ldc, int accumulate, void* stream);
+
+/* row-dot head: out[b] (+)= sum_n H[b,n] * w[n]   (the bias-free dnn_linear / cin_linear,
+ * reference models/deepfm.py:59-60,81; xdeepfm.py:73,88; dcn.py:64-65,86)
+ * bwd: dH[b,n] (+)= g[b]*w[n];  dw[n] = sum_b g[b]*H[b,n] */
+int ctr_rowdot_fwd(const float* H, int64_t ldh, const float* w, int64_t B, int N,
+                   float* out, int accumulate, void* stream);
+int ctr_rowdot_bwd(const float* H, int64_t ldh, const float* w, const float* g, int64_t B, int N,
+                   float* dH, int64_t lddh, int accumulate_dh, float* dw, void* stream);
+
+/* ---- a9: PredictionLayer (reference layers/core.py:154-160) ------------------------------
+ * y[b] = sigmoid(sum_t terms[t][b] + bias)  (task_binary) or the plain sum (regression);
+ * logit[b] (optional) receives the pre-sigmoid value.  terms: HOST array of device pointers.
+ * bwd: dlogit[b] = dy[b] * y(1-y) (binary) or dy[b];  dbias[0] = sum_b dlogit[b] */
+int ctr_predict_fwd(const float* const* terms, int n_terms, const float* bias, int64_t B,
+                    int task_binary, float* logit, float* y, void* stream);
+int ctr_predict_bwd(const float* y, const float* dy, int64_t B, int task_binary,
+                    float* dlogit, float* dbias, void* stream);
+
+/* ---- a10: CIN (reference layers/interaction.py:207-248) ----------------------------------
+ * one layer:  Z[b,n,d] = sum_{h,m} W[n, h*M+m] * Xp[b,h,d] * X0[b,m,d] + bias[n];  Y = act(Z)
+ *   Xp: [B,H,D] with batch stride sxp (elements), X0: [B,M,D] with batch stride sx0;
+ *   Y : [B,N,D] contiguous (kept for the backward).  Channels [0, n_hidden) are the next
+ *       layer's Xp (n_hidden is only needed by the backward); channels [direct_start, N) are
+ *       "direct connect":  out[b, n - direct_start] = sum_d Y[b,n,d], written at out + b*ld_out.
+ *       split_half, not last layer: n_hidden = direct_start = N/2; last layer: n_hidden = 0,
+ *       direct_start = 0; split_half=False: n_hidden = N, direct_start = 0.
+ * bwd: dZ[b,n,d] = ([n < n_hidden] dYh[b,n,d] + [n >= direct_start] dout[b, n-direct_start])
+ *                  * act'(Y[b,n,d])            (materialised in the caller's dZ buffer [B,N,D]);
+ *      dW[n,hm] = sum_{b,d} dZ * P ; dbias[n] = sum_{b,d} dZ ;
+ *      dXp[b,h,d] = sum_{n,m} W dZ X0   (written, batch stride sdxp; NULL when Xp == X0: the
+ *                                        first layer, whose Xp gradient is folded into dX0)
+ *      dX0[b,m,d] += sum_{n,h} W dZ Xp  (accumulated, batch stride sdx0)
+ */
+int ctr_cin_layer_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M,
+                      int D, const float* W, const float* bias, int N, int direct_start, int act,
+                      float* Y, float* out, int64_t ld_out, int64_t B, void* stream);
+int ctr_cin_layer_bwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M,
+                      int D, const float* W, int N, int n_hidden, int direct_start, int act,
+                      const float* Y, const float* dYh, int64_t sdyh,
+                      const float* dout, int64_t ld_dout,
+                      float* dZ, float* dW, float* dbias,
+                      float* dXp, int64_t sdxp, float* dX0, int64_t sdx0,
+                      int64_t B, void* stream);
+
+/* ---- a11: CrossNet (reference layers/interaction.py:438-453) ------------------------------
+ * vector: x_{l+1} = x0 * (x_l . w_l) + b_l + x_l, all L layers in one kernel.
+ *   kernels/bias: [L, n] (the reference's [L,n,1] squeezed).  s[b,l] = x_l . w_l is saved.
+ * matrix: x_{l+1} = x0 (.) (x_l W_l^T + b_l) + x_l ; one call per layer; U = x_l W_l^T + b_l saved.
+ */
+int ctr_cross_vector_fwd(const float* x0, int64_t ldx, const float* kernels, const float* bias,
+                         int L, int n, float* out, int64_t ldo, float* s, int64_t B, void* stream);
+int ctr_cross_vector_bwd(const float* x0, int64_t ldx, const float* kernels, const float* bias,
+                         int L, int n, const float* s, const float* dout, int64_t lddo,
+                         float* dx0, int64_t lddx, int accumulate_dx,
+                         float* dkernels, float* dbias, int64_t B, void* stream);
+int ctr_cross_matrix_layer_fwd(const float* x0, int64_t ldx0, const float* xl, int64_t ldxl,
+                               const float* W, const float* bias, int n,
+                               float* U, int64_t ldu, float* xnext, int64_t ldn,
+                               int64_t B, void* stream);
+/* g = d x_{l+1} [B,n] (read), U saved.  Produces dU = g (.) x0 (in dU buffer), dx0 += g (.) U,
+ * dW = dU^T x_l, db = colsum(dU), gprev = g + dU W  (gprev may alias nothing; written) */
+int ctr_cross_matrix_layer_bwd(const float* x0, int64_t ldx0, const float* xl, int64_t ldxl,
+                               const float* W, const float* U, int64_t ldu,
+                               const float* g, int64_t ldg, int n,
+                               float* dU, int64_t lddu, float* dx0, int64_t lddx0,
+                               float* dW, float* db, float* gprev, int64_t ldgp,
+                               int64_t B, void* stream);
+
+/* ---- a12: CrossNetMix helpers (reference layers/interaction.py:499-534) ------------------
+ * The low-rank expert projections are ctr_sgemm / ctr_dnn_layer calls; these two fuse the rest:
+ * mix fwd : x_{l+1}[b,:] = sum_e softmax_e(gate[b,:])_e * x0[b,:] (.) (uv_e[b,:] + bias) + x_l[b,:]
+ *           uv: [E][B,n] stacked (expert stride = B*ldu), gate: [B,E]
+ * mix bwd : given g = d x_{l+1}: d uv_e = p_e * g (.) x0 ; dgate (through softmax) ;
+ *           dx0 += sum_e p_e g (.) (uv_e+bias) ; dbias = colsum(sum_e p_e g (.) x0) ; dxl = g
+ */
+int ctr_cross_mix_fwd(const float* x0, int64_t ldx0, const float* xl, int64_t ldxl,
+                      const float* uv, int64_t ldu, const float* gate, const float* bias,
+                      int E, int n, float* xnext, int64_t ldn, int64_t B, void* stream);
+int ctr_cross_mix_bwd(const float* x0, int64_t ldx0, const float* uv, int64_t ldu,
+                      const float* gate, const float* bias, const float* g, int64_t ldg,
+                      int E, int n, float* duv, float* dgate, float* dx0, int64_t lddx0,
+                      float* dbias, int64_t B, void* stream);
+
+/* ---- a13: SENET (reference layers/interaction.py:93-101) ---------------------------------
+ * Z = mean_d E; A = relu(W2 relu(W1 Z)); V = E * A[:,:,None].  E,V: [B,F,D] batch stride se/sv.
+ * W1: [R,F], W2: [F,R]. */
+int ctr_senet_fwd(const float* E, int64_t se, int F, int D, const float* W1, const float* W2, int R,
+                  float* V, int64_t sv, int64_t B, void* stream);
+int ctr_senet_bwd(const float* E, int64_t se, int F, int D, const float* W1, const float* W2, int R,
+                  const float* dV, int64_t sdv, float* dE, int64_t sde, int accumulate_de,
+                  float* dW1, float* dW2, int64_t B, void* stream);
+
+/* ---- a14: BilinearInteraction (reference layers/interaction.py:140-156) ------------------
+ * out[b,p,:] = (E[b,i_p,:] @ W_{w(p)}^T) (.) E[b,j_p,:]  for pairs p in combinations order.
+ * W: [n_w, D, D]; wsel = 0: all (one W), 1: each (W_i), 2: interaction (W_p).
+ * out: [B, P, D] written at out + b*so (batch stride so, lets two calls fill one DNN input). */
+int ctr_bilinear_fwd(const float* E, int64_t se, int F, int D, const float* W, int wsel,
+                     float* out, int64_t so, int64_t B, void* stream);
+int ctr_bilinear_bwd(const float* E, int64_t se, int F, int D, const float* W, int wsel,
+                     const float* dout, int64_t sdo, float* dE, int64_t sde, float* dW,
+                     int64_t B, void* stream);
+
+/* ---- a16: whole-table L2 term (reference models/basemodel.py:412-428) --------------------
+ * out[0] += scale * sum(w^2) over n elements */
+int ctr_sumsq_acc(const float* w, int64_t n, float scale, float* out, void* stream);
+
+/* ---- VarLenSparseFeat pooled lookup (reference inputs.py:141-155, layers/sequence.py:49-77)
+ * ids X[b, col .. col+T); mask = (id != 0) when len_col < 0, else t < (int)X[b,len_col].
+ * mode 0 sum, 1 mean (divide by count + 1e-8), 2 max (masked positions contribute row - 1e9).
+ * dst[b*ld + d] = pooled (dst points at the field's slot inside blk).
+ * bwd (dense-compat): atomically adds into the caller-zeroed dense gradient table. */
+int ctr_varlen_pool_fwd(const float* X, int64_t ldx, int64_t B, int col, int T, int len_col,
+                        const float* table, int vocab, int D, int mode,
+                        float* dst, int64_t ld, int32_t* err_flag, void* stream);
+int ctr_varlen_pool_bwd(const float* X, int64_t ldx, int64_t B, int col, int T, int len_col,
+                        const float* table, int vocab, int D, int mode,
+                        const float* ddst, int64_t ld, float* dtable, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_B200_H_ */

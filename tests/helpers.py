@@ -43,3 +43,48 @@ def rel_err(a, b):
     if denom == 0.0:
         return float((a - b).abs().max())
     return float((a - b).abs().max()) / denom
+
+
+def build_columns(cols):
+    from deepctr_torch_b200.inputs import DenseFeat, SparseFeat, VarLenSparseFeat
+    out = []
+    for c in cols:
+        if c["type"] == "sparse":
+            out.append(SparseFeat(c["name"], c["vocab"], embedding_dim=c["dim"], embedding_name=c["embedding_name"]))
+        elif c["type"] == "dense":
+            out.append(DenseFeat(c["name"], c["dimension"]))
+        else:
+            sf = SparseFeat(c["name"], c["vocab"], embedding_dim=c["dim"], embedding_name=c["embedding_name"])
+            out.append(VarLenSparseFeat(sf, maxlen=c["maxlen"], combiner=c["combiner"], length_name=c["length_name"]))
+    return out
+
+
+def build_model(cfg, device="cpu", **extra):
+    """Instantiate the deepctr_torch_b200 model described by an oracle cfg dict."""
+    from deepctr_torch_b200 import models
+    cls = getattr(models, cfg["model"])
+    kw = dict(cfg["kwargs"])
+    for k in ("dnn_hidden_units", "cin_layer_size"):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    kw.update(extra)
+    return cls(build_columns(cfg["linear_columns"]), build_columns(cfg["dnn_columns"]), device=device, **kw)
+
+
+def capture_logit(model, X):
+    """Run model(X) and also return the pre-sigmoid logit (recomputed from y for binary tasks is
+    ill-conditioned, so hook the prediction op's inputs instead)."""
+    from deepctr_torch_b200 import ops
+    captured = {}
+    orig = ops.predict
+
+    def spy(terms, bias, binary=True):
+        captured["logit"] = sum(t.detach().reshape(-1) for t in terms) + (bias.detach() if bias is not None else 0)
+        return orig(terms, bias, binary)
+
+    ops.predict = spy
+    try:
+        y = model(X)
+    finally:
+        ops.predict = orig
+    return y, captured["logit"].reshape(-1, 1)
