@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — CTR samples/sec, forward+backward, batch 65 536 per GPU (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload deepfm|xdeepfm|fibinet|dcn]
+    python bench.py --impl reference ...        # the reference algorithm on the host cores (oracle port)
+
+A step = one pass of the hot path over one synthetic Criteo-shaped batch:
+X[B,39] -> fused gather (+linear, FM) -> interaction + tower -> sigmoid -> BCE(sum) -> backward down
+to per-unique-row table gradients.  No optimizer step (the metric is fwd+bwd), l2 = 0 on both arms.
+
+Printed JSON (one line, rank 0): see the task contract — `value` (device-resident inputs, CUDA
+events), `e2e` (pinned host X/y copied in, loss read back, every step), `roofline` of the dominant
+kernel (CUDA events around its C-ABI entry point in a separate instrumented pass), `cpu_baseline`
+(the oracle port timed on this box's host cores, bounded sample), `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+B_PER_GPU = 65536
+N_ROTATE = 8          # distinct pre-generated batches: 8 x 109 MB of gathered rows cannot sit in L2
+
+WORKLOADS = {
+    # BASELINE.json configs[1..3] + the DCN model the north star names
+    "deepfm": dict(model="DeepFM", D=16, B=65536, kw=dict(dnn_hidden_units=[256, 128]),
+                   desc="DeepFM 26 sparse x 1M x 16 + 13 dense, DNN (256,128), batch 65536"),
+    "xdeepfm": dict(model="xDeepFM", D=16, B=65536,
+                    kw=dict(dnn_hidden_units=[256, 256], cin_layer_size=[128, 128], cin_split_half=True),
+                    desc="xDeepFM CIN (128,128) split_half, DNN (256,256), batch 65536"),
+    "fibinet": dict(model="FiBiNET", D=32, B=32768, kw=dict(bilinear_type="interaction", dnn_hidden_units=[128, 128]),
+                    desc="FiBiNET bilinear interaction, 26 sparse dim 32, DNN (128,128), batch 32768"),
+    "dcn": dict(model="DCN", D=16, B=65536, kw=dict(cross_num=2, cross_parameterization="vector",
+                                                    dnn_hidden_units=[128, 128], l2_reg_cross=0),
+                desc="DCN vector x2, DNN (128,128), batch 65536"),
+}
+
+
+def make_cfg(workload, vocab=1000000):
+    from oracle import ctr_oracle as O
+    w = WORKLOADS[workload]
+    cols = [O.sparse_col("C%d" % (i + 1), vocab, w["D"]) for i in range(26)] + \
+           [O.dense_col("I%d" % (i + 1)) for i in range(13)]
+    return O.make_cfg(w["model"], cols, cols, init_std=0.05, l2_reg_linear=0, l2_reg_embedding=0, **w["kw"])
+
+
+def algorithmic_bytes_per_sample(D, F=26, C=39):
+    """each input read once, each output/grad written once:
+    4*(C_X + 2*F*(D+1) + 2) bytes per sample (3700 B at D=16)."""
+    return 4 * (C + 2 * F * (D + 1) + 2)
+
+
+def tensor_flops_per_sample(cfg):
+    kw = cfg["kwargs"]
+    D = cfg["dnn_columns"][0]["dim"]
+    F = 26
+    in_dim = F * D + 13
+    fl = 0
+    hidden = list(kw.get("dnn_hidden_units", []))
+    if cfg["model"] == "FiBiNET":
+        in_dim = F * (F - 1) * D + 13
+        fl += 2 * 325 * (2 * D * D)
+    prev = in_dim
+    for h in hidden:
+        fl += 2 * prev * h
+        prev = h
+    fl += 2 * prev
+    if cfg["model"] == "xDeepFM":
+        H = F
+        sizes = kw["cin_layer_size"]
+        for i, n in enumerate(sizes):
+            fl += 2 * D * n * H * F
+            H = n // 2 if (kw.get("cin_split_half", True) and i != len(sizes) - 1) else n
+    if cfg["model"] == "DCN":
+        fl += 2 * (F * D + 13) * 2 * kw.get("cross_num", 2)
+    return 3 * fl          # backward = 2x forward
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_fwd_bwd_throughput(cfg, state, batch, steps, warmup, seed=2026):
+    """fwd + BCE(sum) + bwd of the oracle restatement, torch CPU fp32, all host threads.
+    Same loop as the GPU arm; dense table grads like the reference."""
+    from oracle import ctr_oracle as O
+    X, y = O.synthetic_batch(cfg, batch, seed=seed)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in state.items()}
+    times = []
+    for it in range(warmup + steps):
+        for v in leaves.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        logit = O.model_logit(cfg, leaves, X)
+        loss = torch.nn.functional.binary_cross_entropy(torch.sigmoid(logit).squeeze(-1), y, reduction="sum")
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times)
+
+
+def random_state_cpu(cfg, seed=7):
+    """Random-init weights of the architecture (fp32), generated table by table on the CPU."""
+    from helpers import build_model
+    g = torch.Generator().manual_seed(seed)
+    m = build_model(cfg, "cpu")
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    return {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = make_cfg(args.workload)
+    B = min(WORKLOADS[args.workload]["B"], args.cpu_batch) if args.cpu_batch else WORKLOADS[args.workload]["B"]
+    state = random_state_cpu(cfg)
+    steps = max(1, min(args.steps, 4))
+    warm = 1
+    sps, sec = cpu_fwd_bwd_throughput(cfg, state, B, steps, warm)
+    cores = torch.get_num_threads()
+    sample = "%d fwd+bwd steps of batch %d (oracle port of the reference, torch CPU fp32, %d threads of %d cores)" % (
+        steps, B, cores, os.cpu_count())
+    line = {"impl": "reference", "metric": "CTR samples/sec fwd+bwd", "value": sps, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "batch": B},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from deepctr_torch_b200 import _lib
+    from helpers import build_model
+    from oracle import ctr_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    w = WORKLOADS[args.workload]
+    B = w["B"]
+    cfg = make_cfg(args.workload)
+    if world > 1:
+        from deepctr_torch_b200 import sharded
+        model, parallelism = sharded.build_sharded(cfg, dev, rank, world)
+    else:
+        model = build_model(cfg, dev, table_grad="rowwise")
+        parallelism = "single"
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape, generator=gen, device=dev) * 0.05)
+    model.train()
+
+    host_batches = []
+    for i in range(N_ROTATE):
+        X, y = O.synthetic_batch(cfg, B, seed=2026 + 100 * rank + i)
+        host_batches.append((X.pin_memory(), y.pin_memory()))
+    dev_batches = [(X.to(dev), y.to(dev)) for X, y in host_batches]
+    bce = torch.nn.functional.binary_cross_entropy
+
+    def step_resident(i):
+        X, y = dev_batches[i % N_ROTATE]
+        model.zero_grad(set_to_none=True)
+        y_pred = model(X)
+        loss = bce(y_pred.squeeze(1), y, reduction="sum")
+        loss.backward()
+        return loss
+
+    def step_e2e(i):
+        Xh, yh = host_batches[i % N_ROTATE]
+        X = Xh.to(dev, non_blocking=True)
+        y = yh.to(dev, non_blocking=True)
+        model.zero_grad(set_to_none=True)
+        y_pred = model(X)
+        loss = bce(y_pred.squeeze(1), y, reduction="sum")
+        loss.backward()
+        return float(loss.item())          # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e1.record()
+        barrier()
+        timed.launches = _lib.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    launches = timed.launches
+    model.check_ids()
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    # instrumented pass: CUDA events around every C-ABI entry point -> dominant kernel + roofline
+    _lib.enable_timing(True)
+    for i in range(args.steps):
+        step_resident(i)
+    summary = _lib.timing_summary()
+    _lib.enable_timing(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_B = B * world
+    value = total_B * args.steps / (ms * 1e-3)
+    e2e_value = total_B * args.steps / (ms_e2e * 1e-3)
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    per_entry = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in summary.items()}
+    dom = max(per_entry.items(), key=lambda kv: kv[1]["ms_per_step"])
+    D = w["D"]
+    # boundary bytes of the two HBM-bound entry points per sample
+    blk_w = 26 * D + 13
+    ld = (blk_w + 3) // 4 * 4
+    gather_bytes = 4 * (39 + 26 * D + 26 + blk_w + 2)                 # X row + rows + linear w + blk + lin/fm
+    scatter_bytes = 4 * (2 * ld + 26 * 2 + 26 * D + 26 + 2)             # d_blk + blk + inv/cnt + row grads out
+    hbm_entries = {"ctr_gather_fwd": gather_bytes, "ctr_scatter_bwd_rowwise": scatter_bytes}
+    roofs = {}
+    for name, bps in hbm_entries.items():
+        if name in per_entry and per_entry[name]["ms_per_step"] > 0:
+            t = per_entry[name]["ms_per_step"] / max(per_entry[name]["calls_per_step"], 1) * 1e-3
+            gbs = bps * B / t / 1e9
+            roofs[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": gbs / hbm_peak, "bytes_per_sample": bps, "ms": t * 1e3}
+    fl = tensor_flops_per_sample(cfg)
+    a_bytes = algorithmic_bytes_per_sample(D)
+    step_s = ms * 1e-3 / args.steps
+    t_roof_hbm = a_bytes * B / (hbm_peak * 1e9)
+    if dom[0] in roofs:
+        roofline = dict(roofs[dom[0]], kernel=dom[0], traffic=None)
+    else:
+        # dominant entry point is a dense contraction: FLOPs of the whole tower / its time, against
+        # the measured dense bf16 tensor peak (the fp32-grade parity mode runs on FP32 FFMA)
+        t = dom[1]["ms_per_step"] * 1e-3
+        tf = fl * B / 3.0 / t / 1e12 if t > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
+                    "kernel": dom[0], "traffic": None,
+                    "note": "fp32 FFMA parity mode; flops = forward share of the tower attributed to this entry point"}
+    roofline["peak_source"] = peak_src
+    roofline["hbm_kernels"] = roofs
+    roofline["step_vs_hbm_roofline"] = t_roof_hbm / step_s
+
+    line = {
+        "metric": "CTR samples/sec fwd+bwd", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": total_B, "vocab_per_table": 1000000,
+                   "parallelism": parallelism, "table_grad": "rowwise (per-unique-row, SURVEY §8d)",
+                   "l2": 0, "l2_flush": "8 rotating batches, 109 MB of gathered rows each (> L2 with tables)",
+                   "algorithmic_bytes_per_sample": a_bytes, "tensor_flops_per_sample": fl,
+                   "tower_precision": "fp32 FFMA (parity mode)"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(B * 39 * 4 + B * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks, "roofline": roofline, "per_entry_ms": per_entry,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        cb = args.cpu_batch or B
+        sps, sec = cpu_fwd_bwd_throughput(cfg, state, cb, 2, 1)
+        line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "2 fwd+bwd steps of batch %d after 1 warm-up (oracle port, torch CPU fp32, "
+                                          "%d threads; os.cpu_count()=%d)" % (cb, torch.get_num_threads(), os.cpu_count())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="deepfm", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU arm (0 = the workload's batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU path); use --impl reference")
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,7 @@ SPECIAL = {
     "ctr_version": ([], c_int),
     "ctr_last_error": ([], ctypes.c_char_p),
     "ctr_unique_plan_hash_slots": ([c_i64], c_i64),
+    "ctr_launch_count": ([], c_i64),
 }
 
 
@@ -106,10 +107,38 @@ def load():
     return _lib
 
 
+_timing = None   # None, or {entry point: [(start_event, end_event), ...]} while profiling
+
+
+def enable_timing(on=True):
+    """Bracket every entry-point call with CUDA events on the current stream (bench/profiling)."""
+    global _timing
+    _timing = {} if on else None
+
+
+def timing_summary():
+    """{entry point: (calls, total_ms)} — synchronises."""
+    import torch
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (_timing or {}).items()}
+
+
+def launch_count():
+    return int(load().ctr_launch_count())
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; non-zero return -> CtrLibraryError(message)."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timing is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        _timing.setdefault(name, []).append((a, b))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.ctr_last_error()
         raise CtrLibraryError("%s returned %d: %s" % (name, rc, msg.decode() if msg else "?"))

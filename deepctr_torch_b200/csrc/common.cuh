@@ -26,8 +26,11 @@ int  ctr_sm_count();
         }                                                                           \
     } while (0)
 
+void ctr_count_launch();
+
 #define CTR_LAUNCH_OK(name)                                                         \
     do {                                                                            \
+        ctr_count_launch();                                                         \
         cudaError_t _e = cudaGetLastError();                                        \
         if (_e != cudaSuccess) {                                                    \
             ctr_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e)); \

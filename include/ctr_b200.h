@@ -29,6 +29,7 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------------- */
 int         ctr_version(void);            /* ABI version, currently 1 */
 const char* ctr_last_error(void);
+int64_t     ctr_launch_count(void);       /* kernels launched by this library so far (process-wide) */
 
 /* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
 enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3 };
