@@ -45,21 +45,27 @@ struct GatherArgs {
     float* lin;
     float* fm;
     int32_t* err_flag;
+    int n_shards;   // tables row-sharded: pointer [f*n_shards + id % n_shards], row id / n_shards
 };
 
 // ---------------------------------------------------------------------------------------------
 // forward, vector path: D % 4 == 0 and D/4 a power of two <= 32
 // ---------------------------------------------------------------------------------------------
+// Memory-level parallelism is what bounds this kernel: per sample the chain is X row -> ids ->
+// rows.  The ids of the NEXT sample of the warp are prefetched while the current sample's rows are
+// in flight, and the (up to) four row loads of a lane are all issued before the first store.
 template <int LPR>
 __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     constexpr int RPW = 32 / LPR;  // rows per warp step
+    constexpr int STEPS = 4;       // row loads in flight per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // stage slot metadata (table pointer, column, vocab) in shared memory
+    // stage slot metadata (table pointers, column, vocab) in shared memory
     const float** s_tab = reinterpret_cast<const float**>(smem_raw);
-    int32_t* s_col = reinterpret_cast<int32_t*>(s_tab + a.n_emb);
+    const int G = a.n_shards;
+    int32_t* s_col = reinterpret_cast<int32_t*>(s_tab + a.n_emb * G);
     int32_t* s_voc = s_col + a.n_emb;
+    for (int i = threadIdx.x; i < a.n_emb * G; i += blockDim.x) s_tab[i] = a.emb_tables[i];
     for (int i = threadIdx.x; i < a.n_emb; i += blockDim.x) {
-        s_tab[i] = a.emb_tables[i];
         s_col[i] = a.emb_cols[i];
         s_voc[i] = a.emb_vocab[i];
     }
@@ -71,20 +77,57 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     const int D = a.D;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool one_chunk = a.n_emb <= STEPS * RPW;
+    const int lin_col = (lane < a.n_lin) ? a.lin_cols[lane] : 0;
+    const bool lin_fast = a.n_lin <= 32;
+
+    float xv[STEPS];   // raw X values (ids) of this lane's fields for the current sample
+    float xl = 0.f;    // raw X value of this lane's linear field
+    auto prefetch_x = [&](int64_t b, float (&x)[STEPS], float& l) {
+        if (b < a.B) {
+            const float* xrow = a.X + b * a.ldx;
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int f = s * RPW + rslot;
+                x[s] = (f < a.n_emb) ? __ldg(xrow + s_col[f]) : 0.f;
+            }
+            l = (lin_fast && lane < a.n_lin) ? __ldg(xrow + lin_col) : 0.f;
+        }
+    };
+    prefetch_x(warp0, xv, xl);
 
     for (int64_t b = warp0; b < a.B; b += nwarps) {
         const float* xrow = a.X + b * a.ldx;
+        float xn[STEPS];
+        float xln = 0.f;
+        prefetch_x(b + nwarps, xn, xln);
+
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
         float q = 0.f;
-        for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
-            const int f = f0 + rslot;
-            if (f < a.n_emb) {
-                const int64_t id = decode_id(__ldg(xrow + s_col[f]), s_voc[f], a.err_flag);
-                const float4 v = ld_stream4(s_tab[f] + id * D + sub * 4);
-                if (a.blk) st_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4, v);
-                S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
-                q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
+            float4 v[STEPS];
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int f = f0 + s * RPW + rslot;
+                v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f < a.n_emb) {
+                    const float raw = (f0 == 0) ? xv[s] : __ldg(xrow + s_col[f]);
+                    const int64_t id = decode_id(raw, s_voc[f], a.err_flag);
+                    const float* tab = (G == 1) ? s_tab[f] : s_tab[f * G + (int)(id % G)];
+                    const int64_t row = (G == 1) ? id : id / G;
+                    v[s] = ld_stream4(tab + row * D + sub * 4);
+                }
             }
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int f = f0 + s * RPW + rslot;
+                if (f < a.n_emb) {
+                    if (a.blk) st_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4, v[s]);
+                    S.x += v[s].x; S.y += v[s].y; S.z += v[s].z; S.w += v[s].w;
+                    q += v[s].x * v[s].x + v[s].y * v[s].y + v[s].z * v[s].z + v[s].w * v[s].w;
+                }
+            }
+            if (one_chunk) break;
         }
         float fmv = 0.f;
         if (a.fm) {
@@ -104,9 +147,17 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
         }
         // linear term: sparse weights + dense dot; dense copy into the block
         float lp = 0.f;
-        for (int f = lane; f < a.n_lin; f += 32) {
-            const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
-            lp += __ldg(a.lin_tables[f] + id);
+        if (lin_fast) {
+            if (lane < a.n_lin) {
+                const int64_t id = decode_id(xl, a.lin_vocab[lane], a.err_flag);
+                lp = (G == 1) ? __ldg(a.lin_tables[lane] + id)
+                              : __ldg(a.lin_tables[lane * G + (int)(id % G)] + id / G);
+            }
+        } else {
+            for (int f = lane; f < a.n_lin; f += 32) {
+                const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+                lp += (G == 1) ? __ldg(a.lin_tables[f] + id) : __ldg(a.lin_tables[f * G + (int)(id % G)] + id / G);
+            }
         }
         for (int k = lane; k < a.n_lin_dense; k += 32)
             lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
@@ -119,13 +170,18 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
             if (lane == 0) a.lin[b] = lp;
         }
         if (a.fm && lane == 0) a.fm[b] = fmv;
+#pragma unroll
+        for (int s = 0; s < STEPS; ++s) xv[s] = xn[s];
+        xl = xln;
     }
 }
+
 
 // forward, generic path: any D (scalar loads); FM is computed by fm_fwd_kernel afterwards
 __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
     const int lane = threadIdx.x & 31;
     const int D = a.D;
+    const int G = a.n_shards;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t b = warp0; b < a.B; b += nwarps) {
@@ -135,7 +191,7 @@ __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
             for (int i = lane; i < total; i += 32) {
                 const int f = i / D, d = i - f * D;
                 const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], a.err_flag);
-                a.blk[b * a.ld_blk + i] = __ldg(a.emb_tables[f] + id * D + d);
+                a.blk[b * a.ld_blk + i] = __ldg(a.emb_tables[f * G + (int)(id % G)] + (id / G) * D + d);
             }
             float* drow = a.blk + b * a.ld_blk + (int64_t)total;
             for (int k = lane; k < a.n_dense; k += 32) drow[k] = __ldg(xrow + a.dense_cols[k]);
@@ -143,7 +199,7 @@ __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
         float lp = 0.f;
         for (int f = lane; f < a.n_lin; f += 32) {
             const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
-            lp += __ldg(a.lin_tables[f] + id);
+            lp += __ldg(a.lin_tables[f * G + (int)(id % G)] + id / G);
         }
         for (int k = lane; k < a.n_lin_dense; k += 32)
             lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
@@ -223,31 +279,41 @@ struct ScatterArgs {
     const int32_t* cnt;
 };
 
-// One warp per sample.  Pass 1 recomputes S = sum_f E (only when the FM branch is live), pass 2
-// forms r[b,f,:] = d_blk + g_fm (S - E) and adds it to its destination row: dense mode ->
-// red.global.add.v4.f32 into [V,D]; rowwise mode -> plain store when the id is unique in the
-// batch (cnt == 1), vector reduction otherwise.
+// One warp per sample.  r[b,f,:] = d_blk + g_fm (S - E) is added to its destination row: dense
+// mode -> red.global.add.v4.f32 into [V,D]; rowwise mode -> plain 128-bit store when the id is
+// unique in the batch (cnt == 1), vector reduction otherwise.  All loads of a lane (up to four
+// d_blk rows, four blk rows, the inv/cnt lookups) are issued before the first store.
 template <int LPR, bool ROWWISE>
 __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
     constexpr int RPW = 32 / LPR;
+    constexpr int STEPS = 4;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rslot = lane / LPR;
     const int D = a.D;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool one_chunk = a.n_emb <= STEPS * RPW;
 
     for (int64_t b = warp0; b < a.B; b += nwarps) {
         const float* xrow = a.X ? a.X + b * a.ldx : nullptr;
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
         float gfm = 0.f;
+        float4 e0[STEPS];          // blk rows of the first chunk (kept for pass 2)
         if (a.g_fm) {
             gfm = __ldg(a.g_fm + b);
-            for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
-                const int f = f0 + rslot;
-                if (f < a.n_emb) {
-                    const float4 v = ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
-                    S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+            for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
+                float4 v[STEPS];
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    v[s] = (f < a.n_emb) ? ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    S.x += v[s].x; S.y += v[s].y; S.z += v[s].z; S.w += v[s].w;
+                    if (f0 == 0) e0[s] = v[s];
                 }
             }
 #pragma unroll
@@ -258,30 +324,51 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
                 S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
             }
         }
-        for (int f0 = 0; f0 < a.n_emb; f0 += RPW) {
-            const int f = f0 + rslot;
-            if (f < a.n_emb) {
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.d_blk) r = ld_stream4(a.d_blk + b * a.ld_dblk + (int64_t)f * D + sub * 4);
-                if (a.g_fm) {
-                    const float4 v = ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
-                    r.x += gfm * (S.x - v.x);
-                    r.y += gfm * (S.y - v.y);
-                    r.z += gfm * (S.z - v.z);
-                    r.w += gfm * (S.w - v.w);
-                }
-                if (ROWWISE) {
-                    const int pc = a.emb_cols[f];
-                    const int u = __ldg(a.inv + b * a.n_plan + pc);
-                    const int c = __ldg(a.cnt + (int64_t)pc * a.B + u);
-                    float* dst = a.emb_out[f] + (int64_t)u * D + sub * 4;
-                    if (c == 1) st_stream4(dst, r);
-                    else red_add4(dst, r);
-                } else {
-                    const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], nullptr);
-                    red_add4(a.emb_out[f] + id * D + sub * 4, r);
+        for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
+            float4 r[STEPS];
+            int u[STEPS];
+            int c[STEPS];
+            int64_t id[STEPS];
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int f = f0 + s * RPW + rslot;
+                r[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                u[s] = 0; c[s] = 0; id[s] = 0;
+                if (f < a.n_emb) {
+                    if (a.d_blk) r[s] = ld_stream4(a.d_blk + b * a.ld_dblk + (int64_t)f * D + sub * 4);
+                    if (ROWWISE) u[s] = __ldg(a.inv + b * a.n_plan + a.emb_cols[f]);
+                    else id[s] = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], nullptr);
                 }
             }
+            if (ROWWISE) {
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    if (f < a.n_emb) c[s] = __ldg(a.cnt + (int64_t)a.emb_cols[f] * a.B + u[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < STEPS; ++s) {
+                const int f = f0 + s * RPW + rslot;
+                if (f < a.n_emb) {
+                    if (a.g_fm) {
+                        const float4 v = (f0 == 0) ? e0[s]
+                                                   : ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
+                        r[s].x += gfm * (S.x - v.x);
+                        r[s].y += gfm * (S.y - v.y);
+                        r[s].z += gfm * (S.z - v.z);
+                        r[s].w += gfm * (S.w - v.w);
+                    }
+                    if (ROWWISE) {
+                        float* dst = a.emb_out[f] + (int64_t)u[s] * D + sub * 4;
+                        if (c[s] == 1) st_stream4(dst, r[s]);
+                        else red_add4(dst, r[s]);
+                    } else {
+                        red_add4(a.emb_out[f] + id[s] * D + sub * 4, r[s]);
+                    }
+                }
+            }
+            if (one_chunk) break;
         }
         if (a.g_lin) {
             const float gl = __ldg(a.g_lin + b);
@@ -389,6 +476,9 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     return x;
 }
 
+// Thread mapping is column-major (i = c*B + b): the lanes of a warp work on the same id column, so
+// the "next unique index" counter of that column is bumped once per warp (ballot-aggregated)
+// instead of once per inserted key.
 __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restrict__ X, int64_t ldx,
                                                           int64_t B, int n_cols,
                                                           const int32_t* __restrict__ cols,
@@ -398,29 +488,50 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
                                                           int32_t* inv, int32_t* err_flag) {
     const int64_t total = B * n_cols;
     const uint32_t mask = (uint32_t)(H - 1);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % n_cols);
-        const int64_t b = i / n_cols;
-        const int32_t key = (int32_t)decode_id(__ldg(X + b * ldx + cols[c]), vocab[c], err_flag);
-        int32_t* kc = keys + (int64_t)c * H;
-        uint32_t slot = mix32((uint32_t)key) & mask;
-        while (true) {
-            int32_t k = __ldcg(kc + slot);
-            if (k == -1) {
-                const int32_t old = atomicCAS(kc + slot, -1, key);
-                if (old == -1) {  // this thread inserted the key: hand out the next unique index
-                    const int32_t u = atomicAdd(n_uniq + c, 1);
-                    vals[(int64_t)c * H + slot] = u;
-                    uniq[(int64_t)c * B + u] = key;
-                    break;
+    const int lane = threadIdx.x & 31;
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
+    for (int64_t base = first; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        const bool valid = i < total;
+        int c = 0;
+        int64_t b = 0;
+        bool won = false;
+        uint32_t slot = 0;
+        int32_t key = 0;
+        if (valid) {
+            c = (int)(i / B);
+            b = i - (int64_t)c * B;
+            key = (int32_t)decode_id(__ldg(X + b * ldx + cols[c]), vocab[c], err_flag);
+            int32_t* kc = keys + (int64_t)c * H;
+            slot = mix32((uint32_t)key) & mask;
+            while (true) {
+                int32_t k = __ldcg(kc + slot);
+                if (k == -1) {
+                    const int32_t old = atomicCAS(kc + slot, -1, key);
+                    if (old == -1) {
+                        won = true;
+                        break;
+                    }
+                    k = old;
                 }
-                k = old;
+                if (k == key) break;
+                slot = (slot + 1) & mask;
             }
-            if (k == key) break;
-            slot = (slot + 1) & mask;
+            inv[b * n_cols + c] = (int32_t)slot;  // replaced by the unique index in plan_finalize_kernel
         }
-        inv[i] = (int32_t)slot;  // replaced by the unique index in plan_finalize_kernel
+        __syncwarp();
+        // lanes that inserted a key of the same column share one atomicAdd
+        const unsigned winners = __ballot_sync(0xffffffffu, won);
+        if (won) {
+            const unsigned peers = __match_any_sync(winners, c) ;
+            const int leader = __ffs(peers) - 1;
+            int32_t base_u = 0;
+            if (lane == leader) base_u = atomicAdd(n_uniq + c, __popc(peers));
+            base_u = __shfl_sync(peers, base_u, leader);
+            const int32_t u = base_u + __popc(peers & ((1u << lane) - 1u));
+            vals[(int64_t)c * H + slot] = u;
+            uniq[(int64_t)c * B + u] = key;
+        }
     }
 }
 
@@ -431,7 +542,7 @@ __global__ void __launch_bounds__(256) plan_finalize_kernel(int64_t B, int n_col
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % n_cols);
-        const int32_t u = vals[(int64_t)c * H + inv[i]];
+        const int32_t u = __ldcg(vals + (int64_t)c * H + inv[i]);
         inv[i] = u;
         atomicAdd(cnt + (int64_t)c * B + u, 1);
     }
@@ -488,8 +599,9 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
                               const int32_t* dense_cols, int n_lin_dense,
                               const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
                               int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
-                              void* stream) {
+                              int n_shards, void* stream) {
     CTR_ARG(X && B >= 0 && ldx >= 0, "ctr_gather_fwd: X/B/ldx invalid");
+    CTR_ARG(n_shards >= 1, "ctr_gather_fwd: n_shards must be >= 1");
     CTR_ARG(n_emb >= 0 && n_lin >= 0 && n_dense >= 0 && n_lin_dense >= 0, "ctr_gather_fwd: negative count");
     CTR_ARG(n_emb == 0 || (D > 0 && emb_tables && emb_cols && emb_vocab), "ctr_gather_fwd: embedding slot arrays missing");
     CTR_ARG(n_lin == 0 || (lin_tables && lin_cols && lin_vocab), "ctr_gather_fwd: linear slot arrays missing");
@@ -499,14 +611,14 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
     if (B == 0) return 0;
     GatherArgs a{X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols,
                  lin_vocab, n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk,
-                 lin, fm, err_flag};
+                 lin, fm, err_flag, n_shards};
     cudaStream_t st = as_stream(stream);
     const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
-    const bool vec_ok = lpr > 0 && n_emb <= kMaxSmemSlots &&
+    const bool vec_ok = lpr > 0 && n_emb * n_shards <= kMaxSmemSlots &&
                         (!blk || ((ld_blk % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk) & 15) == 0)));
     const unsigned grid = sample_grid(B, 8, 8);
     if (vec_ok) {
-        const size_t smem = (size_t)n_emb * (sizeof(void*) + 8);
+        const size_t smem = (size_t)n_emb * n_shards * sizeof(void*) + (size_t)n_emb * 8;
         switch (lpr) {
             case 1: gather_fwd_vec_kernel<1><<<grid, 256, smem, st>>>(a); break;
             case 2: gather_fwd_vec_kernel<2><<<grid, 256, smem, st>>>(a); break;

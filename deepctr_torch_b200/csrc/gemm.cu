@@ -7,6 +7,8 @@
 // conflict-free 128-bit load), double-buffered through registers; operands with any element
 // strides, optional activation-gradient prologue on A and fused bias/activation/mask epilogues;
 // split-K with fp32 atomics for the weight-gradient shapes (M,N small, K = batch).
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace {
@@ -262,6 +264,16 @@ __global__ void __launch_bounds__(256) predict_bwd_kernel(const float* __restric
 
 }  // namespace
 
+// CTR_GEMM=simt | tc forces one engine (tests, A/B profiling); default: tensor cores (3xTF32
+// split, gemm_tc.cu) for everything but tiny problems, FP32 FFMA tiles below that.
+static int gemm_engine(const GemmArgs& g) {
+    const char* e = getenv("CTR_GEMM");
+    if (e && e[0] == 's') return 0;
+    if (e && e[0] == 't') return 1;
+    const double macs = (double)g.M * (double)g.N * (double)g.K;
+    return macs >= 2097152.0 ? 1 : 0;
+}
+
 int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return 0;
     if (g.K <= 0) {
@@ -270,6 +282,7 @@ int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
             CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
         return 0;
     }
+    if (gemm_engine(g) == 1) return launch_gemm_tc(g, st);
     const bool big = (g.M >= 128 && g.N >= 96) || (g.N >= 128 && g.M >= 96);
     const int BM = big ? 128 : 64, BN = big ? 128 : 64, BK = 16;
     const int64_t gm = ceil_div64(g.M, BM), gn = ceil_div64(g.N, BN);

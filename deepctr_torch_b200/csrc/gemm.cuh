@@ -34,8 +34,10 @@ inline GemmArgs gemm_args_default() {
     return g;
 }
 
-// returns 0 or an error code (ctr_set_error already called)
+// returns 0 or an error code (ctr_set_error already called); dispatches between the tcgen05
+// 3xTF32 kernel (gemm_tc.cu) and the FP32 FFMA tiles (gemm.cu)
 int launch_sgemm(const GemmArgs& g, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 
 // out[n] = sum_m A[m*sam + n*san] * (mask ? act'(mask[m*smm + n*smn]) : 1) * (w ? w[m] : 1)
 int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, int64_t smm,

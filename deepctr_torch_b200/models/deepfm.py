@@ -29,7 +29,7 @@ class DeepFM(BaseModel):
         self.to(device)
 
     def forward(self, X):
-        E, dnn_input, lin, fm = self.embed(X, want_fm=self.use_fm, want_blk=self.use_dnn)
+        E, dnn_input, lin, fm = self.embed(X, want_fm=self.use_fm, want_blk=self.use_dnn or self.use_fm)
         terms = [lin]
         if self.use_fm and fm is not None:
             terms.append(fm)

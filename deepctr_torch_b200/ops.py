@@ -141,7 +141,7 @@ class _FusedInput(torch.autograd.Function):
                   plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
                   plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
                   _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
-                  _stream())
+                  plan.n_shards, _stream())
         ctx.plan, ctx.grad_mode = plan, grad_mode
         ctx.want_blk, ctx.want_fm = want_blk, want_fm
         ctx.has_ldw = lin_dense_w is not None

@@ -44,6 +44,9 @@ enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH =
  * lin[b] = sum_f lin_tables[f][id(b,f)] + sum_k X[b, lin_dense_cols[k]] * lin_dense_w[k]
  * fm[b]  = 0.5 * sum_d ((sum_f E)^2 - sum_f E^2)     (only if fm != NULL)
  * Any of {blk, lin, fm} may be NULL (branch switched off).  D is the (uniform) embedding dim.
+ * n_shards > 1: every table is row-sharded over the GPUs of the node (p2p.cu): the pointer arrays
+ * hold n_slots * n_shards device pointers, entry [f*n_shards + s] = the rows {id : id % n_shards
+ * == s} of field f stored at local index id / n_shards, on this GPU or a peer (NVLink P2P loads).
  */
 int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B,
                    int n_emb, int D, const float* const* emb_tables, const int32_t* emb_cols,
@@ -53,7 +56,7 @@ int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B,
                    int n_dense, const int32_t* dense_cols,
                    int n_lin_dense, const int32_t* lin_dense_cols, const float* lin_dense_w,
                    float* blk, int64_t ld_blk, float* lin, float* fm,
-                   int32_t* err_flag, void* stream);
+                   int32_t* err_flag, int n_shards, void* stream);
 
 /* FM on an already assembled block (used when pooled VarLen fields were added to it).
  * replaces FM.forward layers/interaction.py:26-34.  E = blk viewed as [B, F, D], row stride ld. */
@@ -107,6 +110,31 @@ int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv, cons
                             const float* blk, int64_t ld_blk,
                             const float* d_blk, int64_t ld_dblk,
                             const float* g_fm, const float* g_lin, void* stream);
+
+/* ---- multi-GPU: row-sharded tables over NVLink peer memory (replaces torch.nn.DataParallel,
+ * reference models/basemodel.py:206-209) ---------------------------------------------------
+ * ctr_p2p_alloc/free : cudaMalloc'ed (zero-filled) buffer that can be exported to peers — the
+ *                      only entry points that allocate; ctr_p2p_export writes the 64-byte CUDA
+ *                      IPC handle, ctr_p2p_open maps a peer's buffer (peer access enabled lazily).
+ * ctr_rowgrad_push   : after ctr_scatter_bwd_rowwise, appends every unique (local row id / G,
+ *                      gradient row) of field f to the receive list of its owner GPU id % G:
+ *                      slot = atomicAdd(recv_count[owner][f], 1) (remote atomic), then
+ *                      recv_ids[owner][f*cap + slot], recv_emb_rows[owner][(f*cap+slot)*D ..]
+ *                      (fields n_emb.. are the linear tables, rows in recv_lin_rows[owner]).
+ *                      recv_* are DEVICE arrays of n_shards peer pointers.  A full list sets
+ *                      bit 1 of *err_flag.
+ */
+int ctr_p2p_alloc(int64_t bytes, void** ptr);
+int ctr_p2p_free(void* ptr);
+int ctr_p2p_export(void* ptr, unsigned char* handle64);
+int ctr_p2p_open(const unsigned char* handle64, void** peer_ptr);
+int ctr_p2p_close(void* peer_ptr);
+int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
+                     int n_emb, int D, const float* const* emb_rowgrad, const int32_t* emb_plan_col,
+                     int n_lin, const float* const* lin_rowgrad, const int32_t* lin_plan_col,
+                     int32_t* const* recv_count, int32_t* const* recv_ids,
+                     float* const* recv_emb_rows, float* const* recv_lin_rows,
+                     int64_t cap, int32_t* err_flag, void* stream);
 
 /* gradient of Linear's dense weight: dw[k] = sum_b g[b] * X[b, cols[k]]   (basemodel.py:88-90) */
 int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n, const int32_t* cols,

@@ -1,0 +1,94 @@
+"""The two GEMM engines behind every dense op (tcgen05 3xTF32 split / FP32 FFMA tiles) against
+an fp64 torch reference, for the operand layouts the tower uses (NT forward, NN dgrad, TN wgrad
+with split-K), odd sizes, strided leading dimensions and the fused prologue/epilogues."""
+import os
+
+import pytest
+import torch
+
+from deepctr_torch_b200 import _lib, ops
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sgemm(A, sam, sak, Bm, sbn, sbk, M, N, K, accumulate=False, C=None):
+    if C is None:
+        C = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), sam, sak, ops._ptr(Bm), sbn, sbk, ops._ptr(C), C.stride(0),
+              1 if accumulate else 0, ops._stream())
+    return C
+
+
+@pytest.fixture(params=["tc", "simt"])
+def engine(request):
+    old = os.environ.get("CTR_GEMM")
+    os.environ["CTR_GEMM"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CTR_GEMM", None)
+    else:
+        os.environ["CTR_GEMM"] = old
+
+
+SHAPES = [(128, 256, 32), (1000, 256, 429), (4096, 128, 256), (77, 33, 19), (256, 429, 3000), (130, 520, 64),
+          (5, 7, 3), (513, 96, 1664)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_nt_nn_tn_layouts(engine, M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    # NT: A [M,K] row-major (ld padded), B [N,K] row-major
+    lda = (K + 3) // 4 * 4 + 4
+    Abuf = torch.randn(M, lda, device=DEV, generator=g)
+    Bm = torch.randn(N, K, device=DEV, generator=g)
+    C = _sgemm(Abuf, lda, 1, Bm, K, 1, M, N, K)
+    ref = Abuf[:, :K].double() @ Bm.double().t()
+    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    # NN (dgrad): B stored [K, N] row-major
+    Bkn = torch.randn(K, N, device=DEV, generator=g)
+    C = _sgemm(Abuf, lda, 1, Bkn, 1, N, M, N, K)
+    ref = Abuf[:, :K].double() @ Bkn.double()
+    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    # TN (wgrad): A stored [K, M], B stored [K, N]; split-K path when K is large
+    Akm = torch.randn(K, M, device=DEV, generator=g)
+    C = _sgemm(Akm, 1, M, Bkn, 1, N, M, N, K)
+    ref = Akm.double().t() @ Bkn.double()
+    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    # accumulate into C
+    C0 = torch.randn(M, N, device=DEV, generator=g)
+    C = _sgemm(Akm, 1, M, Bkn, 1, N, M, N, K, accumulate=True, C=C0.clone())
+    assert rel_err(C.cpu(), (ref + C0.double()).cpu()) <= 2e-6
+
+
+def test_wgrad_shape_split_k(engine):
+    """dW[256,429] = dZ^T[256,B] X[B,429] with B = 65536 (the BASELINE tower's first layer)."""
+    g = torch.Generator(device=DEV).manual_seed(1)
+    B, N, K = 65536, 256, 429
+    dZ = torch.randn(B, N, device=DEV, generator=g) * 0.01
+    X = torch.randn(B, 432, device=DEV, generator=g)
+    C = _sgemm(dZ, 1, N, X, 1, 432, N, K, B)
+    ref = dZ.double().t() @ X[:, :K].double()
+    assert rel_err(C.cpu(), ref.cpu()) <= 5e-6
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", "linear"])
+def test_dnn_layer_fwd_bwd(engine, act):
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, K, N = 3000, 429, 256
+    x = torch.randn(B, 432, device=DEV, generator=g)[:, :K].requires_grad_(True)
+    W = (torch.randn(N, K, device=DEV, generator=g) * 0.1).requires_grad_(True)
+    b = (torch.randn(N, device=DEV, generator=g) * 0.1).requires_grad_(True)
+    y = ops.dnn_layer(x, W, b, act)
+    w = torch.randn(B, N, device=DEV, generator=g)
+    (y * w).sum().backward()
+    xd, Wd, bd = x.detach().double().requires_grad_(True), W.detach().double().requires_grad_(True), \
+        b.detach().double().requires_grad_(True)
+    z = xd @ Wd.t() + bd
+    yr = {"relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh, "linear": lambda t: t}[act](z)
+    (yr * w.double()).sum().backward()
+    assert rel_err(y.detach().cpu(), yr.detach().cpu()) <= 2e-6
+    assert rel_err(x.grad.cpu(), xd.grad.cpu()) <= 5e-6
+    assert rel_err(W.grad.cpu(), Wd.grad.cpu()) <= 5e-6
+    assert rel_err(b.grad.cpu(), bd.grad.cpu()) <= 5e-6
