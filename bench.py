@@ -218,7 +218,9 @@ def run_gpu_arm(args):
     cfg = make_cfg(args.workload)
     if world > 1:
         from deepctr_torch_b200 import sharded
-        model, parallelism = sharded.build_sharded(cfg, dev, rank, world)
+        # BASELINE config #5 shape: total vocabulary 40M rows = 26 tables x 1 538 462 rows, row-sharded
+        cfg = make_cfg(args.workload, vocab=1538462)
+        model, parallelism = sharded.build_sharded(cfg, dev, rank, world, batch=B)
     else:
         model = build_model(cfg, dev, table_grad="rowwise")
         parallelism = "single"
@@ -241,6 +243,8 @@ def run_gpu_arm(args):
         y_pred = model(X)
         loss = bce(y_pred.squeeze(1), y, reduction="sum")
         loss.backward()
+        if world > 1:       # dense-grad all-reduce (= barrier for the pushed row gradients)
+            model.sharded.clear_received(model.sharded.finish_step())
         return loss
 
     def step_e2e(i):
@@ -251,7 +255,23 @@ def run_gpu_arm(args):
         y_pred = model(X)
         loss = bce(y_pred.squeeze(1), y, reduction="sum")
         loss.backward()
+        if world > 1:
+            model.sharded.clear_received(model.sharded.finish_step())
         return float(loss.item())          # device -> host read of the step's result
+
+    use_graph = (world == 1) and not args.no_graph
+    if use_graph:
+        # the whole fwd+loss+bwd step captured once as a CUDA graph and replayed (public API:
+        # model.make_graphed_step); removes the ~30 per-launch host overheads from the step
+        gstep = model.make_graphed_step(B)
+
+        def step_resident(i):      # noqa: F811
+            X, y = dev_batches[i % N_ROTATE]
+            return gstep(X, y)
+
+        def step_e2e(i):           # noqa: F811
+            Xh, yh = host_batches[i % N_ROTATE]
+            return float(gstep(Xh, yh).item())
 
     def barrier():
         if world > 1:
@@ -285,9 +305,17 @@ def run_gpu_arm(args):
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
 
     # instrumented pass: CUDA events around every C-ABI entry point -> dominant kernel + roofline
+    def step_eager(i):
+        X, y = dev_batches[i % N_ROTATE]
+        model.zero_grad(set_to_none=True)
+        loss = bce(model(X).squeeze(1), y, reduction="sum")
+        loss.backward()
+        if world > 1:
+            model.sharded.clear_received(model.sharded.finish_step())
+
     _lib.enable_timing(True)
     for i in range(args.steps):
-        step_resident(i)
+        step_eager(i)
     summary = _lib.timing_summary()
     _lib.enable_timing(False)
 
@@ -338,11 +366,12 @@ def run_gpu_arm(args):
         "metric": "CTR samples/sec fwd+bwd", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": total_B, "vocab_per_table": 1000000,
+        "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": total_B, "vocab_per_table": cfg["dnn_columns"][0]["vocab"],
                    "parallelism": parallelism, "table_grad": "rowwise (per-unique-row, SURVEY §8d)",
                    "l2": 0, "l2_flush": "8 rotating batches, 109 MB of gathered rows each (> L2 with tables)",
                    "algorithmic_bytes_per_sample": a_bytes, "tensor_flops_per_sample": fl,
-                   "tower_precision": "fp32 FFMA (parity mode)"},
+                   "tower_precision": "3xTF32 on tcgen05, fp32 accumulate (parity mode)" if os.environ.get("CTR_GEMM", "") != "simt" else "fp32 FFMA (parity mode)",
+                   "cuda_graph": bool(use_graph)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(B * 39 * 4 + B * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -369,6 +398,7 @@ def main():
     ap.add_argument("--workload", default="deepfm", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU arm (0 = the workload's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

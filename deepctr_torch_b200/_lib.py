@@ -24,15 +24,15 @@ SIGNATURES = {
     "ctr_scatter_bwd_dense": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P,
                               _P, c_i64, _P, c_i64, _P, _P, _P],
     "ctr_unique_plan": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P, c_i64, _P, _P, _P, _P, _P, _P],
-    "ctr_scatter_bwd_rowwise": [c_i64, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P,
+    "ctr_scatter_bwd_rowwise": [c_i64, c_int, _P, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
                                 _P, c_i64, _P, c_i64, _P, _P, _P],
     "ctr_p2p_alloc": [c_i64, _P],
     "ctr_p2p_free": [_P],
     "ctr_p2p_export": [_P, _P],
     "ctr_p2p_open": [_P, _P],
     "ctr_p2p_close": [_P],
-    "ctr_rowgrad_push": [c_i64, c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P,
-                         c_i64, _P, _P],
+    "ctr_rowgrad_push": [c_i64, c_int, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
+                         _P, _P, _P, _P, c_i64, _P, _P],
     "ctr_lin_dense_wgrad": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P],
     "ctr_dnn_layer_fwd": [_P, c_i64, _P, c_i64, c_i64, _P, _P, c_i64, c_i64, c_int, c_int, c_int, _P],
     "ctr_dnn_layer_bwd": [_P, c_i64, _P, c_i64, c_i64, _P, c_i64, _P, c_i64, _P, c_i64, c_int,

@@ -12,7 +12,13 @@
 //   dX    : rows tile x (HT*M) hm columns per step with HT whole h-groups so that
 //           dXp[b,h,d] = sum_m G*X0 is complete inside the tile (plain store) and
 //           dX0[b,m,d] += sum_h G*Xp accumulates in CTA-private shared memory (no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
+
+int launch_cin_tc_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D,
+                      const float* W, const float* bias, int N, int direct_start, int act, float* Y,
+                      float* out, int64_t ld_out, int64_t B, cudaStream_t st);
 
 namespace {
 
@@ -449,6 +455,15 @@ extern "C" int ctr_cin_layer_fwd(const float* Xp, int64_t sxp, int H, const floa
     CTR_ARG(D <= BM, "ctr_cin_layer_fwd: embedding dim %d > %d unsupported", D, BM);
     if (B == 0) return 0;
     cudaStream_t st = as_stream(stream);
+    {   // tensor-core path (cin_tc.cu) unless CTR_GEMM=simt or the shape is unsupported
+        const char* e = getenv("CTR_GEMM");
+        if (!(e && e[0] == 's')) {
+            const int rc = launch_cin_tc_fwd(Xp, sxp, H, X0, sx0, M, D, W, bias, N, direct_start, act, Y, out,
+                                             ld_out, B, st);
+            if (rc == 1) return 0;
+            if (rc != 0) return rc;
+        }
+    }
     const int n_direct = N - direct_start;
     if (n_direct > 0)
         CTR_CUDA(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, n_direct * sizeof(float), B, st));

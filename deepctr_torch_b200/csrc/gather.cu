@@ -260,7 +260,11 @@ struct ScatterArgs {
     int64_t ldx;
     int64_t B;
     int n_emb, D;
-    float* const* emb_out;         // dense: grad tables [V,D]; rowwise: row-grad buffers [B,D]
+    float* const* emb_out;         // dense: grad tables [V,D] (device pointer array)
+    float* emb_rg;                 // rowwise: row-grad buffers [n_emb][B,D] at emb_rg + f*emb_rg_stride
+    int64_t emb_rg_stride;
+    float* lin_rg;                 // rowwise: [n_lin][B] at lin_rg + f*lin_rg_stride
+    int64_t lin_rg_stride;
     const int32_t* emb_cols;       // dense: X column; rowwise: plan column
     const int32_t* emb_vocab;
     int n_lin;
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
                         r[s].w += gfm * (S.w - v.w);
                     }
                     if (ROWWISE) {
-                        float* dst = a.emb_out[f] + (int64_t)u[s] * D + sub * 4;
+                        float* dst = a.emb_rg + f * a.emb_rg_stride + (int64_t)u[s] * D + sub * 4;
                         if (c[s] == 1) st_stream4(dst, r[s]);
                         else red_add4(dst, r[s]);
                     } else {
@@ -377,8 +381,9 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
                     const int pc = a.lin_cols[f];
                     const int u = __ldg(a.inv + b * a.n_plan + pc);
                     const int c = __ldg(a.cnt + (int64_t)pc * a.B + u);
-                    if (c == 1) a.lin_out[f][u] = gl;
-                    else atomicAdd(a.lin_out[f] + u, gl);
+                    float* dst = a.lin_rg + f * a.lin_rg_stride + u;
+                    if (c == 1) *dst = gl;
+                    else atomicAdd(dst, gl);
                 } else {
                     const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], nullptr);
                     atomicAdd(a.lin_out[f] + id, gl);
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a)
             if (ROWWISE) {
                 const int pc = a.emb_cols[f];
                 const int u = a.inv[b * a.n_plan + pc];
-                atomicAdd(a.emb_out[f] + (int64_t)u * D + d, r);
+                atomicAdd(a.emb_rg + f * a.emb_rg_stride + (int64_t)u * D + d, r);
             } else {
                 const int64_t id = decode_id(xrow[a.emb_cols[f]], a.emb_vocab[f], nullptr);
                 atomicAdd(a.emb_out[f] + id * D + d, r);
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a)
             for (int f = lane; f < a.n_lin; f += 32) {
                 if (ROWWISE) {
                     const int u = a.inv[b * a.n_plan + a.lin_cols[f]];
-                    atomicAdd(a.lin_out[f] + u, gl);
+                    atomicAdd(a.lin_rg + f * a.lin_rg_stride + u, gl);
                 } else {
                     const int64_t id = decode_id(xrow[a.lin_cols[f]], a.lin_vocab[f], nullptr);
                     atomicAdd(a.lin_out[f] + id, gl);
@@ -435,9 +440,10 @@ __global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a)
 // (cnt == 0: padding beyond n_uniq; cnt > 1: accumulated with reductions).  force_all zeroes
 // everything (generic path uses atomics only).
 __global__ void __launch_bounds__(256) rowgrad_prep_kernel(int64_t B, const int32_t* __restrict__ cnt,
-                                                           int n_emb, int D, float* const* emb_out,
+                                                           int n_emb, int D, float* emb_rg,
+                                                           int64_t emb_rg_stride,
                                                            const int32_t* emb_plan, int n_lin,
-                                                           float* const* lin_out,
+                                                           float* lin_rg, int64_t lin_rg_stride,
                                                            const int32_t* lin_plan, int force_all) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(256) rowgrad_prep_kernel(int64_t B, const int3
             const int64_t u = (i / D4) % B;
             const int f = (int)(i / ((int64_t)D4 * B));
             if (force_all || __ldg(cnt + (int64_t)emb_plan[f] * B + u) != 1)
-                *reinterpret_cast<float4*>(emb_out[f] + u * D + sub * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(emb_rg + f * emb_rg_stride + u * D + sub * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
         const int64_t total = (int64_t)n_emb * B * D;
@@ -457,14 +463,14 @@ __global__ void __launch_bounds__(256) rowgrad_prep_kernel(int64_t B, const int3
             const int d = (int)(i % D);
             const int64_t u = (i / D) % B;
             const int f = (int)(i / ((int64_t)D * B));
-            if (force_all || cnt[(int64_t)emb_plan[f] * B + u] != 1) emb_out[f][u * D + d] = 0.f;
+            if (force_all || cnt[(int64_t)emb_plan[f] * B + u] != 1) emb_rg[f * emb_rg_stride + u * D + d] = 0.f;
         }
     }
     const int64_t total_l = (int64_t)n_lin * B;
     for (int64_t i = tid; i < total_l; i += nthreads) {
         const int64_t u = i % B;
         const int f = (int)(i / B);
-        if (force_all || __ldg(cnt + (int64_t)lin_plan[f] * B + u) != 1) lin_out[f][u] = 0.f;
+        if (force_all || __ldg(cnt + (int64_t)lin_plan[f] * B + u) != 1) lin_rg[f * lin_rg_stride + u] = 0.f;
     }
 }
 
@@ -662,13 +668,13 @@ extern "C" int ctr_fm_bwd(const float* blk, int64_t ld, int64_t B, int F, int D,
     return 0;
 }
 
-static int launch_scatter(ScatterArgs& a, bool rowwise, cudaStream_t st) {
+static int launch_scatter(ScatterArgs& a, bool rowwise, cudaStream_t st, bool force_generic = false) {
     const int lpr = (a.n_emb > 0) ? lpr_for_dim(a.D) : 1;
     const bool aligned =
         (!a.blk || (a.ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.blk) & 15) == 0)) &&
         (!a.d_blk || (a.ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.d_blk) & 15) == 0));
     const unsigned grid = sample_grid(a.B, 8, 8);
-    if (lpr > 0 && aligned) {
+    if (lpr > 0 && aligned && !force_generic) {
 #define LAUNCH_SC(L)                                                                     \
     if (rowwise) scatter_bwd_vec_kernel<L, true><<<grid, 256, 0, st>>>(a);               \
     else scatter_bwd_vec_kernel<L, false><<<grid, 256, 0, st>>>(a);
@@ -702,8 +708,11 @@ extern "C" int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B, int
     CTR_ARG(n_lin == 0 || !g_lin || (lin_grads && lin_cols && lin_vocab), "ctr_scatter_bwd_dense: linear arrays missing");
     CTR_ARG(!g_fm || blk, "ctr_scatter_bwd_dense: FM gradient needs blk");
     if (B == 0) return 0;
-    ScatterArgs a{X, ldx, B, n_emb, D, emb_grads, emb_cols, emb_vocab, g_lin ? n_lin : 0, lin_grads,
-                  lin_cols, lin_vocab, blk, ld_blk, d_blk, ld_dblk, g_fm, g_lin, 0, nullptr, nullptr};
+    ScatterArgs a{};
+    a.X = X; a.ldx = ldx; a.B = B; a.n_emb = n_emb; a.D = D;
+    a.emb_out = emb_grads; a.emb_cols = emb_cols; a.emb_vocab = emb_vocab;
+    a.n_lin = g_lin ? n_lin : 0; a.lin_out = lin_grads; a.lin_cols = lin_cols; a.lin_vocab = lin_vocab;
+    a.blk = blk; a.ld_blk = ld_blk; a.d_blk = d_blk; a.ld_dblk = ld_dblk; a.g_fm = g_fm; a.g_lin = g_lin;
     if (!d_blk && !g_fm) a.n_emb = 0;
     const int r = launch_scatter(a, false, as_stream(stream));
     return r < 0 ? r : (r > 2 ? r : 0);
@@ -742,24 +751,32 @@ extern "C" int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_col
 
 extern "C" int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv,
                                        const int32_t* cnt, const int32_t* n_uniq, int n_emb, int D,
-                                       float* const* emb_rowgrad, const int32_t* emb_plan_col,
-                                       int n_lin, float* const* lin_rowgrad,
-                                       const int32_t* lin_plan_col, const float* blk, int64_t ld_blk,
-                                       const float* d_blk, int64_t ld_dblk, const float* g_fm,
-                                       const float* g_lin, void* stream) {
+                                       float* emb_rowgrad, int64_t emb_rowgrad_stride,
+                                       const int32_t* emb_plan_col, int n_lin, float* lin_rowgrad,
+                                       int64_t lin_rowgrad_stride, const int32_t* lin_plan_col,
+                                       const float* blk, int64_t ld_blk, const float* d_blk,
+                                       int64_t ld_dblk, const float* g_fm, const float* g_lin,
+                                       void* stream) {
     (void)n_uniq;
     CTR_ARG(inv && cnt && n_plan_cols > 0 && B >= 0, "ctr_scatter_bwd_rowwise: plan missing");
-    CTR_ARG(n_emb == 0 || (D > 0 && emb_rowgrad && emb_plan_col), "ctr_scatter_bwd_rowwise: embedding arrays missing");
-    CTR_ARG(n_lin == 0 || (lin_rowgrad && lin_plan_col), "ctr_scatter_bwd_rowwise: linear arrays missing");
+    CTR_ARG(n_emb == 0 || (D > 0 && emb_rowgrad && emb_plan_col && emb_rowgrad_stride >= B * D),
+            "ctr_scatter_bwd_rowwise: embedding row-gradient buffer missing or too small");
+    CTR_ARG(n_lin == 0 || (lin_rowgrad && lin_plan_col && g_lin && lin_rowgrad_stride >= B),
+            "ctr_scatter_bwd_rowwise: linear row-gradient buffer / g_lin missing");
     CTR_ARG(!g_fm || blk, "ctr_scatter_bwd_rowwise: FM gradient needs blk");
     if (B == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    ScatterArgs a{nullptr, 0, B, n_emb, D, emb_rowgrad, emb_plan_col, nullptr, n_lin, lin_rowgrad,
-                  lin_plan_col, nullptr, blk, ld_blk, d_blk, ld_dblk, g_fm, g_lin, n_plan_cols, inv, cnt};
+    ScatterArgs a{};
+    a.B = B; a.n_emb = n_emb; a.D = D;
+    a.emb_rg = emb_rowgrad; a.emb_rg_stride = emb_rowgrad_stride; a.emb_cols = emb_plan_col;
+    a.n_lin = n_lin; a.lin_rg = lin_rowgrad; a.lin_rg_stride = lin_rowgrad_stride; a.lin_cols = lin_plan_col;
+    a.blk = blk; a.ld_blk = ld_blk; a.d_blk = d_blk; a.ld_dblk = ld_dblk; a.g_fm = g_fm; a.g_lin = g_lin;
+    a.n_plan = n_plan_cols; a.inv = inv; a.cnt = cnt;
     const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
     const bool aligned =
         (!blk || (ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(blk) & 15) == 0)) &&
-        (!d_blk || (ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(d_blk) & 15) == 0));
+        (!d_blk || (ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(d_blk) & 15) == 0)) &&
+        (n_emb == 0 || (emb_rowgrad_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(emb_rowgrad) & 15) == 0));
     const int force_all = (lpr > 0 && aligned) ? 0 : 1;
     {
         int64_t work = (int64_t)n_emb * B * (D % 4 == 0 ? D / 4 : D);
@@ -768,13 +785,12 @@ extern "C" int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t
         const int64_t cap = (int64_t)ctr_sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        rowgrad_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, cnt, n_emb, D, emb_rowgrad,
+        rowgrad_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, cnt, n_emb, D, emb_rowgrad, emb_rowgrad_stride,
                                                               emb_plan_col, n_lin, lin_rowgrad,
-                                                              lin_plan_col, force_all);
+                                                              lin_rowgrad_stride, lin_plan_col, force_all);
         CTR_LAUNCH_OK("rowgrad_prep_kernel");
     }
-    // the sparse linear rows still need a value when the linear branch received no gradient
-    const int r = launch_scatter(a, true, st);
+    const int r = launch_scatter(a, true, st, force_all != 0);
     return r < 0 ? r : (r > 2 ? r : 0);
 }
 

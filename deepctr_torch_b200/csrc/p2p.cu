@@ -21,10 +21,12 @@ struct PushArgs {
     const int32_t* n_uniq;
     const int32_t* uniq;
     int n_emb, D;
-    const float* const* emb_rowgrad;
+    const float* emb_rowgrad;
+    int64_t emb_rg_stride;
     const int32_t* emb_plan_col;
     int n_lin;
-    const float* const* lin_rowgrad;
+    const float* lin_rowgrad;
+    int64_t lin_rg_stride;
     const int32_t* lin_plan_col;
     int32_t* const* recv_count;
     int32_t* const* recv_ids;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
         }
         a.recv_ids[owner][(int64_t)f * a.cap + slot] = local;
         if (is_emb) {
-            const float* src = a.emb_rowgrad[f] + u * a.D;
+            const float* src = a.emb_rowgrad + f * a.emb_rg_stride + u * a.D;
             float* dst = a.recv_emb_rows[owner] + ((int64_t)f * a.cap + slot) * a.D;
             if ((a.D & 3) == 0) {
                 for (int d = 0; d < a.D; d += 4)
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
             }
         } else {
             const int fl = f - a.n_emb;
-            a.recv_lin_rows[owner][(int64_t)fl * a.cap + slot] = a.lin_rowgrad[fl][u];
+            a.recv_lin_rows[owner][(int64_t)fl * a.cap + slot] = a.lin_rowgrad[fl * a.lin_rg_stride + u];
         }
     }
 }
@@ -106,9 +108,9 @@ extern "C" int ctr_p2p_close(void* peer_ptr) {
 }
 
 extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
-                                int n_emb, int D, const float* const* emb_rowgrad,
-                                const int32_t* emb_plan_col, int n_lin,
-                                const float* const* lin_rowgrad, const int32_t* lin_plan_col,
+                                int n_emb, int D, const float* emb_rowgrad, int64_t emb_rowgrad_stride,
+                                const int32_t* emb_plan_col, int n_lin, const float* lin_rowgrad,
+                                int64_t lin_rowgrad_stride, const int32_t* lin_plan_col,
                                 int32_t* const* recv_count, int32_t* const* recv_ids,
                                 float* const* recv_emb_rows, float* const* recv_lin_rows,
                                 int64_t cap, int32_t* err_flag, void* stream) {
@@ -117,8 +119,8 @@ extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, 
     CTR_ARG(n_emb == 0 || (D > 0 && emb_rowgrad && emb_plan_col && recv_emb_rows), "ctr_rowgrad_push: embedding arrays missing");
     CTR_ARG(n_lin == 0 || (lin_rowgrad && lin_plan_col && recv_lin_rows), "ctr_rowgrad_push: linear arrays missing");
     if (B == 0 || n_emb + n_lin == 0) return 0;
-    PushArgs a{B, n_shards, n_uniq, uniq, n_emb, D, emb_rowgrad, emb_plan_col, n_lin, lin_rowgrad, lin_plan_col,
-               recv_count, recv_ids, recv_emb_rows, recv_lin_rows, cap, err_flag};
+    PushArgs a{B, n_shards, n_uniq, uniq, n_emb, D, emb_rowgrad, emb_rowgrad_stride, emb_plan_col, n_lin,
+               lin_rowgrad, lin_rowgrad_stride, lin_plan_col, recv_count, recv_ids, recv_emb_rows, recv_lin_rows, cap, err_flag};
     int64_t blocks = ceil_div64((int64_t)(n_emb + n_lin) * B, 256);
     const int64_t limit = (int64_t)ctr_sm_count() * 8;
     if (blocks > limit) blocks = limit;

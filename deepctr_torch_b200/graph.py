@@ -1,0 +1,56 @@
+"""CUDA-graph capture of one training step (forward -> loss -> backward).
+
+The hot path is ~30 short kernel launches per step; at B200 speeds the Python/launch overhead of
+issuing them one by one is comparable to their run time.  Every launch of libctr_b200.so goes to
+torch's current stream, allocates nothing and never synchronises, so the whole step is capturable:
+``GraphedStep`` records it once into a ``torch.cuda.CUDAGraph`` and replays it with new inputs copied
+into static buffers.  Gradients land in the same ``.grad`` tensors on every replay (dense tower: dense
+tensors; tables: dense or per-unique-row sparse COO, depending on ``model.table_grad``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+class GraphedStep:
+    def __init__(self, model, batch_size, loss_fn=None, warmup=3, with_reg=False):
+        self.model = model
+        dev = torch.device(model.device)
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedStep needs a CUDA model")
+        n_cols = max(e for _, e in model.feature_index.values())
+        self.X = torch.zeros(batch_size, n_cols, device=dev, dtype=torch.float32)
+        self.y = torch.zeros(batch_size, device=dev, dtype=torch.float32)
+        self.loss_fn = loss_fn or F.binary_cross_entropy
+        self.with_reg = with_reg
+        model.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):     # sizes workspaces, sets kernel attributes
+                model.zero_grad(set_to_none=True)
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.check_ids()
+        model.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.y_pred = self._body()
+
+    def _body(self):
+        y_pred = self.model(self.X)
+        loss = self.loss_fn(y_pred.squeeze(1), self.y, reduction="sum")
+        total = loss
+        if self.with_reg:
+            total = loss + self.model.get_regularization_loss().sum()
+        total.backward()
+        return loss, y_pred
+
+    def __call__(self, X, y):
+        """Copy one batch in (host or device tensors) and replay; returns the (device) loss tensor."""
+        self.X.copy_(X, non_blocking=True)
+        self.y.copy_(y.reshape(-1), non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -437,6 +437,11 @@ class BaseModel(nn.Module):
                 self.check_ids()
         return np.concatenate(pred_ans).astype("float64")
 
+    def make_graphed_step(self, batch_size, loss_fn=None, with_reg=False):
+        """One forward+loss+backward captured as a CUDA graph (see deepctr_torch_b200.graph)."""
+        from ..graph import GraphedStep
+        return GraphedStep(self, batch_size, loss_fn=loss_fn, with_reg=with_reg)
+
     def _in_multi_worker_mode(self):
         return None
 

@@ -90,6 +90,7 @@ class GatherPlan:
         self.emb_plan_col = torch.tensor([plan_cols.index(s[1]) for s in emb_slots], **i32)
         self.lin_plan_col = torch.tensor([plan_cols.index(s[1]) for s in lin_slots], **i32)
         self.err_flag = torch.zeros(1, **i32)
+        self.n_shards = 1
         self._ptr_key = None
         self._emb_ptrs = self._lin_ptrs = None
         self._ws = {}
@@ -197,13 +198,24 @@ class _FusedInput(torch.autograd.Function):
                       _ptr(plan.err_flag), _stream())
             rg_emb = torch.empty(max(n_emb, 1), B, max(plan.D, 1), device=dev, dtype=torch.float32)
             rg_lin = torch.empty(max(plan.n_lin, 1), B, device=dev, dtype=torch.float32)
-            eg = torch.tensor([rg_emb[f].data_ptr() for f in range(n_emb)], **i64) if n_emb else None
-            lg = torch.tensor([rg_lin[f].data_ptr() for f in range(plan.n_lin)], **i64) if plan.n_lin else None
             _lib.call("ctr_scatter_bwd_rowwise", B, n_plan, _ptr(ws["inv"]), _ptr(ws["cnt"]),
-                      _ptr(ws["n_uniq"]), n_emb, plan.D, _ptr(eg), _ptr(plan.emb_plan_col),
-                      plan.n_lin, _ptr(lg), _ptr(plan.lin_plan_col),
+                      _ptr(ws["n_uniq"]), n_emb, plan.D, _ptr(rg_emb), B * max(plan.D, 1),
+                      _ptr(plan.emb_plan_col), plan.n_lin, _ptr(rg_lin), B, _ptr(plan.lin_plan_col),
                       _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
                       _ptr(d_fm), _ptr(d_lin), _stream())
+            if ctx.grad_mode == "sharded":
+                # deliver every unique (row, gradient) to the rank that owns the row (csrc/p2p.cu);
+                # table gradients then live in the owners' receive lists, not in autograd
+                from . import sharded
+                sharded.push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb)
+                grads_emb = [None] * plan.n_emb
+                grads_lin = [None] * plan.n_lin
+                d_ldw = None
+                if ctx.has_ldw:
+                    d_ldw = torch.empty(plan.n_lin_dense, 1, device=dev, dtype=torch.float32)
+                    _lib.call("ctr_lin_dense_wgrad", _ptr(X), X.stride(0), B, plan.n_lin_dense,
+                              _ptr(plan.lin_dense_cols), _ptr(d_lin), _ptr(d_ldw), _stream())
+                return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
             uniq = ws["uniq"].to(torch.int64)
             emb_pc = plan.emb_plan_col.tolist() if not hasattr(plan, "_emb_pc") else plan._emb_pc
             lin_pc = plan.lin_plan_col.tolist() if not hasattr(plan, "_lin_pc") else plan._lin_pc

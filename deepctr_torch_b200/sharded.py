@@ -1,0 +1,306 @@
+"""Row-sharded embedding tables across the GPUs of one node (one process per GPU).
+
+Replaces the reference's single-process ``torch.nn.DataParallel`` (reference
+``deepctr_torch/models/basemodel.py:206-209``), which replicates every table on every GPU each
+step.  Here every table is split by rows: rank ``s`` owns ``{id : id % G == s}`` at local index
+``id // G``; the dense tower is replicated and its gradients are all-reduced with NCCL.
+
+Sparse data path (no NCCL collective on it — see ``csrc/p2p.cu``):
+
+* every rank allocates ONE peer-shareable arena (``ctr_p2p_alloc``) with an identical layout:
+  its table shards followed by two receive lists for row gradients; CUDA IPC handles are exchanged
+  once (``all_gather_object``) and opened with ``ctr_p2p_open``;
+* forward: the fused gather kernel reads remote rows through the peer pointers (NVLink P2P loads);
+* backward: local duplicate-free row gradients, then ``ctr_rowgrad_push`` appends each
+  (local row, gradient) to its owner's receive list (remote atomic slot claim + P2P stores).
+  The dense-gradient all-reduce that follows doubles as the barrier that makes the lists complete;
+  the lists are double-buffered by step parity so a fast rank can never overwrite a list its owner
+  is still consuming.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+# ----------------------------------------------------------------------------------------------
+# pure host logic (exercised on CPU with gloo in tests/test_sharded_host.py)
+# ----------------------------------------------------------------------------------------------
+def local_rows(vocab, rank, world):
+    """Number of rows of a [vocab, *] table owned by `rank` (ids with id % world == rank)."""
+    return (vocab - rank + world - 1) // world if vocab > rank else 0
+
+
+def max_local_rows(vocab, world):
+    return (vocab + world - 1) // world
+
+
+def shard_rows(full, rank, world):
+    """Rows of `full` owned by `rank`, in local order (local index = id // world)."""
+    return full[rank::world].contiguous()
+
+
+def unshard_rows(shards, vocab):
+    """Inverse of shard_rows: list of per-rank shards -> the full [vocab, *] table."""
+    world = len(shards)
+    out = shards[0].new_empty((vocab,) + tuple(shards[0].shape[1:]))
+    for r, sh in enumerate(shards):
+        n = local_rows(vocab, r, world)
+        out[r::world] = sh[:n]
+    return out
+
+
+class ArenaLayout:
+    """Identical on every rank: byte offsets of table shards and receive lists inside the arena."""
+
+    def __init__(self, emb_vocabs, lin_vocabs, dim, world, batch, align=256):
+        self.world, self.D = world, dim
+        self.n_emb, self.n_lin = len(emb_vocabs), len(lin_vocabs)
+        self.cap = batch * world                       # worst case: every rank sends `batch` rows
+        cursor = 0
+
+        def take(nbytes):
+            nonlocal cursor
+            off = cursor
+            cursor = (cursor + nbytes + align - 1) // align * align
+            return off
+
+        self.emb_rows = [max_local_rows(v, world) for v in emb_vocabs]
+        self.lin_rows = [max_local_rows(v, world) for v in lin_vocabs]
+        self.emb_off = [take(r * dim * 4) for r in self.emb_rows]
+        self.lin_off = [take(r * 4) for r in self.lin_rows]
+        nf = self.n_emb + self.n_lin
+        self.recv = []
+        for _ in range(2):                              # double-buffered by step parity
+            self.recv.append({"count": take(max(nf, 1) * 4), "ids": take(max(nf, 1) * self.cap * 4),
+                              "emb": take(max(self.n_emb, 1) * self.cap * dim * 4),
+                              "lin": take(max(self.n_lin, 1) * self.cap * 4)})
+        self.nbytes = cursor
+
+
+def gather_full_state_dict(local_state, table_vocabs, group=None):
+    """Gather-on-save: turn a rank-local state_dict (sharded tables, replicated dense params) into
+    the reference-compatible full state_dict.  `table_vocabs`: {state key: logical vocab}."""
+    world = dist.get_world_size(group)
+    full = {}
+    for k, v in local_state.items():
+        if k in table_vocabs:
+            rows = max_local_rows(table_vocabs[k], world)
+            pad = v.new_zeros((rows,) + tuple(v.shape[1:]))
+            pad[:v.shape[0]] = v
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad, group=group)
+            full[k] = unshard_rows(parts, table_vocabs[k])
+        else:
+            full[k] = v
+    return full
+
+
+def scatter_full_state_dict(full_state, table_vocabs, rank, world):
+    """Scatter-on-load: the rank-local view of a reference-compatible full state_dict."""
+    out = {}
+    for k, v in full_state.items():
+        if k in table_vocabs:
+            sh = shard_rows(v, rank, world)
+            rows = max_local_rows(table_vocabs[k], world)
+            pad = sh.new_zeros((rows,) + tuple(sh.shape[1:]))
+            pad[:sh.shape[0]] = sh
+            out[k] = pad
+        else:
+            out[k] = v
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# device side
+# ----------------------------------------------------------------------------------------------
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier so torch can alias memory from ctr_p2p_alloc."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class P2PArena:
+    def __init__(self, nbytes, device, group=None):
+        self.device = torch.device(device)
+        self.nbytes = nbytes
+        lib = _lib.load()
+        p = ctypes.c_void_p()
+        rc = lib.ctr_p2p_alloc(nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise _lib.CtrLibraryError("ctr_p2p_alloc(%d) failed: %s" % (nbytes, lib.ctr_last_error().decode()))
+        self.ptr = p.value
+        self._raw = _RawCuda(self.ptr, nbytes)
+        self.bytes = torch.as_tensor(self._raw, device=self.device)
+        handle = (ctypes.c_ubyte * 64)()
+        rc = lib.ctr_p2p_export(ctypes.c_void_p(self.ptr), handle)
+        if rc != 0:
+            raise _lib.CtrLibraryError("ctr_p2p_export failed: %s" % lib.ctr_last_error().decode())
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptr = []
+        for r in range(world):
+            if r == rank:
+                self.peer_ptr.append(self.ptr)
+                continue
+            q = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            rc = lib.ctr_p2p_open(buf, ctypes.byref(q))
+            if rc != 0:
+                raise _lib.CtrLibraryError("ctr_p2p_open(rank %d) failed: %s" % (r, lib.ctr_last_error().decode()))
+            self.peer_ptr.append(q.value)
+
+    def view(self, offset, shape, dtype=torch.float32):
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        return self.bytes[offset:offset + nbytes].view(dtype).view(*shape)
+
+
+class ShardedPlan(ops.GatherPlan):
+    """GatherPlan whose table pointers address every rank's shard and which pushes row gradients."""
+
+    def setup_shards(self, arena, layout, rank, world, logical_emb_vocab, logical_lin_vocab):
+        self.n_shards = world
+        self.rank, self.world = rank, world
+        self.arena, self.layout = arena, layout
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.emb_vocab = torch.tensor(logical_emb_vocab, **i32)
+        self.lin_vocab = torch.tensor(logical_lin_vocab, **i32)
+        vocab_of = {}
+        for col, v in list(zip(self.emb_cols.tolist(), logical_emb_vocab)) + list(zip(self.lin_cols.tolist(), logical_lin_vocab)):
+            vocab_of[col] = max(vocab_of.get(col, 0), v)
+        self.plan_vocab = torch.tensor([vocab_of[c] for c in self.plan_cols_host], **i32)
+        self._emb_ptrs = torch.tensor([arena.peer_ptr[s] + layout.emb_off[f]
+                                       for f in range(layout.n_emb) for s in range(world)], **i64)
+        self._lin_ptrs = torch.tensor([arena.peer_ptr[s] + layout.lin_off[f]
+                                       for f in range(layout.n_lin) for s in range(world)], **i64)
+        self.recv_ptrs = []
+        for par in range(2):
+            r = layout.recv[par]
+            self.recv_ptrs.append({k: torch.tensor([arena.peer_ptr[s] + r[k] for s in range(world)], **i64)
+                                   for k in ("count", "ids", "emb", "lin")})
+        self.step_parity = 0
+
+    def table_ptrs(self):
+        return self._emb_ptrs, self._lin_ptrs
+
+    def recv_views(self, parity):
+        """This rank's receive lists: (count [n_fields], ids [n_fields, cap], emb [n_emb, cap, D], lin [n_lin, cap])."""
+        L, r = self.layout, self.layout.recv[parity]
+        nf = max(L.n_emb + L.n_lin, 1)
+        return (self.arena.view(r["count"], (nf,), torch.int32),
+                self.arena.view(r["ids"], (nf, L.cap), torch.int32),
+                self.arena.view(r["emb"], (max(L.n_emb, 1), L.cap, L.D)),
+                self.arena.view(r["lin"], (max(L.n_lin, 1), L.cap)))
+
+
+def push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb):
+    """Called from the fused-input backward in sharded mode."""
+    par = plan.step_parity
+    rp = plan.recv_ptrs[par]
+    _lib.call("ctr_rowgrad_push", B, plan.world, ops._ptr(ws["n_uniq"]), ops._ptr(ws["uniq"]),
+              n_emb, plan.D, ops._ptr(rg_emb), B * max(plan.D, 1), ops._ptr(plan.emb_plan_col),
+              plan.n_lin, ops._ptr(rg_lin), B, ops._ptr(plan.lin_plan_col),
+              ops._ptr(rp["count"]), ops._ptr(rp["ids"]), ops._ptr(rp["emb"]), ops._ptr(rp["lin"]),
+              plan.layout.cap, ops._ptr(plan.err_flag), ops._stream())
+
+
+class ShardedRuntime:
+    """Attached to a model as ``model.sharded``: dense-gradient all-reduce and step bookkeeping."""
+
+    def __init__(self, model, plan, group=None):
+        self.model, self.plan, self.group = model, plan, group
+        table_ids = set(id(p) for p in plan.emb_params + plan.lin_params)
+        self.dense_params = [p for p in model.parameters() if id(p) not in table_ids]
+
+    def finish_step(self):
+        """All-reduce the replicated parameters' gradients (this also orders every rank's
+        ``ctr_rowgrad_push`` before any owner reads its receive list), then flip the parity and
+        clear the list that peers will fill two steps from now."""
+        grads = [p.grad for p in self.dense_params if p.grad is not None]
+        if grads:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, group=self.group)
+            off = 0
+            for g in grads:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+        else:
+            dist.barrier(group=self.group)
+        done = self.plan.step_parity
+        self.plan.step_parity ^= 1
+        return done
+
+    def received_row_grads(self, parity):
+        """(counts, ids, emb_rows, lin_rows) delivered to this rank in the step of `parity`."""
+        return self.plan.recv_views(parity)
+
+    def clear_received(self, parity):
+        self.plan.recv_views(parity)[0].zero_()
+
+
+def build_sharded(cfg, device, rank, world, batch=65536, group=None):
+    """Build the model described by an oracle-style cfg with row-sharded tables on this rank."""
+    import copy
+    from .config import model_from_cfg as build_model
+
+    local_cfg = copy.deepcopy(cfg)
+    for col in local_cfg["linear_columns"] + local_cfg["dnn_columns"]:
+        if col["type"] == "sparse":
+            col["vocab"] = max_local_rows(col["vocab"], world)
+    model = build_model(local_cfg, device, table_grad="rowwise")
+    attach_shards(model, cfg, rank, world, batch, group)
+    return model, "dp%d: tower data-parallel (NCCL all-reduce), tables row-sharded (NVLink P2P gather/push)" % world
+
+
+def attach_shards(model, logical_cfg, rank, world, batch, group=None):
+    """Move the (local-size) tables of `model` into a peer-shared arena and switch its fused input
+    to the sharded plan.  `logical_cfg` carries the full vocabulary sizes."""
+    from .inputs import split_columns
+    dev = next(model.parameters()).device
+    sparse, dense, varlen = split_columns(model.dnn_feature_columns)
+    lsparse, ldense, lvarlen = split_columns(model.linear_feature_columns)
+    if varlen or lvarlen:
+        raise NotImplementedError("VarLenSparseFeat tables are not sharded")
+    logical = {c["name"]: c["vocab"] for c in logical_cfg["linear_columns"] + logical_cfg["dnn_columns"]
+               if c["type"] == "sparse"}
+    emb_vocab = [logical[c.name] for c in sparse]
+    lin_vocab = [logical[c.name] for c in lsparse]
+    D = sparse[0].embedding_dim if sparse else 1
+    layout = ArenaLayout(emb_vocab, lin_vocab, D, world, batch)
+    arena = P2PArena(layout.nbytes, dev, group)
+    with torch.no_grad():
+        for f, c in enumerate(sparse):
+            w = model.embedding_dict[c.embedding_name].weight
+            view = arena.view(layout.emb_off[f], (layout.emb_rows[f], D))
+            view.copy_(w.data[:layout.emb_rows[f]])
+            w.data = view
+        for f, c in enumerate(lsparse):
+            w = model.linear_model.embedding_dict[c.embedding_name].weight
+            view = arena.view(layout.lin_off[f], (layout.lin_rows[f], 1))
+            view.copy_(w.data[:layout.lin_rows[f]])
+            w.data = view
+    base = model._gather_plan(dev)
+    fi = model.feature_index
+    emb_slots = [(model.embedding_dict[c.embedding_name].weight, fi[c.name][0], logical[c.name]) for c in sparse]
+    lin_slots = [(model.linear_model.embedding_dict[c.embedding_name].weight, fi[c.name][0], logical[c.name])
+                 for c in lsparse]
+    plan = ShardedPlan(emb_slots, lin_slots, base.dense_cols.tolist(), base.lin_dense_cols.tolist(), D, dev)
+    plan.varlen, plan.lin_varlen, plan.n_sparse = [], [], len(sparse)
+    plan.setup_shards(arena, layout, rank, world, emb_vocab, lin_vocab)
+    model._plan = plan
+    model.table_grad = "sharded"
+    model.sharded = ShardedRuntime(model, plan, group)
+    dist.barrier(group=group)       # every arena is mapped before the first remote access
+    return model

@@ -93,7 +93,8 @@ int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B,
  *                      hash_keys/hash_vals: int32 [n_cols*H] scratch, n_uniq: int32 [n_cols];
  *                      all three are (re)initialised inside.  Entries u >= n_uniq[c] get
  *                      uniq = 0, cnt = 0.
- *   ctr_scatter_bwd_rowwise: emb_rowgrad[f] is a [B, D] buffer, lin_rowgrad[f] a [B] buffer;
+ *   ctr_scatter_bwd_rowwise: field f writes the [B, D] buffer at emb_rowgrad + f*emb_rowgrad_stride
+ *                      (linear field f the [B] buffer at lin_rowgrad + f*lin_rowgrad_stride);
  *                      row u of field f receives the summed gradient of uniq id u of the plan
  *                      column emb_plan_col[f]; rows u >= n_uniq are zero-filled so that
  *                      (uniq, rowgrad) is always a valid padded sparse-COO pair of length B.
@@ -105,8 +106,10 @@ int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_cols, const in
                     int32_t* err_flag, void* stream);
 int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv, const int32_t* cnt,
                             const int32_t* n_uniq,
-                            int n_emb, int D, float* const* emb_rowgrad, const int32_t* emb_plan_col,
-                            int n_lin, float* const* lin_rowgrad, const int32_t* lin_plan_col,
+                            int n_emb, int D, float* emb_rowgrad, int64_t emb_rowgrad_stride,
+                            const int32_t* emb_plan_col,
+                            int n_lin, float* lin_rowgrad, int64_t lin_rowgrad_stride,
+                            const int32_t* lin_plan_col,
                             const float* blk, int64_t ld_blk,
                             const float* d_blk, int64_t ld_dblk,
                             const float* g_fm, const float* g_lin, void* stream);
@@ -130,8 +133,10 @@ int ctr_p2p_export(void* ptr, unsigned char* handle64);
 int ctr_p2p_open(const unsigned char* handle64, void** peer_ptr);
 int ctr_p2p_close(void* peer_ptr);
 int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
-                     int n_emb, int D, const float* const* emb_rowgrad, const int32_t* emb_plan_col,
-                     int n_lin, const float* const* lin_rowgrad, const int32_t* lin_plan_col,
+                     int n_emb, int D, const float* emb_rowgrad, int64_t emb_rowgrad_stride,
+                     const int32_t* emb_plan_col,
+                     int n_lin, const float* lin_rowgrad, int64_t lin_rowgrad_stride,
+                     const int32_t* lin_plan_col,
                      int32_t* const* recv_count, int32_t* const* recv_ids,
                      float* const* recv_emb_rows, float* const* recv_lin_rows,
                      int64_t cap, int32_t* err_flag, void* stream);

@@ -46,29 +46,14 @@ def rel_err(a, b):
 
 
 def build_columns(cols):
-    from deepctr_torch_b200.inputs import DenseFeat, SparseFeat, VarLenSparseFeat
-    out = []
-    for c in cols:
-        if c["type"] == "sparse":
-            out.append(SparseFeat(c["name"], c["vocab"], embedding_dim=c["dim"], embedding_name=c["embedding_name"]))
-        elif c["type"] == "dense":
-            out.append(DenseFeat(c["name"], c["dimension"]))
-        else:
-            sf = SparseFeat(c["name"], c["vocab"], embedding_dim=c["dim"], embedding_name=c["embedding_name"])
-            out.append(VarLenSparseFeat(sf, maxlen=c["maxlen"], combiner=c["combiner"], length_name=c["length_name"]))
-    return out
+    from deepctr_torch_b200.config import columns_from_cfg
+    return columns_from_cfg(cols)
 
 
 def build_model(cfg, device="cpu", **extra):
     """Instantiate the deepctr_torch_b200 model described by an oracle cfg dict."""
-    from deepctr_torch_b200 import models
-    cls = getattr(models, cfg["model"])
-    kw = dict(cfg["kwargs"])
-    for k in ("dnn_hidden_units", "cin_layer_size"):
-        if k in kw:
-            kw[k] = tuple(kw[k])
-    kw.update(extra)
-    return cls(build_columns(cfg["linear_columns"]), build_columns(cfg["dnn_columns"]), device=device, **kw)
+    from deepctr_torch_b200.config import model_from_cfg
+    return model_from_cfg(cfg, device, **extra)
 
 
 def capture_logit(model, X):

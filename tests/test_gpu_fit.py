@@ -53,3 +53,31 @@ def test_fit_with_callbacks_and_rowwise_sgd(tmp_path):
     assert "val_auc" in hist.history and len(hist.history["loss"]) >= 1
     state = torch.load(tmp_path / "w.ckpt")
     m.load_state_dict(state)
+
+
+def test_graphed_step_matches_eager():
+    """The CUDA-graph replay of one step produces the same loss and gradients as the eager step."""
+    from helpers import load_case
+    c = load_case("deepfm_criteo_shape")
+    results = []
+    for graphed in (False, True):
+        m = build_model(c["cfg"], "cuda:0", table_grad="rowwise")
+        m.load_state_dict(c["state"])
+        m.train()
+        X, y = c["X"].cuda(), c["y"].cuda()
+        if graphed:
+            step = m.make_graphed_step(X.shape[0])
+            loss = step(X, y)
+            loss = step(X, y)            # replaying twice must not accumulate
+        else:
+            y_pred = m(X)
+            loss = torch.nn.functional.binary_cross_entropy(y_pred.squeeze(1), y, reduction="sum")
+            loss.backward()
+        m.check_ids()
+        grads = {k: (p.grad.to_dense() if p.grad.is_sparse else p.grad).detach().cpu().clone()
+                 for k, p in m.named_parameters()}
+        results.append((float(loss), grads))
+    assert abs(results[0][0] - results[1][0]) <= 1e-5 * abs(results[0][0])
+    for k in results[0][1]:
+        a, b = results[0][1][k], results[1][1][k]
+        assert (a - b).abs().max() <= 1e-5 * max(1e-6, a.abs().max()), k

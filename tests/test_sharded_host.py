@@ -1,0 +1,75 @@
+"""Host logic of the row-sharded multi-GPU path, on CPU with gloo (world_size 2): shard layout
+arithmetic, arena layout symmetry, gather-on-save / scatter-on-load of reference-compatible
+state_dicts through torch.distributed."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deepctr_torch_b200 import sharded
+
+
+def test_shard_unshard_roundtrip():
+    for vocab in (1, 2, 7, 8, 1000, 1538462):
+        for world in (1, 2, 3, 8):
+            full = torch.arange(vocab * 2, dtype=torch.float32).view(vocab, 2)
+            shards = [sharded.shard_rows(full, r, world) for r in range(world)]
+            assert [s.shape[0] for s in shards] == [sharded.local_rows(vocab, r, world) for r in range(world)]
+            assert sum(s.shape[0] for s in shards) == vocab
+            assert max(s.shape[0] for s in shards) == sharded.max_local_rows(vocab, world) or vocab < world
+            for r, s in enumerate(shards):       # local index = id // world, owner = id % world
+                for j in range(0, s.shape[0], max(1, s.shape[0] // 5)):
+                    assert s[j, 0].item() == (j * world + r) * 2
+            assert torch.equal(sharded.unshard_rows(shards, vocab), full)
+
+
+def test_arena_layout_is_rank_independent_and_disjoint():
+    L = sharded.ArenaLayout([1000, 77, 5], [1000, 77], dim=16, world=4, batch=64)
+    spans = []
+    for f in range(3):
+        spans.append((L.emb_off[f], L.emb_rows[f] * 16 * 4))
+    for f in range(2):
+        spans.append((L.lin_off[f], L.lin_rows[f] * 4))
+    for par in range(2):
+        r = L.recv[par]
+        spans += [(r["count"], 5 * 4), (r["ids"], 5 * L.cap * 4), (r["emb"], 3 * L.cap * 16 * 4), (r["lin"], 2 * L.cap * 4)]
+    spans.sort()
+    for (o1, n1), (o2, _) in zip(spans, spans[1:]):
+        assert o1 + n1 <= o2
+        assert o1 % 256 == 0
+    assert spans[-1][0] + spans[-1][1] <= L.nbytes
+    assert L.cap == 64 * 4
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        vocabs = {"embedding_dict.C1.weight": 11, "linear_model.embedding_dict.C1.weight": 11,
+                  "embedding_dict.C2.weight": 4}
+        full = {"embedding_dict.C1.weight": torch.randn(11, 8, generator=g),
+                "linear_model.embedding_dict.C1.weight": torch.randn(11, 1, generator=g),
+                "embedding_dict.C2.weight": torch.randn(4, 8, generator=g),
+                "dnn.linears.0.weight": torch.randn(5, 3, generator=g)}
+        local = sharded.scatter_full_state_dict(full, vocabs, rank, world)
+        assert local["embedding_dict.C1.weight"].shape[0] == sharded.max_local_rows(11, world)
+        assert torch.equal(local["embedding_dict.C1.weight"][:sharded.local_rows(11, rank, world)],
+                           full["embedding_dict.C1.weight"][rank::world])
+        back = sharded.gather_full_state_dict(local, vocabs)
+        ok = all(torch.equal(back[k], full[k]) for k in full)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_state_dict_gather_scatter_gloo_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
