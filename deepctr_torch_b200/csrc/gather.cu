@@ -13,10 +13,11 @@ namespace {
 
 constexpr int kMaxSmemSlots = 256;  // slot metadata staged in shared memory up to this many fields
 
-__device__ __forceinline__ int64_t decode_id(float xv, int vocab, int32_t* err_flag) {
-    // fp32 -> int64 by truncation, exactly like `.long()` (reference basemodel.py:369)
-    int64_t id = (int64_t)xv;
-    if (id < 0 || id >= (int64_t)vocab) {
+__device__ __forceinline__ int decode_id(float xv, int vocab, int32_t* err_flag) {
+    // fp32 -> integer by truncation, exactly like `.long()` (reference basemodel.py:369); ids live in
+    // [0, vocab) with vocab < 2^31, out-of-range / negative / huge values trip the unsigned compare
+    int id = __float2int_rz(xv);
+    if ((unsigned)id >= (unsigned)vocab) {
         if (err_flag) atomicOr(err_flag, 1);
         id = 0;
     }
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rslot = lane / LPR;
-    const int D = a.D;
+    constexpr int D = LPR * 4;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool one_chunk = a.n_emb <= STEPS * RPW;
@@ -112,10 +113,10 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                 v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (f < a.n_emb) {
                     const float raw = (f0 == 0) ? xv[s] : __ldg(xrow + s_col[f]);
-                    const int64_t id = decode_id(raw, s_voc[f], a.err_flag);
-                    const float* tab = (G == 1) ? s_tab[f] : s_tab[f * G + (int)(id % G)];
-                    const int64_t row = (G == 1) ? id : id / G;
-                    v[s] = ld_stream4(tab + row * D + sub * 4);
+                    const int id = decode_id(raw, s_voc[f], a.err_flag);
+                    const float* tab = (G == 1) ? s_tab[f] : s_tab[f * G + id % G];
+                    const int row = (G == 1) ? id : id / G;
+                    v[s] = ld_stream4(tab + (size_t)row * D + sub * 4);
                 }
             }
 #pragma unroll
@@ -149,9 +150,8 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
         float lp = 0.f;
         if (lin_fast) {
             if (lane < a.n_lin) {
-                const int64_t id = decode_id(xl, a.lin_vocab[lane], a.err_flag);
-                lp = (G == 1) ? __ldg(a.lin_tables[lane] + id)
-                              : __ldg(a.lin_tables[lane * G + (int)(id % G)] + id / G);
+                const int id = decode_id(xl, a.lin_vocab[lane], a.err_flag);
+                lp = (G == 1) ? __ldg(a.lin_tables[lane] + id) : __ldg(a.lin_tables[lane * G + id % G] + id / G);
             }
         } else {
             for (int f = lane; f < a.n_lin; f += 32) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rslot = lane / LPR;
-    const int D = a.D;
+    constexpr int D = LPR * 4;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool one_chunk = a.n_emb <= STEPS * RPW;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
             float4 r[STEPS];
             int u[STEPS];
             int c[STEPS];
-            int64_t id[STEPS];
+            int id[STEPS];
 #pragma unroll
             for (int s = 0; s < STEPS; ++s) {
                 const int f = f0 + s * RPW + rslot;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
                         if (c[s] == 1) st_stream4(dst, r[s]);
                         else red_add4(dst, r[s]);
                     } else {
-                        red_add4(a.emb_out[f] + id[s] * D + sub * 4, r[s]);
+                        red_add4(a.emb_out[f] + (size_t)id[s] * D + sub * 4, r[s]);
                     }
                 }
             }
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
                     if (c == 1) *dst = gl;
                     else atomicAdd(dst, gl);
                 } else {
-                    const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], nullptr);
+                    const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], nullptr);
                     atomicAdd(a.lin_out[f] + id, gl);
                 }
             }

@@ -10,22 +10,31 @@
 // instructions per K atom into ONE fp32 accumulator in tensor memory (error ~2^-21 per product).
 //
 // CTA = 128 x BN output tile (BN multiple of 32, <= 256), 9 warps:
-//   warps 0-7  producers: LDG (any strides, bounds, optional act'(mask) prologue) -> hi/lo split
-//              -> STS.128 into the canonical K-major no-swizzle UMMA layout (8x16B core matrices),
-//              fence.proxy.async + mbarrier arrive;  after the main loop the same warps run the
-//              epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias/activation/mask -> global.
+//   warps 0-7  producers: global -> registers (128-bit loads) -> hi/lo split -> STS.128 into the
+//              canonical no-swizzle UMMA core-matrix layout, fence.proxy.async + mbarrier arrive;
+//              after the main loop the same warps run the epilogue: tcgen05.ld (32 lanes x 16
+//              columns) -> bias/activation/mask -> global.
 //   warp 8     TMEM alloc/dealloc; one elected lane issues the MMAs and tcgen05.commit's.
+// Operand staging modes (chosen per operand on the host):
+//   K-contiguous  (forward X, W; dgrad dY): 128-bit loads along k -> K-major core matrices
+//   MN-contiguous (wgrad dY^T, X^T; dgrad W^T): 128-bit loads along m/n -> MN-major core matrices
+//                 (instruction descriptor a_major/b_major = 1), no register transpose needed
+//   scalar        any strides / unaligned: 32-bit loads -> K-major core matrices
 // Pipeline: `stages` shared-memory stages of 32 fp32 of K (full/empty mbarriers), split-K across
 // gridDim.z with fp32 atomics for the weight-gradient shapes.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                 // fp32 elements of K per stage = 8 chunks of 16 B
+constexpr int TC_BK = 32;                 // fp32 elements of K per stage
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_PROD_WARPS + 1) * 32;
+
+enum { LD_SCALAR = 0, LD_KVEC = 1, LD_MNVEC = 2 };
 
 struct TcParams {
     GemmArgs g;
@@ -33,7 +42,102 @@ struct TcParams {
     int BN;               // N tile (multiple of 32)
     int stages;
     int tmem_cols;        // power of two >= max(32, BN)
+    int a_mode, b_mode;
 };
+
+__device__ __forceinline__ float4 mask4(float4 v, float4 y, int act) {
+    v.x *= act_grad_from_y(act, y.x);
+    v.y *= act_grad_from_y(act, y.y);
+    v.z *= act_grad_from_y(act, y.z);
+    v.w *= act_grad_from_y(act, y.w);
+    return v;
+}
+
+__device__ __forceinline__ void split_store(float* hi_ptr, float* lo_ptr, float4 v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(hi_ptr) = hi;
+    *reinterpret_cast<float4*>(lo_ptr) = lo;
+}
+
+// Stage one operand tile (R rows x 32 k) of matrix P(row, k) = P[row*s_row + k*s_k] into shared
+// memory as hi/lo, in the layout selected by `mode`.
+template <int MODE>
+__device__ __forceinline__ void stage_operand(const float* __restrict__ P, int64_t s_row, int64_t s_k,
+                                              const float* __restrict__ mask, int64_t m_row, int64_t m_k,
+                                              int mask_act, int64_t row0, int64_t n_rows, int64_t k0,
+                                              int64_t kend, int R, float* hi, float* lo, int warp, int lane) {
+    if (MODE == LD_MNVEC) {
+        // unit = 4 consecutive rows; lane -> (k within group of 8, unit within 4); MN-major layout:
+        // float offset = ((g * (R/4) + unit) * 8 + kk) * 4
+        const int kk = lane & 7, ui = lane >> 3;
+        for (int unit = warp * 4 + ui; unit < R / 4; unit += TC_PROD_WARPS * 4) {
+            const int64_t row = row0 + unit * 4;
+#pragma unroll
+            for (int g = 0; g < TC_BK / 8; ++g) {
+                const int64_t k = k0 + g * 8 + kk;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < kend) {
+                    if (row + 3 < n_rows) {
+                        v = __ldg(reinterpret_cast<const float4*>(P + row + k * s_k));
+                        if (mask) v = mask4(v, __ldg(reinterpret_cast<const float4*>(mask + row + k * m_k)), mask_act);
+                    } else {
+                        float t[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int e = 0; e < 4; ++e)
+                            if (row + e < n_rows) {
+                                t[e] = __ldg(P + row + e + k * s_k);
+                                if (mask) t[e] *= act_grad_from_y(mask_act, __ldg(mask + row + e + k * m_k));
+                            }
+                        v = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+                const int off = ((g * (R / 4) + unit) * 8 + kk) * 4;
+                split_store(hi + off, lo + off, v);
+            }
+        }
+    } else {
+        // K-major layout: float offset = (c * R + r) * 4, c = 16-byte chunk along k (0..7)
+        const int r_lo = lane & 7, c_lo = lane >> 3;
+        for (int U = warp; U < (R / 8) * 2; U += TC_PROD_WARPS) {
+            const int r = (U >> 1) * 8 + r_lo;
+            const int c = (U & 1) * 4 + c_lo;
+            const int64_t row = row0 + r;
+            const int64_t k = k0 + c * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < n_rows && k < kend) {
+                if (MODE == LD_KVEC && k + 3 < kend) {
+                    v = __ldg(reinterpret_cast<const float4*>(P + row * s_row + k));
+                    if (mask) v = mask4(v, __ldg(reinterpret_cast<const float4*>(mask + row * m_row + k)), mask_act);
+                } else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int e = 0; e < 4; ++e)
+                        if (k + e < kend) {
+                            t[e] = __ldg(P + row * s_row + (k + e) * s_k);
+                            if (mask) t[e] *= act_grad_from_y(mask_act, __ldg(mask + row * m_row + (k + e) * m_k));
+                        }
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            const int off = (c * R + r) * 4;
+            split_store(hi + off, lo + off, v);
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_dispatch(int mode, const float* P, int64_t s_row, int64_t s_k,
+                                               const float* mask, int64_t m_row, int64_t m_k, int mask_act,
+                                               int64_t row0, int64_t n_rows, int64_t k0, int64_t kend, int R,
+                                               float* hi, float* lo, int warp, int lane) {
+    if (mode == LD_KVEC)
+        stage_operand<LD_KVEC>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
+    else if (mode == LD_MNVEC)
+        stage_operand<LD_MNVEC>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
+    else
+        stage_operand<LD_SCALAR>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -62,20 +166,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_PROD_WARPS) {   // TMEM allocation by the MMA warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == TC_PROD_WARPS) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < TC_PROD_WARPS) {
         // ------------------------------ producers ------------------------------------------
-        const int r_lo = lane & 7, c_lo = lane >> 3;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -86,120 +184,94 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
             float* b_hi = reinterpret_cast<float*>(st + 2 * a_tile);
             float* b_lo = reinterpret_cast<float*>(st + 2 * a_tile + b_tile);
             const int64_t k0 = kbeg + (int64_t)kb * TC_BK;
-            // A: 16 row groups x 2 chunk halves = 32 units of (8 rows x 4 chunks)
-            for (int U = warp; U < (TC_BM / 8) * 2; U += TC_PROD_WARPS) {
-                const int r = (U >> 1) * 8 + r_lo;
-                const int c = (U & 1) * 4 + c_lo;
-                const int64_t m = m0 + r;
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int64_t k = k0 + c * 4 + e;
-                    float x = 0.f;
-                    if (m < g.M && k < kend) {
-                        x = __ldg(g.A + m * g.sam + k * g.sak);
-                        if (g.amask) x *= act_grad_from_y(g.amask_act, __ldg(g.amask + m * g.smm + k * g.smk));
-                    }
-                    v[e] = x;
-                }
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
-                const int off = (c * TC_BM + r) * 4;     // floats: chunk-major, 16 B per row
-                *reinterpret_cast<float4*>(a_hi + off) = hi;
-                *reinterpret_cast<float4*>(a_lo + off) = lo;
-            }
-            for (int U = warp; U < (BN / 8) * 2; U += TC_PROD_WARPS) {
-                const int r = (U >> 1) * 8 + r_lo;
-                const int c = (U & 1) * 4 + c_lo;
-                const int64_t n = n0 + r;
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int64_t k = k0 + c * 4 + e;
-                    float x = 0.f;
-                    if (n < g.N && k < kend) {
-                        x = __ldg(g.B + n * g.sbn + k * g.sbk);
-                        if (g.bmask) x *= act_grad_from_y(g.bmask_act, __ldg(g.bmask + n * g.sbmn + k * g.sbmk));
-                    }
-                    v[e] = x;
-                }
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
-                const int off = (c * BN + r) * 4;
-                *reinterpret_cast<float4*>(b_hi + off) = hi;
-                *reinterpret_cast<float4*>(b_lo + off) = lo;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+            stage_dispatch(p.a_mode, g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, m0, g.M, k0, kend,
+                           TC_BM, a_hi, a_lo, warp, lane);
+            stage_dispatch(p.b_mode, g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, n0, g.N, k0, kend,
+                           BN, b_hi, b_lo, warp, lane);
+            fence_async_smem();                                           // generic -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
         }
         // ------------------------------ epilogue -------------------------------------------
         mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         const int quad = warp & 3;                       // TMEM lane quadrant of this warp
         const int half = warp >> 2;                      // column half
         const int64_t m = m0 + quad * 32 + lane;
         const bool split = gridDim.z > 1;
         const int col_beg = half * (BN / 2), col_end = col_beg + BN / 2;
+        const bool vec_store = !split && !g.accumulate && (g.ldc % 4 == 0) &&
+                               ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && g.epilogue != EPI_CROSS;
         for (int c0 = col_beg; c0 < col_end; c0 += 16) {
             uint32_t raw[16];
             tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < g.M) {
+            tmem_ld_wait();
+            if (m < g.M && n0 + c0 < g.N) {
+                float out[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int64_t n = n0 + c0 + j;
-                    if (n >= g.N) break;
                     float v = __uint_as_float(raw[j]);
-                    float* cp = g.C + m * g.ldc + n;
-                    switch (g.epilogue) {
-                        case EPI_BIAS_ACT:
-                            if (g.bias) v += __ldg(g.bias + n);
-                            v = act_apply(g.act, v);
-                            break;
-                        case EPI_MUL_ACTGRAD:
-                            v *= act_grad_from_y(g.act, __ldg(g.aux + m * g.ldaux + n));
-                            break;
-                        case EPI_CROSS: {
-                            const float u = v + __ldg(g.bias + n);
-                            if (g.out2) g.out2[m * g.ldout2 + n] = u;
-                            v = __ldg(g.aux + m * g.ldaux + n) * u + __ldg(g.aux2 + m * g.ldaux2 + n);
-                            break;
+                    if (n < g.N) {
+                        switch (g.epilogue) {
+                            case EPI_BIAS_ACT:
+                                if (g.bias) v += __ldg(g.bias + n);
+                                v = act_apply(g.act, v);
+                                break;
+                            case EPI_MUL_ACTGRAD:
+                                v *= act_grad_from_y(g.act, __ldg(g.aux + m * g.ldaux + n));
+                                break;
+                            case EPI_CROSS: {
+                                const float u = v + __ldg(g.bias + n);
+                                if (g.out2) g.out2[m * g.ldout2 + n] = u;
+                                v = __ldg(g.aux + m * g.ldaux + n) * u + __ldg(g.aux2 + m * g.ldaux2 + n);
+                                break;
+                            }
+                            default: break;
                         }
-                        default: break;
                     }
-                    if (split) atomicAdd(cp, v);
-                    else if (g.accumulate) *cp += v;
-                    else *cp = v;
+                    out[j] = v;
+                }
+                float* crow = g.C + m * g.ldc + n0 + c0;
+                if (vec_store && n0 + c0 + 15 < g.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(crow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n0 + c0 + j < g.N) {
+                            if (split) atomicAdd(crow + j, out[j]);
+                            else if (g.accumulate) crow[j] += out[j];
+                            else crow[j] = out[j];
+                        }
+                    }
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
     } else {
         // ------------------------------ MMA issuer -----------------------------------------
-        // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13),
-        // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc = tf32_idesc(BN) | ((p.a_mode == LD_MNVEC) ? (1u << 15) : 0u) |
+                               ((p.b_mode == LD_MNVEC) ? (1u << 16) : 0u);
+        // per K atom (8 k): K-major tiles advance by two 16-byte chunks (2 * R * 16 B);
+        // MN-major tiles by one 8-k group ((R/4) * 128 B)
+        const uint32_t a_step = (p.a_mode == LD_MNVEC) ? (TC_BM / 4) * 128u : 2u * TC_BM * 16u;
+        const uint32_t b_step = (p.b_mode == LD_MNVEC) ? ((uint32_t)BN / 4) * 128u : 2u * (uint32_t)BN * 16u;
+        const uint32_t a_lbo = (p.a_mode == LD_MNVEC) ? (TC_BM / 4) * 128u : TC_BM * 16u;
+        const uint32_t b_lbo = (p.b_mode == LD_MNVEC) ? ((uint32_t)BN / 4) * 128u : (uint32_t)BN * 16u;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
             mbar_wait(&full_bar[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_fence_after();
             if (lane == 0) {
                 const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
                 const uint32_t a_hi = base, a_lo = base + a_tile, b_hi = base + 2 * a_tile,
                                b_lo = base + 2 * a_tile + b_tile;
-                const uint32_t a_lbo = TC_BM * 16, b_lbo = (uint32_t)BN * 16;   // stride between the two K chunks
 #pragma unroll
                 for (int j = 0; j < TC_BK / 8; ++j) {
-                    const uint32_t ao = (uint32_t)(2 * j) * a_lbo, bo = (uint32_t)(2 * j) * b_lbo;
+                    const uint32_t ao = (uint32_t)j * a_step, bo = (uint32_t)j * b_step;
                     const uint64_t dah = make_smem_desc(a_hi + ao, a_lbo, 128);
                     const uint64_t dal = make_smem_desc(a_lo + ao, a_lbo, 128);
                     const uint64_t dbh = make_smem_desc(b_hi + bo, b_lbo, 128);
@@ -216,17 +288,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     }
     __syncthreads();
     if (warp == TC_PROD_WARPS) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                     : "memory");
+        tc_fence_after();
+        tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
-}  // namespace
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-bool gemm_tc_supported(const GemmArgs& g) {
-    return g.M > 0 && g.N > 0 && g.K > 0;
+// pick the staging mode of one operand P(row,k) = P[row*s_row + k*s_k] (+ optional mask)
+int pick_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int64_t m_row, int64_t m_k) {
+    const char* e = getenv("CTR_TC_LOAD");
+    if (e && e[0] == 's') return LD_SCALAR;
+    if (s_k == 1 && s_row % 4 == 0 && aligned16(P) &&
+        (!mask || (m_k == 1 && m_row % 4 == 0 && aligned16(mask))))
+        return LD_KVEC;
+    if (s_row == 1 && s_k % 4 == 0 && aligned16(P) &&
+        (!mask || (m_row == 1 && m_k % 4 == 0 && aligned16(mask))))
+        return (e && e[0] == 'k') ? LD_SCALAR : LD_MNVEC;
+    return LD_SCALAR;
 }
+
+}  // namespace
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     TcParams p;
@@ -242,6 +324,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.BN = BN;
     p.tmem_cols = 32;
     while (p.tmem_cols < BN) p.tmem_cols <<= 1;
+    p.a_mode = pick_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk);
+    p.b_mode = pick_mode(g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk);
     const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)BN * TC_BK * 4;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
@@ -270,10 +354,10 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (splits > 1 && !g.accumulate)
         CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
     const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static bool configured = false;
+    if (!configured) {
         CTR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-        configured = 220 * 1024;
+        configured = true;
     }
     dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)splits);
     gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
