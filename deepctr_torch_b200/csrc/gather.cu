@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
             lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
         if (a.blk) {
             float* drow = a.blk + b * a.ld_blk + (int64_t)a.n_emb * D;
-            for (int k = lane; k < a.n_dense; k += 32) drow[k] = __ldg(xrow + a.dense_cols[k]);
+            const int n_pad = (int)(a.ld_blk - (int64_t)a.n_emb * D);      // dense columns, then zeros up to ld
+            for (int k = lane; k < n_pad; k += 32) drow[k] = (k < a.n_dense) ? __ldg(xrow + a.dense_cols[k]) : 0.f;
         }
         if (a.lin) {
             lp = warp_sum(lp);
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
                 a.blk[b * a.ld_blk + i] = __ldg(a.emb_tables[f * G + (int)(id % G)] + (id / G) * D + d);
             }
             float* drow = a.blk + b * a.ld_blk + (int64_t)total;
-            for (int k = lane; k < a.n_dense; k += 32) drow[k] = __ldg(xrow + a.dense_cols[k]);
+            const int n_pad = (int)(a.ld_blk - total);
+            for (int k = lane; k < n_pad; k += 32) drow[k] = (k < a.n_dense) ? __ldg(xrow + a.dense_cols[k]) : 0.f;
         }
         float lp = 0.f;
         for (int f = lane; f < a.n_lin; f += 32) {
@@ -445,32 +447,27 @@ __global__ void __launch_bounds__(256) rowgrad_prep_kernel(int64_t B, const int3
                                                            const int32_t* emb_plan, int n_lin,
                                                            float* lin_rg, int64_t lin_rg_stride,
                                                            const int32_t* lin_plan, int force_all) {
+    // one thread per (field, unique slot): a single cnt lookup decides the whole row
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int D4 = (D % 4 == 0) ? D / 4 : 0;
-    if (D4) {
-        const int64_t total = (int64_t)n_emb * B * D4;
-        for (int64_t i = tid; i < total; i += nthreads) {
-            const int sub = (int)(i % D4);
-            const int64_t u = (i / D4) % B;
-            const int f = (int)(i / ((int64_t)D4 * B));
-            if (force_all || __ldg(cnt + (int64_t)emb_plan[f] * B + u) != 1)
-                *reinterpret_cast<float4*>(emb_rg + f * emb_rg_stride + u * D + sub * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    } else {
-        const int64_t total = (int64_t)n_emb * B * D;
-        for (int64_t i = tid; i < total; i += nthreads) {
-            const int d = (int)(i % D);
-            const int64_t u = (i / D) % B;
-            const int f = (int)(i / ((int64_t)D * B));
-            if (force_all || cnt[(int64_t)emb_plan[f] * B + u] != 1) emb_rg[f * emb_rg_stride + u * D + d] = 0.f;
-        }
-    }
-    const int64_t total_l = (int64_t)n_lin * B;
-    for (int64_t i = tid; i < total_l; i += nthreads) {
-        const int64_t u = i % B;
+    const int64_t total = (int64_t)(n_emb + n_lin) * B;
+    const bool vec = (D % 4 == 0) && (emb_rg_stride % 4 == 0);
+    for (int64_t i = tid; i < total; i += nthreads) {
         const int f = (int)(i / B);
-        if (force_all || __ldg(cnt + (int64_t)lin_plan[f] * B + u) != 1) lin_rg[f * lin_rg_stride + u] = 0.f;
+        const int64_t u = i - (int64_t)f * B;
+        if (f < n_emb) {
+            if (force_all || __ldg(cnt + (int64_t)emb_plan[f] * B + u) != 1) {
+                float* row = emb_rg + f * emb_rg_stride + u * D;
+                if (vec) {
+                    for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(row + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    for (int d = 0; d < D; ++d) row[d] = 0.f;
+                }
+            }
+        } else {
+            const int fl = f - n_emb;
+            if (force_all || __ldg(cnt + (int64_t)lin_plan[fl] * B + u) != 1) lin_rg[fl * lin_rg_stride + u] = 0.f;
+        }
     }
 }
 
@@ -779,8 +776,7 @@ extern "C" int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t
         (n_emb == 0 || (emb_rowgrad_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(emb_rowgrad) & 15) == 0));
     const int force_all = (lpr > 0 && aligned) ? 0 : 1;
     {
-        int64_t work = (int64_t)n_emb * B * (D % 4 == 0 ? D / 4 : D);
-        if ((int64_t)n_lin * B > work) work = (int64_t)n_lin * B;
+        const int64_t work = (int64_t)(n_emb + n_lin) * B;
         int64_t blocks = ceil_div64(work, 256);
         const int64_t cap = (int64_t)ctr_sm_count() * 8;
         if (blocks > cap) blocks = cap;

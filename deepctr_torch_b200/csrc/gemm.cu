@@ -190,6 +190,48 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
     }
 }
 
+// contiguous rows (san == 1), 128-bit loads: thread = (column quad, row lane)
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict__ A, int64_t sam,
+                                                         const float* __restrict__ mask, int64_t smm,
+                                                         int mask_act, const float* __restrict__ w,
+                                                         int64_t M, int nq, int64_t rows_per_block,
+                                                         float* out) {
+    extern __shared__ float4 s_part[];           // [ylanes][nq_tile]
+    const int xq = blockDim.x;                   // column quads per block
+    const int q = blockIdx.x * xq + threadIdx.x;
+    const int64_t mbeg = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t mend = (mbeg + rows_per_block < M) ? mbeg + rows_per_block : M;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) {
+        for (int64_t m = mbeg + threadIdx.y; m < mend; m += blockDim.y) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(A + m * sam) + q);
+            if (mask) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(mask + m * smm) + q);
+                v.x *= act_grad_from_y(mask_act, y.x); v.y *= act_grad_from_y(mask_act, y.y);
+                v.z *= act_grad_from_y(mask_act, y.z); v.w *= act_grad_from_y(mask_act, y.w);
+            }
+            if (w) {
+                const float ww = __ldg(w + m);
+                v.x *= ww; v.y *= ww; v.z *= ww; v.w *= ww;
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    s_part[threadIdx.y * xq + threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && q < nq) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < (int)blockDim.y; ++i) {
+            const float4 v = s_part[i * xq + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        atomicAdd(out + q * 4 + 0, t.x);
+        atomicAdd(out + q * 4 + 1, t.y);
+        atomicAdd(out + q * 4 + 2, t.z);
+        atomicAdd(out + q * 4 + 3, t.w);
+    }
+}
+
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const float* __restrict__ H, int64_t ldh,
                                                          const float* __restrict__ w, int64_t B,
                                                          int N, float* out, int accumulate) {
@@ -314,6 +356,26 @@ int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, i
                   cudaStream_t st) {
     CTR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
     if (M <= 0 || N <= 0) return 0;
+    if (san == 1 && N % 4 == 0 && sam % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+        (!mask || (smn == 1 && smm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0))) {
+        const int nq = (int)(N / 4);
+        int xq = 1;
+        while (xq < nq && xq < 64) xq <<= 1;
+        const int ylanes = 256 / xq;
+        const int64_t gx = ceil_div64(nq, xq);
+        int64_t gy = ceil_div64(4LL * ctr_sm_count(), gx);
+        const int64_t max_gy = ceil_div64(M, (int64_t)ylanes * 8);
+        if (gy > max_gy) gy = max_gy;
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        const int64_t rows_per_block = ceil_div64(M, gy);
+        gy = ceil_div64(M, rows_per_block);
+        dim3 grid((unsigned)gx, (unsigned)gy), block(xq, ylanes);
+        colsum_vec_kernel<<<grid, block, sizeof(float4) * 256, st>>>(A, sam, mask, smm, mask_act, w, M, nq,
+                                                                     rows_per_block, out);
+        CTR_LAUNCH_OK("colsum_vec_kernel");
+        return 0;
+    }
     const int64_t gx = ceil_div64(N, 32);
     int64_t gy = ceil_div64(4LL * ctr_sm_count(), gx);
     const int64_t max_gy = ceil_div64(M, 64);

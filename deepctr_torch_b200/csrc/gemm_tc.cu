@@ -34,7 +34,7 @@ constexpr int TC_BK = 32;                 // fp32 elements of K per stage
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_PROD_WARPS + 1) * 32;
 
-enum { LD_SCALAR = 0, LD_KVEC = 1, LD_MNVEC = 2 };
+enum { LD_SCALAR = 0, LD_KVEC = 1, LD_TRANS = 2 };
 
 struct TcParams {
     GemmArgs g;
@@ -45,106 +45,143 @@ struct TcParams {
     int a_mode, b_mode;
 };
 
-__device__ __forceinline__ float4 mask4(float4 v, float4 y, int act) {
-    v.x *= act_grad_from_y(act, y.x);
-    v.y *= act_grad_from_y(act, y.y);
-    v.z *= act_grad_from_y(act, y.z);
-    v.w *= act_grad_from_y(act, y.w);
-    return v;
-}
+struct OperandView {
+    const float* P; int64_t s_row, s_k;          // P(row,k) = P[row*s_row + k*s_k]
+    const float* mask; int64_t m_row, m_k; int mask_act;
+    int64_t row0, n_rows;
+};
 
-__device__ __forceinline__ void split_store(float* hi_ptr, float* lo_ptr, float4 v) {
-    float4 hi, lo;
-    split_tf32(v.x, hi.x, lo.x);
-    split_tf32(v.y, hi.y, lo.y);
-    split_tf32(v.z, hi.z, lo.z);
-    split_tf32(v.w, hi.w, lo.w);
-    *reinterpret_cast<float4*>(hi_ptr) = hi;
-    *reinterpret_cast<float4*>(lo_ptr) = lo;
-}
+constexpr int kMaxItems = 8;   // float4 registers per operand per stage (R <= 256)
+constexpr int kItemsA = 4;     // the A tile always has 128 rows
 
-// Stage one operand tile (R rows x 32 k) of matrix P(row, k) = P[row*s_row + k*s_k] into shared
-// memory as hi/lo, in the layout selected by `mode`.
-template <int MODE>
-__device__ __forceinline__ void stage_operand(const float* __restrict__ P, int64_t s_row, int64_t s_k,
-                                              const float* __restrict__ mask, int64_t m_row, int64_t m_k,
-                                              int mask_act, int64_t row0, int64_t n_rows, int64_t k0,
-                                              int64_t kend, int R, float* hi, float* lo, int warp, int lane) {
-    if (MODE == LD_MNVEC) {
-        // unit = 4 consecutive rows; lane -> (k within group of 8, unit within 4); MN-major layout:
-        // float offset = ((g * (R/4) + unit) * 8 + kk) * 4
-        const int kk = lane & 7, ui = lane >> 3;
-        for (int unit = warp * 4 + ui; unit < R / 4; unit += TC_PROD_WARPS * 4) {
-            const int64_t row = row0 + unit * 4;
+// ---- phase 1: issue every global load of this stage into registers (no dependent use in between)
+template <int MODE, int NIT>
+__device__ __forceinline__ void tile_load(const OperandView& o, int R, int64_t k0, int64_t kend, int warp,
+                                          int lane, float4 (&v)[NIT], float4 (&vm)[NIT]) {
+    if (MODE == LD_TRANS) {
+        // item = (row quad, chunk): 4 loads of 4 consecutive rows at k, k+1, k+2, k+3
+        const int rq_l = (lane >> 3) * 2 + (lane & 1), c_l = (lane >> 1) & 3;
 #pragma unroll
-            for (int g = 0; g < TC_BK / 8; ++g) {
-                const int64_t k = k0 + g * 8 + kk;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < kend) {
-                    if (row + 3 < n_rows) {
-                        v = __ldg(reinterpret_cast<const float4*>(P + row + k * s_k));
-                        if (mask) v = mask4(v, __ldg(reinterpret_cast<const float4*>(mask + row + k * m_k)), mask_act);
+        for (int it = 0; it < NIT / 4; ++it) {
+            const int U = warp + TC_PROD_WARPS * it;
+            const bool live = U < (R / 32) * 2;
+            const int64_t row = o.row0 + ((U >> 1) * 8 + rq_l) * 4;
+            const int64_t k = k0 + ((U & 1) * 4 + c_l) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (live && k + e < kend) {
+                    if (row + 3 < o.n_rows) {
+                        x = __ldg(reinterpret_cast<const float4*>(o.P + row + (k + e) * o.s_k));
+                        if (o.mask) y = __ldg(reinterpret_cast<const float4*>(o.mask + row + (k + e) * o.m_k));
                     } else {
-                        float t[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int e = 0; e < 4; ++e)
-                            if (row + e < n_rows) {
-                                t[e] = __ldg(P + row + e + k * s_k);
-                                if (mask) t[e] *= act_grad_from_y(mask_act, __ldg(mask + row + e + k * m_k));
+                        float t[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (row + i < o.n_rows) {
+                                t[i] = __ldg(o.P + row + i + (k + e) * o.s_k);
+                                if (o.mask) u[i] = __ldg(o.mask + row + i + (k + e) * o.m_k);
                             }
-                        v = make_float4(t[0], t[1], t[2], t[3]);
+                        x = make_float4(t[0], t[1], t[2], t[3]);
+                        y = make_float4(u[0], u[1], u[2], u[3]);
                     }
                 }
-                const int off = ((g * (R / 4) + unit) * 8 + kk) * 4;
-                split_store(hi + off, lo + off, v);
+                v[it * 4 + e] = x;
+                vm[it * 4 + e] = y;
             }
         }
     } else {
-        // K-major layout: float offset = (c * R + r) * 4, c = 16-byte chunk along k (0..7)
-        const int r_lo = lane & 7, c_lo = lane >> 3;
-        for (int U = warp; U < (R / 8) * 2; U += TC_PROD_WARPS) {
-            const int r = (U >> 1) * 8 + r_lo;
-            const int c = (U & 1) * 4 + c_lo;
-            const int64_t row = row0 + r;
-            const int64_t k = k0 + c * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < n_rows && k < kend) {
+        const int r_l = lane & 7, c_l = lane >> 3;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int U = warp + TC_PROD_WARPS * it;
+            const bool live = U < (R / 8) * 2;
+            const int64_t row = o.row0 + (U >> 1) * 8 + r_l;
+            const int64_t k = k0 + ((U & 1) * 4 + c_l) * 4;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (live && row < o.n_rows && k < kend) {
                 if (MODE == LD_KVEC && k + 3 < kend) {
-                    v = __ldg(reinterpret_cast<const float4*>(P + row * s_row + k));
-                    if (mask) v = mask4(v, __ldg(reinterpret_cast<const float4*>(mask + row * m_row + k)), mask_act);
+                    x = __ldg(reinterpret_cast<const float4*>(o.P + row * o.s_row + k));
+                    if (o.mask) y = __ldg(reinterpret_cast<const float4*>(o.mask + row * o.m_row + k));
                 } else {
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    float t[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if (k + e < kend) {
-                            t[e] = __ldg(P + row * s_row + (k + e) * s_k);
-                            if (mask) t[e] *= act_grad_from_y(mask_act, __ldg(mask + row * m_row + (k + e) * m_k));
+                            t[e] = __ldg(o.P + row * o.s_row + (k + e) * o.s_k);
+                            if (o.mask) u[e] = __ldg(o.mask + row * o.m_row + (k + e) * o.m_k);
                         }
-                    v = make_float4(t[0], t[1], t[2], t[3]);
+                    x = make_float4(t[0], t[1], t[2], t[3]);
+                    y = make_float4(u[0], u[1], u[2], u[3]);
                 }
             }
-            const int off = (c * R + r) * 4;
-            split_store(hi + off, lo + off, v);
+            v[it] = x;
+            vm[it] = y;
         }
     }
 }
 
-__device__ __forceinline__ void stage_dispatch(int mode, const float* P, int64_t s_row, int64_t s_k,
-                                               const float* mask, int64_t m_row, int64_t m_k, int mask_act,
-                                               int64_t row0, int64_t n_rows, int64_t k0, int64_t kend, int R,
-                                               float* hi, float* lo, int warp, int lane) {
-    if (mode == LD_KVEC)
-        stage_operand<LD_KVEC>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
-    else if (mode == LD_MNVEC)
-        stage_operand<LD_MNVEC>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
-    else
-        stage_operand<LD_SCALAR>(P, s_row, s_k, mask, m_row, m_k, mask_act, row0, n_rows, k0, kend, R, hi, lo, warp, lane);
+__device__ __forceinline__ float4 apply_mask(float4 x, float4 y, int act) {
+    x.x *= act_grad_from_y(act, y.x);
+    x.y *= act_grad_from_y(act, y.y);
+    x.z *= act_grad_from_y(act, y.z);
+    x.w *= act_grad_from_y(act, y.w);
+    return x;
 }
+
+// ---- phase 2: mask, split into hi/lo, store into the tile
+template <int MODE, int NIT>
+__device__ __forceinline__ void tile_store(const OperandView& o, int R, int warp, int lane,
+                                           float4 (&v)[NIT], float4 (&vm)[NIT], float* hi, float* lo) {
+    if (MODE == LD_TRANS) {
+        const int rq_l = (lane >> 3) * 2 + (lane & 1), c_l = (lane >> 1) & 3;
+#pragma unroll
+        for (int it = 0; it < NIT / 4; ++it) {
+            const int U = warp + TC_PROD_WARPS * it;
+            if (U < (R / 32) * 2) {
+                const int r = ((U >> 1) * 8 + rq_l) * 4, c = (U & 1) * 4 + c_l;
+                float4 x0 = v[it * 4 + 0], x1 = v[it * 4 + 1], x2 = v[it * 4 + 2], x3 = v[it * 4 + 3];
+                if (o.mask) {
+                    x0 = apply_mask(x0, vm[it * 4 + 0], o.mask_act);
+                    x1 = apply_mask(x1, vm[it * 4 + 1], o.mask_act);
+                    x2 = apply_mask(x2, vm[it * 4 + 2], o.mask_act);
+                    x3 = apply_mask(x3, vm[it * 4 + 3], o.mask_act);
+                }
+                // 4x4 register transpose: row r+i gets (k, k+1, k+2, k+3)
+                split_store(hi + tile_off(R, r + 0, c), lo + tile_off(R, r + 0, c), make_float4(x0.x, x1.x, x2.x, x3.x));
+                split_store(hi + tile_off(R, r + 1, c), lo + tile_off(R, r + 1, c), make_float4(x0.y, x1.y, x2.y, x3.y));
+                split_store(hi + tile_off(R, r + 2, c), lo + tile_off(R, r + 2, c), make_float4(x0.z, x1.z, x2.z, x3.z));
+                split_store(hi + tile_off(R, r + 3, c), lo + tile_off(R, r + 3, c), make_float4(x0.w, x1.w, x2.w, x3.w));
+            }
+        }
+    } else {
+        const int r_l = lane & 7, c_l = lane >> 3;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int U = warp + TC_PROD_WARPS * it;
+            if (U < (R / 8) * 2) {
+                const int r = (U >> 1) * 8 + r_l, c = (U & 1) * 4 + c_l;
+                float4 x = v[it];
+                if (o.mask) x = apply_mask(x, vm[it], o.mask_act);
+                split_store(hi + tile_off(R, r, c), lo + tile_off(R, r, c), x);
+            }
+        }
+    }
+}
+
+#define TC_MODE_SWITCH(mode, CALL)                \
+    do {                                          \
+        if ((mode) == LD_KVEC) { CALL(LD_KVEC); } \
+        else if ((mode) == LD_TRANS) { CALL(LD_TRANS); } \
+        else { CALL(LD_SCALAR); }                 \
+    } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
     const int BN = p.BN, S = p.stages;
-    const uint32_t a_tile = TC_BM * TC_BK * 4;          // bytes of one A tile (hi or lo)
-    const uint32_t b_tile = (uint32_t)BN * TC_BK * 4;
+    const uint32_t a_tile = (TC_BM + 1) * 128;          // bytes of one A tile (hi or lo), see tile_off
+    const uint32_t b_tile = ((uint32_t)BN + 1) * 128;
     const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;
     unsigned char* tiles = smem_raw;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * stage_bytes);
@@ -174,20 +211,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
     if (warp < TC_PROD_WARPS) {
         // ------------------------------ producers ------------------------------------------
+        OperandView oa{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, m0, g.M};
+        OperandView ob{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, n0, g.N};
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
+            const int64_t k0 = kbeg + (int64_t)kb * TC_BK;
+            float4 va[kItemsA], vam[kItemsA], vb[kMaxItems], vbm[kMaxItems];
+            // all global loads of the stage are in flight before anything waits on them (and before
+            // this warp blocks on the stage's empty barrier)
+#define TC_LOAD_A(MODE) tile_load<MODE, kItemsA>(oa, TC_BM, k0, kend, warp, lane, va, vam)
+#define TC_LOAD_B(MODE) tile_load<MODE, kMaxItems>(ob, BN, k0, kend, warp, lane, vb, vbm)
+            TC_MODE_SWITCH(p.a_mode, TC_LOAD_A);
+            TC_MODE_SWITCH(p.b_mode, TC_LOAD_B);
             mbar_wait(&empty_bar[s], ph ^ 1u);
             unsigned char* st = tiles + (size_t)s * stage_bytes;
             float* a_hi = reinterpret_cast<float*>(st);
             float* a_lo = reinterpret_cast<float*>(st + a_tile);
             float* b_hi = reinterpret_cast<float*>(st + 2 * a_tile);
             float* b_lo = reinterpret_cast<float*>(st + 2 * a_tile + b_tile);
-            const int64_t k0 = kbeg + (int64_t)kb * TC_BK;
-            stage_dispatch(p.a_mode, g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, m0, g.M, k0, kend,
-                           TC_BM, a_hi, a_lo, warp, lane);
-            stage_dispatch(p.b_mode, g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, n0, g.N, k0, kend,
-                           BN, b_hi, b_lo, warp, lane);
+#define TC_STORE_A(MODE) tile_store<MODE, kItemsA>(oa, TC_BM, warp, lane, va, vam, a_hi, a_lo)
+#define TC_STORE_B(MODE) tile_store<MODE, kMaxItems>(ob, BN, warp, lane, vb, vbm, b_hi, b_lo)
+            TC_MODE_SWITCH(p.a_mode, TC_STORE_A);
+            TC_MODE_SWITCH(p.b_mode, TC_STORE_B);
             fence_async_smem();                                           // generic -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
@@ -252,14 +298,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         tc_fence_before();
     } else {
         // ------------------------------ MMA issuer -----------------------------------------
-        const uint32_t idesc = tf32_idesc(BN) | ((p.a_mode == LD_MNVEC) ? (1u << 15) : 0u) |
-                               ((p.b_mode == LD_MNVEC) ? (1u << 16) : 0u);
-        // per K atom (8 k): K-major tiles advance by two 16-byte chunks (2 * R * 16 B);
-        // MN-major tiles by one 8-k group ((R/4) * 128 B)
-        const uint32_t a_step = (p.a_mode == LD_MNVEC) ? (TC_BM / 4) * 128u : 2u * TC_BM * 16u;
-        const uint32_t b_step = (p.b_mode == LD_MNVEC) ? ((uint32_t)BN / 4) * 128u : 2u * (uint32_t)BN * 16u;
-        const uint32_t a_lbo = (p.a_mode == LD_MNVEC) ? (TC_BM / 4) * 128u : TC_BM * 16u;
-        const uint32_t b_lbo = (p.b_mode == LD_MNVEC) ? ((uint32_t)BN / 4) * 128u : (uint32_t)BN * 16u;
+        const uint32_t idesc = tf32_idesc(BN);
+        // per K atom (8 k = two 16-byte chunks) the tiles advance by 2 * (R+1) * 16 bytes
+        const uint32_t a_lbo = (TC_BM + 1) * 16u, b_lbo = ((uint32_t)BN + 1) * 16u;
+        const uint32_t a_step = 2u * a_lbo, b_step = 2u * b_lbo;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -304,7 +346,7 @@ int pick_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int
         return LD_KVEC;
     if (s_row == 1 && s_k % 4 == 0 && aligned16(P) &&
         (!mask || (m_row == 1 && m_k % 4 == 0 && aligned16(mask))))
-        return (e && e[0] == 'k') ? LD_SCALAR : LD_MNVEC;
+        return (e && e[0] == 'k') ? LD_SCALAR : LD_TRANS;
     return LD_SCALAR;
 }
 
@@ -326,7 +368,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     while (p.tmem_cols < BN) p.tmem_cols <<= 1;
     p.a_mode = pick_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk);
     p.b_mode = pick_mode(g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk);
-    const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)BN * TC_BK * 4;
+    const size_t stage_bytes = 2 * (size_t)(TC_BM + 1) * 128 + 2 * (size_t)(BN + 1) * 128;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) {

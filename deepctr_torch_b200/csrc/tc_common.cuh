@@ -94,6 +94,40 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Shared-memory operand tile (R rows x 32 k, fp32): K-major core matrices, 16-byte chunk c of row r
+// at byte offset c*(R+1)*16 + r*16.  The +1 row of padding per chunk staggers the chunks over the
+// banks so that transposing loaders store conflict-free; UMMA descriptor: LBO = (R+1)*16 (between
+// the two chunks of a K atom), SBO = 128 (between 8-row core matrices).
+__device__ __forceinline__ int tile_off(int R, int r, int c) { return (c * (R + 1) + r) * 4; }   // in floats
+__device__ __forceinline__ uint32_t tile_bytes(int R) { return (uint32_t)(R + 1) * 128u; }
+
+__device__ __forceinline__ void split_store(float* hi_ptr, float* lo_ptr, float4 v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(hi_ptr) = hi;
+    *reinterpret_cast<float4*>(lo_ptr) = lo;
+}
+
+// issue the 3xTF32 MMAs of one 32-wide K stage (4 atoms x {lo*hi, hi*lo, hi*hi}); tiles as above
+__device__ __forceinline__ void issue_stage_mmas(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                 uint32_t b_lo, int RA, int RB, uint32_t idesc, bool first) {
+    const uint32_t a_lbo = (uint32_t)(RA + 1) * 16u, b_lbo = (uint32_t)(RB + 1) * 16u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t ao = (uint32_t)j * 2u * a_lbo, bo = (uint32_t)j * 2u * b_lbo;
+        const uint64_t dah = make_smem_desc(a_hi + ao, a_lbo, 128);
+        const uint64_t dal = make_smem_desc(a_lo + ao, a_lbo, 128);
+        const uint64_t dbh = make_smem_desc(b_hi + bo, b_lbo, 128);
+        const uint64_t dbl = make_smem_desc(b_lo + bo, b_lbo, 128);
+        umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small terms first
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+
 // tf32 x tf32 -> f32 instruction descriptor, K-major A and B, M = 128
 __device__ __forceinline__ uint32_t tf32_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

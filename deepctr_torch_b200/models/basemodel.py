@@ -161,7 +161,9 @@ class BaseModel(nn.Module):
     def embed(self, X, want_fm=False, want_blk=True):
         """Fused lookup for this batch.
 
-        Returns ``(E, dnn_input, lin, fm)``: ``E [B,F,D]`` embedding block (sparse fields in column
+        Returns ``(E, dnn_input, lin, fm, blk)``: ``blk [B, ld]`` is the zero-padded block
+        (``ld = round_up(width, 4)``) that the DNN tower consumes without slicing (None when pooled
+        VarLen fields force a generic assembly); ``E [B,F,D]`` embedding block (sparse fields in column
         order, then pooled VarLen fields — reference basemodel.py:368-380), ``dnn_input
         [B, F*D + n_dense]`` (= ``combined_dnn_input``, inputs.py:126-138), ``lin [B]`` the
         linear logit (basemodel.py:63-92), ``fm [B]`` the FM term or None."""
@@ -203,7 +205,7 @@ class BaseModel(nn.Module):
             lcol = self.feature_index[c.length_name][0] if c.length_name is not None else None
             lin = lin + ops.varlen_pool(X, self.linear_model.embedding_dict[c.embedding_name].weight, s, e - s,
                                         lcol, c.combiner, plan.err_flag).squeeze(1)
-        return E, dnn_input, lin, fm
+        return E, dnn_input, lin, fm, (blk if not varlen else None)
 
     def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):
         """API-compatible view of the fused lookup (reference basemodel.py:354-380): a list of
@@ -211,7 +213,7 @@ class BaseModel(nn.Module):
         _, dense, _ = split_columns(feature_columns)
         if not support_dense and len(dense) > 0:
             raise ValueError("DenseFeat is not supported in dnn_feature_columns")
-        E, _, _, _ = self.embed(X)
+        E = self.embed(X)[0]
         emb_list = [E[:, f:f + 1, :] for f in range(E.shape[1])] if E is not None else []
         dense_list = [X[:, self.feature_index[c.name][0]:self.feature_index[c.name][1]] for c in dense]
         return emb_list, dense_list

@@ -12,17 +12,18 @@ class _DeepCrossBase(BaseModel):
     row-dots on the two halves of the weight, so the concatenation is never materialised."""
 
     def _head(self, X):
-        E, dnn_input, lin, _ = self.embed(X)
+        E, dnn_input, lin, _, blk = self.embed(X)
+        deep_in = blk if blk is not None else dnn_input
         terms = [lin]
         n_in = dnn_input.shape[1]
         w = self.dnn_linear.weight
         if len(self.dnn_hidden_units) > 0 and self.cross_num > 0:
             cross_out = self.crossnet(dnn_input)
-            deep_out = self.dnn(dnn_input)
+            deep_out = self.dnn(deep_in)
             terms.append(ops.rowdot(cross_out, w[:, :n_in]))
             terms.append(ops.rowdot(deep_out, w[:, n_in:]))
         elif len(self.dnn_hidden_units) > 0:
-            terms.append(ops.rowdot(self.dnn(dnn_input), w))
+            terms.append(ops.rowdot(self.dnn(deep_in), w))
         elif self.cross_num > 0:
             terms.append(ops.rowdot(self.crossnet(dnn_input), w))
         return self.out.forward_terms(terms)

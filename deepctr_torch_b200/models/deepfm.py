@@ -29,10 +29,10 @@ class DeepFM(BaseModel):
         self.to(device)
 
     def forward(self, X):
-        E, dnn_input, lin, fm = self.embed(X, want_fm=self.use_fm, want_blk=self.use_dnn or self.use_fm)
+        E, dnn_input, lin, fm, blk = self.embed(X, want_fm=self.use_fm, want_blk=self.use_dnn or self.use_fm)
         terms = [lin]
         if self.use_fm and fm is not None:
             terms.append(fm)
         if self.use_dnn:
-            terms.append(ops.rowdot(self.dnn(dnn_input), self.dnn_linear.weight))
+            terms.append(ops.rowdot(self.dnn(blk if blk is not None else dnn_input), self.dnn_linear.weight))
         return self.out.forward_terms(terms)

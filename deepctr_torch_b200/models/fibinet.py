@@ -36,7 +36,7 @@ class FiBiNET(BaseModel):
         return (sparse_dim if include_sparse else 0) + (dense_dim if include_dense else 0)
 
     def forward(self, X):
-        E, dnn_input, lin, _ = self.embed(X)
+        E, dnn_input, lin, _, _ = self.embed(X)
         B = X.shape[0]
         W = self.Bilinear.stacked_weight()           # shared by both passes (fibinet.py:82-83)
         senet_out = self.SE(E)

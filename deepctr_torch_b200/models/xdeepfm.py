@@ -41,10 +41,10 @@ class xDeepFM(BaseModel):
         self.to(device)
 
     def forward(self, X):
-        E, dnn_input, lin, _ = self.embed(X, want_blk=self.use_cin or self.use_dnn)
+        E, dnn_input, lin, _, blk = self.embed(X, want_blk=self.use_cin or self.use_dnn)
         terms = [lin]
         if self.use_cin:
             terms.append(ops.rowdot(self.cin(E), self.cin_linear.weight))
         if self.use_dnn:
-            terms.append(ops.rowdot(self.dnn(dnn_input), self.dnn_linear.weight))
+            terms.append(ops.rowdot(self.dnn(blk if blk is not None else dnn_input), self.dnn_linear.weight))
         return self.out.forward_terms(terms)

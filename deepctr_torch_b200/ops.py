@@ -288,10 +288,17 @@ class _DnnLayer(torch.autograd.Function):
         B, K = x.shape
         Wc = W if W.is_contiguous() else W.contiguous()
         N = Wc.shape[1] if w_kn else Wc.shape[0]
-        if not w_kn and K % 4 != 0:
+        Kw = Wc.shape[0] if w_kn else Wc.shape[1]
+        if not w_kn and Kw % 4 != 0:
             # rows of an [N, K] weight with K % 4 != 0 are not 16-byte aligned: stage a zero-padded
             # copy ([N, round_up(K,4)], a few hundred KB) so the GEMM producers can use 128-bit loads
-            Wc = torch.nn.functional.pad(Wc, (0, _round4(K) - K))
+            Wc = torch.nn.functional.pad(Wc, (0, _round4(Kw) - Kw))
+        if K != Kw:
+            # zero-padded input block [B, round_up(K,4)] (the fused gather writes zeros behind the
+            # dense columns): contract over the padded width against the zero-padded weight, so
+            # neither the forward nor the backward needs a strided slice of the 113 MB block
+            if w_kn or K != _round4(Kw):
+                raise ValueError("dnn_layer: input width %d does not match weight width %d" % (K, Kw))
         swn, swk = (1, N) if w_kn else (Wc.shape[1], 1)
         y = torch.empty(B, N, device=x.device, dtype=torch.float32)
         _lib.call("ctr_dnn_layer_fwd", _ptr(x), x.stride(0), _ptr(Wc), swn, swk, _ptr(bias),
@@ -308,16 +315,21 @@ class _DnnLayer(torch.autograd.Function):
         N = y.shape[1]
         dy = _rowmajor(dy)
         swn, swk = (1, N) if ctx.w_kn else (Wc.shape[1], 1)
+        Kw = ctx.wshape[0] if ctx.w_kn else ctx.wshape[1]
+        padded_in = (K != Kw)
         sdwn, sdwk = (1, N) if ctx.w_kn else (K, 1)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         ldx = _round4(K)
         dx_full = torch.empty(B, ldx, device=x.device, dtype=torch.float32) if need_dx else None
-        dW = torch.empty(ctx.wshape, device=x.device, dtype=torch.float32) if need_dw else None
+        dW = (torch.empty((N, K) if padded_in else ctx.wshape, device=x.device, dtype=torch.float32)
+              if need_dw else None)
         db = torch.empty(N, device=x.device, dtype=torch.float32) if ctx.has_bias else None
         _lib.call("ctr_dnn_layer_bwd", _ptr(x), x.stride(0), _ptr(Wc), swn, swk, _ptr(y), N,
                   _ptr(dy), dy.stride(0), _ptr(dx_full), ldx, 0, _ptr(dW), sdwn, sdwk, _ptr(db),
                   B, K, N, ctx.act, _stream())
         dx = dx_full[:, :K] if need_dx else None
+        if padded_in and dW is not None:
+            dW = dW[:, :Kw].contiguous()
         return dx, dW, db, None, None
 
 

@@ -56,7 +56,8 @@ def test_gather_is_bit_exact_and_block_layout():
     m = build_model(c["cfg"], DEV)
     m.load_state_dict(c["state"])
     X = c["X"].to(DEV)
-    E, dnn_input, lin, fm = m.embed(X, want_fm=True)
+    E, dnn_input, lin, fm, blk = m.embed(X, want_fm=True)
+    assert blk.shape[1] % 4 == 0 and torch.equal(blk[:, dnn_input.shape[1]:].cpu(), torch.zeros(X.shape[0], blk.shape[1] - dnn_input.shape[1]))
     findex = O.feature_index(c["cfg"])
     rows = O.embedding_rows(c["state"], "embedding_dict.", c["X"], c["cfg"]["dnn_columns"], findex)
     ref_E = torch.stack(rows, dim=1)
