@@ -53,12 +53,14 @@ struct GatherArgs {
 // forward, vector path: D % 4 == 0 and D/4 a power of two <= 32
 // ---------------------------------------------------------------------------------------------
 // Memory-level parallelism is what bounds this kernel: per sample the chain is X row -> ids ->
-// rows.  The ids of the NEXT sample of the warp are prefetched while the current sample's rows are
-// in flight, and the (up to) four row loads of a lane are all issued before the first store.
-template <int LPR>
+// rows.  A warp works on SPW samples at once: all their ids are fetched first, then all their row
+// loads (SPW x 4 x 128 bit per lane) are issued before the first store, so ~2 * F rows per warp are
+// in flight at the same time.
+template <int LPR, int SPW>
 __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     constexpr int RPW = 32 / LPR;  // rows per warp step
-    constexpr int STEPS = 4;       // row loads in flight per lane
+    constexpr int STEPS = 4;       // row loads in flight per lane and sample
+    constexpr int D = LPR * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // stage slot metadata (table pointers, column, vocab) in shared memory
     const float** s_tab = reinterpret_cast<const float**>(smem_raw);
@@ -75,108 +77,101 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rslot = lane / LPR;
-    constexpr int D = LPR * 4;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool one_chunk = a.n_emb <= STEPS * RPW;
-    const int lin_col = (lane < a.n_lin) ? a.lin_cols[lane] : 0;
-    const bool lin_fast = a.n_lin <= 32;
 
-    float xv[STEPS];   // raw X values (ids) of this lane's fields for the current sample
-    float xl = 0.f;    // raw X value of this lane's linear field
-    auto prefetch_x = [&](int64_t b, float (&x)[STEPS], float& l) {
-        if (b < a.B) {
-            const float* xrow = a.X + b * a.ldx;
+    for (int64_t bb = warp0 * SPW; bb < a.B; bb += nwarps * SPW) {
+        float4 S[SPW];
+        float q[SPW];
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int f = s * RPW + rslot;
-                x[s] = (f < a.n_emb) ? __ldg(xrow + s_col[f]) : 0.f;
-            }
-            l = (lin_fast && lane < a.n_lin) ? __ldg(xrow + lin_col) : 0.f;
+        for (int t = 0; t < SPW; ++t) {
+            S[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[t] = 0.f;
         }
-    };
-    prefetch_x(warp0, xv, xl);
-
-    for (int64_t b = warp0; b < a.B; b += nwarps) {
-        const float* xrow = a.X + b * a.ldx;
-        float xn[STEPS];
-        float xln = 0.f;
-        prefetch_x(b + nwarps, xn, xln);
-
-        float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
-        float q = 0.f;
         for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
-            float4 v[STEPS];
+            // every load below is UNCONDITIONAL (sample / field indices are clamped to a valid element and
+            // the result is simply not used when out of range): a load inside a data-dependent branch is
+            // waited for at the join, which would serialise the SPW x STEPS row loads of a lane
+            float xr[SPW][STEPS];
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int f = f0 + s * RPW + rslot;
-                v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (f < a.n_emb) {
-                    const float raw = (f0 == 0) ? xv[s] : __ldg(xrow + s_col[f]);
-                    const int id = decode_id(raw, s_voc[f], a.err_flag);
-                    const float* tab = (G == 1) ? s_tab[f] : s_tab[f * G + id % G];
+            for (int t = 0; t < SPW; ++t) {
+                const int64_t bc = (bb + t < a.B) ? bb + t : a.B - 1;
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    xr[t][s] = __ldg(a.X + bc * a.ldx + s_col[f < a.n_emb ? f : a.n_emb - 1]);
+                }
+            }
+            float4 v[SPW][STEPS];
+#pragma unroll
+            for (int t = 0; t < SPW; ++t) {
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    const int fc = f < a.n_emb ? f : a.n_emb - 1;
+                    const int id = decode_id(xr[t][s], s_voc[fc], a.err_flag);
+                    const float* tab = (G == 1) ? s_tab[fc] : s_tab[fc * G + id % G];
                     const int row = (G == 1) ? id : id / G;
-                    v[s] = ld_stream4(tab + (size_t)row * D + sub * 4);
+                    v[t][s] = ld_stream4(tab + (size_t)row * D + sub * 4);
                 }
             }
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int f = f0 + s * RPW + rslot;
-                if (f < a.n_emb) {
-                    if (a.blk) st_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4, v[s]);
-                    S.x += v[s].x; S.y += v[s].y; S.z += v[s].z; S.w += v[s].w;
-                    q += v[s].x * v[s].x + v[s].y * v[s].y + v[s].z * v[s].z + v[s].w * v[s].w;
+            for (int t = 0; t < SPW; ++t) {
+                const int64_t b = bb + t;
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    if (b < a.B && f < a.n_emb) {
+                        if (a.blk) st_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4, v[t][s]);
+                        S[t].x += v[t][s].x; S[t].y += v[t][s].y; S[t].z += v[t][s].z; S[t].w += v[t][s].w;
+                        q[t] += v[t][s].x * v[t][s].x + v[t][s].y * v[t][s].y + v[t][s].z * v[t][s].z +
+                                v[t][s].w * v[t][s].w;
+                    }
                 }
             }
-            if (one_chunk) break;
         }
-        float fmv = 0.f;
-        if (a.fm) {
-            // sum S over the lanes that hold the same quad of d (stride LPR), q over all lanes
 #pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) {
-                S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
-                S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
-                S.z += __shfl_xor_sync(0xffffffffu, S.z, o);
-                S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
-            }
-            float t = S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w;
+        for (int t = 0; t < SPW; ++t) {
+            const int64_t b = bb + t;
+            if (b >= a.B) break;                      // warp-uniform
+            const float* xrow = a.X + b * a.ldx;
+            float fmv = 0.f;
+            if (a.fm) {
+                float4 Ss = S[t];
+                // sum S over the lanes that hold the same quad of d (stride LPR), q over all lanes
 #pragma unroll
-            for (int o = 1; o < LPR; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            q = warp_sum(q);
-            fmv = 0.5f * (t - q);
-        }
-        // linear term: sparse weights + dense dot; dense copy into the block
-        float lp = 0.f;
-        if (lin_fast) {
-            if (lane < a.n_lin) {
-                const int id = decode_id(xl, a.lin_vocab[lane], a.err_flag);
-                lp = (G == 1) ? __ldg(a.lin_tables[lane] + id) : __ldg(a.lin_tables[lane * G + id % G] + id / G);
+                for (int o = LPR; o < 32; o <<= 1) {
+                    Ss.x += __shfl_xor_sync(0xffffffffu, Ss.x, o);
+                    Ss.y += __shfl_xor_sync(0xffffffffu, Ss.y, o);
+                    Ss.z += __shfl_xor_sync(0xffffffffu, Ss.z, o);
+                    Ss.w += __shfl_xor_sync(0xffffffffu, Ss.w, o);
+                }
+                float tt = Ss.x * Ss.x + Ss.y * Ss.y + Ss.z * Ss.z + Ss.w * Ss.w;
+#pragma unroll
+                for (int o = 1; o < LPR; o <<= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+                fmv = 0.5f * (tt - warp_sum(q[t]));
             }
-        } else {
+            // linear term: sparse weights + dense dot; dense copy (and zero padding) into the block
+            float lp = 0.f;
             for (int f = lane; f < a.n_lin; f += 32) {
-                const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
-                lp += (G == 1) ? __ldg(a.lin_tables[f] + id) : __ldg(a.lin_tables[f * G + (int)(id % G)] + id / G);
+                const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+                lp += (G == 1) ? __ldg(a.lin_tables[f] + id) : __ldg(a.lin_tables[f * G + id % G] + id / G);
             }
+            for (int k = lane; k < a.n_lin_dense; k += 32)
+                lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
+            if (a.blk) {
+                float* drow = a.blk + b * a.ld_blk + (int64_t)a.n_emb * D;
+                const int n_pad = (int)(a.ld_blk - (int64_t)a.n_emb * D);  // dense columns, then zeros up to ld
+                for (int k = lane; k < n_pad; k += 32) drow[k] = (k < a.n_dense) ? __ldg(xrow + a.dense_cols[k]) : 0.f;
+            }
+            if (a.lin) {
+                lp = warp_sum(lp);
+                if (lane == 0) a.lin[b] = lp;
+            }
+            if (a.fm && lane == 0) a.fm[b] = fmv;
         }
-        for (int k = lane; k < a.n_lin_dense; k += 32)
-            lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
-        if (a.blk) {
-            float* drow = a.blk + b * a.ld_blk + (int64_t)a.n_emb * D;
-            const int n_pad = (int)(a.ld_blk - (int64_t)a.n_emb * D);      // dense columns, then zeros up to ld
-            for (int k = lane; k < n_pad; k += 32) drow[k] = (k < a.n_dense) ? __ldg(xrow + a.dense_cols[k]) : 0.f;
-        }
-        if (a.lin) {
-            lp = warp_sum(lp);
-            if (lane == 0) a.lin[b] = lp;
-        }
-        if (a.fm && lane == 0) a.fm[b] = fmv;
-#pragma unroll
-        for (int s = 0; s < STEPS; ++s) xv[s] = xn[s];
-        xl = xln;
     }
 }
-
 
 // forward, generic path: any D (scalar loads); FM is computed by fm_fwd_kernel afterwards
 __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
@@ -285,110 +280,130 @@ struct ScatterArgs {
     const int32_t* cnt;
 };
 
-// One warp per sample.  r[b,f,:] = d_blk + g_fm (S - E) is added to its destination row: dense
-// mode -> red.global.add.v4.f32 into [V,D]; rowwise mode -> plain 128-bit store when the id is
-// unique in the batch (cnt == 1), vector reduction otherwise.  All loads of a lane (up to four
-// d_blk rows, four blk rows, the inv/cnt lookups) are issued before the first store.
-template <int LPR, bool ROWWISE>
-__global__ void __launch_bounds__(256) scatter_bwd_vec_kernel(ScatterArgs a) {
+// A warp works on SPW samples at once.  r[b,f,:] = d_blk + g_fm (S - E) is added to its destination
+// row: dense mode -> red.global.add.v4.f32 into [V,D]; rowwise mode -> plain 128-bit store when the
+// id is unique in the batch (cnt == 1), vector reduction otherwise.  All loads are unconditional
+// (clamped indices) and issued before the first dependent instruction; only stores are predicated.
+template <int LPR, bool ROWWISE, int SPW>
+__global__ void __launch_bounds__(128) scatter_bwd_vec_kernel(ScatterArgs a) {
     constexpr int RPW = 32 / LPR;
     constexpr int STEPS = 4;
+    constexpr int D = LPR * 4;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rslot = lane / LPR;
-    constexpr int D = LPR * 4;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool one_chunk = a.n_emb <= STEPS * RPW;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int64_t b = warp0; b < a.B; b += nwarps) {
-        const float* xrow = a.X ? a.X + b * a.ldx : nullptr;
-        float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
-        float gfm = 0.f;
-        float4 e0[STEPS];          // blk rows of the first chunk (kept for pass 2)
+    for (int64_t bb = warp0 * SPW; bb < a.B; bb += nwarps * SPW) {
+        int64_t bc[SPW];
+        float gfm[SPW];
+        float4 S[SPW];
+#pragma unroll
+        for (int t = 0; t < SPW; ++t) {
+            bc[t] = (bb + t < a.B) ? bb + t : a.B - 1;
+            gfm[t] = a.g_fm ? __ldg(a.g_fm + bc[t]) : 0.f;
+            S[t] = zero4;
+        }
+        float4 e0[SPW][STEPS];         // blk rows of the first chunk (reused in pass 2)
         if (a.g_fm) {
-            gfm = __ldg(a.g_fm + b);
             for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
-                float4 v[STEPS];
+                float4 v[SPW][STEPS];
 #pragma unroll
-                for (int s = 0; s < STEPS; ++s) {
-                    const int f = f0 + s * RPW + rslot;
-                    v[s] = (f < a.n_emb) ? ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int t = 0; t < SPW; ++t)
 #pragma unroll
-                for (int s = 0; s < STEPS; ++s) {
-                    S.x += v[s].x; S.y += v[s].y; S.z += v[s].z; S.w += v[s].w;
-                    if (f0 == 0) e0[s] = v[s];
-                }
+                    for (int s = 0; s < STEPS; ++s) {
+                        const int f = f0 + s * RPW + rslot;
+                        const int fc = f < a.n_emb ? f : a.n_emb - 1;
+                        v[t][s] = ld_stream4(a.blk + bc[t] * a.ld_blk + (int64_t)fc * D + sub * 4);
+                    }
+#pragma unroll
+                for (int t = 0; t < SPW; ++t)
+#pragma unroll
+                    for (int s = 0; s < STEPS; ++s) {
+                        const bool live = f0 + s * RPW + rslot < a.n_emb;
+                        S[t].x += live ? v[t][s].x : 0.f; S[t].y += live ? v[t][s].y : 0.f;
+                        S[t].z += live ? v[t][s].z : 0.f; S[t].w += live ? v[t][s].w : 0.f;
+                        if (f0 == 0) e0[t][s] = v[t][s];
+                    }
             }
 #pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) {
-                S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
-                S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
-                S.z += __shfl_xor_sync(0xffffffffu, S.z, o);
-                S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
-            }
+            for (int t = 0; t < SPW; ++t)
+#pragma unroll
+                for (int o = LPR; o < 32; o <<= 1) {
+                    S[t].x += __shfl_xor_sync(0xffffffffu, S[t].x, o);
+                    S[t].y += __shfl_xor_sync(0xffffffffu, S[t].y, o);
+                    S[t].z += __shfl_xor_sync(0xffffffffu, S[t].z, o);
+                    S[t].w += __shfl_xor_sync(0xffffffffu, S[t].w, o);
+                }
         }
         for (int f0 = 0; f0 < a.n_emb; f0 += STEPS * RPW) {
-            float4 r[STEPS];
-            int u[STEPS];
-            int c[STEPS];
-            int id[STEPS];
+            float4 r[SPW][STEPS];
+            int u[SPW][STEPS];
+            int c[SPW][STEPS];
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int f = f0 + s * RPW + rslot;
-                r[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                u[s] = 0; c[s] = 0; id[s] = 0;
-                if (f < a.n_emb) {
-                    if (a.d_blk) r[s] = ld_stream4(a.d_blk + b * a.ld_dblk + (int64_t)f * D + sub * 4);
-                    if (ROWWISE) u[s] = __ldg(a.inv + b * a.n_plan + a.emb_cols[f]);
-                    else id[s] = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], nullptr);
-                }
-            }
-            if (ROWWISE) {
+            for (int t = 0; t < SPW; ++t)
 #pragma unroll
                 for (int s = 0; s < STEPS; ++s) {
                     const int f = f0 + s * RPW + rslot;
-                    if (f < a.n_emb) c[s] = __ldg(a.cnt + (int64_t)a.emb_cols[f] * a.B + u[s]);
+                    const int fc = f < a.n_emb ? f : a.n_emb - 1;
+                    r[t][s] = a.d_blk ? ld_stream4(a.d_blk + bc[t] * a.ld_dblk + (int64_t)fc * D + sub * 4) : zero4;
+                    if (ROWWISE) u[t][s] = __ldg(a.inv + bc[t] * a.n_plan + a.emb_cols[fc]);
+                    else u[t][s] = decode_id(__ldg(a.X + bc[t] * a.ldx + a.emb_cols[fc]), a.emb_vocab[fc], nullptr);
                 }
+            if (ROWWISE) {
+#pragma unroll
+                for (int t = 0; t < SPW; ++t)
+#pragma unroll
+                    for (int s = 0; s < STEPS; ++s) {
+                        const int f = f0 + s * RPW + rslot;
+                        const int fc = f < a.n_emb ? f : a.n_emb - 1;
+                        c[t][s] = __ldg(a.cnt + (int64_t)a.emb_cols[fc] * a.B + u[t][s]);
+                    }
             }
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int f = f0 + s * RPW + rslot;
-                if (f < a.n_emb) {
-                    if (a.g_fm) {
-                        const float4 v = (f0 == 0) ? e0[s]
-                                                   : ld_stream4(a.blk + b * a.ld_blk + (int64_t)f * D + sub * 4);
-                        r[s].x += gfm * (S.x - v.x);
-                        r[s].y += gfm * (S.y - v.y);
-                        r[s].z += gfm * (S.z - v.z);
-                        r[s].w += gfm * (S.w - v.w);
-                    }
-                    if (ROWWISE) {
-                        float* dst = a.emb_rg + f * a.emb_rg_stride + (int64_t)u[s] * D + sub * 4;
-                        if (c[s] == 1) st_stream4(dst, r[s]);
-                        else red_add4(dst, r[s]);
-                    } else {
-                        red_add4(a.emb_out[f] + (size_t)id[s] * D + sub * 4, r[s]);
+            for (int t = 0; t < SPW; ++t)
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int f = f0 + s * RPW + rslot;
+                    if (f < a.n_emb && bb + t < a.B) {
+                        float4 rr = r[t][s];
+                        if (a.g_fm) {
+                            const float4 v = (f0 == 0) ? e0[t][s]
+                                                       : ld_stream4(a.blk + bc[t] * a.ld_blk + (int64_t)f * D + sub * 4);
+                            rr.x += gfm[t] * (S[t].x - v.x);
+                            rr.y += gfm[t] * (S[t].y - v.y);
+                            rr.z += gfm[t] * (S[t].z - v.z);
+                            rr.w += gfm[t] * (S[t].w - v.w);
+                        }
+                        if (ROWWISE) {
+                            float* dst = a.emb_rg + f * a.emb_rg_stride + (int64_t)u[t][s] * D + sub * 4;
+                            if (c[t][s] == 1) st_stream4(dst, rr);
+                            else red_add4(dst, rr);
+                        } else {
+                            red_add4(a.emb_out[f] + (size_t)u[t][s] * D + sub * 4, rr);
+                        }
                     }
                 }
-            }
-            if (one_chunk) break;
         }
         if (a.g_lin) {
-            const float gl = __ldg(a.g_lin + b);
-            for (int f = lane; f < a.n_lin; f += 32) {
-                if (ROWWISE) {
-                    const int pc = a.lin_cols[f];
-                    const int u = __ldg(a.inv + b * a.n_plan + pc);
-                    const int c = __ldg(a.cnt + (int64_t)pc * a.B + u);
-                    float* dst = a.lin_rg + f * a.lin_rg_stride + u;
-                    if (c == 1) *dst = gl;
-                    else atomicAdd(dst, gl);
-                } else {
-                    const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], nullptr);
-                    atomicAdd(a.lin_out[f] + id, gl);
+#pragma unroll
+            for (int t = 0; t < SPW; ++t) {
+                if (bb + t >= a.B) break;
+                const float gl = __ldg(a.g_lin + bc[t]);
+                for (int f = lane; f < a.n_lin; f += 32) {
+                    if (ROWWISE) {
+                        const int pc = a.lin_cols[f];
+                        const int uu = __ldg(a.inv + bc[t] * a.n_plan + pc);
+                        const int cc = __ldg(a.cnt + (int64_t)pc * a.B + uu);
+                        float* dst = a.lin_rg + f * a.lin_rg_stride + uu;
+                        if (cc == 1) *dst = gl;
+                        else atomicAdd(dst, gl);
+                    } else {
+                        const int id = decode_id(__ldg(a.X + bc[t] * a.ldx + a.lin_cols[f]), a.lin_vocab[f], nullptr);
+                        atomicAdd(a.lin_out[f] + id, gl);
+                    }
                 }
             }
         }
@@ -619,16 +634,16 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
     const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
     const bool vec_ok = lpr > 0 && n_emb * n_shards <= kMaxSmemSlots &&
                         (!blk || ((ld_blk % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk) & 15) == 0)));
-    const unsigned grid = sample_grid(B, 8, 8);
+    const unsigned grid = sample_grid((B + 1) / 2, 8, 8);
     if (vec_ok) {
         const size_t smem = (size_t)n_emb * n_shards * sizeof(void*) + (size_t)n_emb * 8;
         switch (lpr) {
-            case 1: gather_fwd_vec_kernel<1><<<grid, 256, smem, st>>>(a); break;
-            case 2: gather_fwd_vec_kernel<2><<<grid, 256, smem, st>>>(a); break;
-            case 4: gather_fwd_vec_kernel<4><<<grid, 256, smem, st>>>(a); break;
-            case 8: gather_fwd_vec_kernel<8><<<grid, 256, smem, st>>>(a); break;
-            case 16: gather_fwd_vec_kernel<16><<<grid, 256, smem, st>>>(a); break;
-            default: gather_fwd_vec_kernel<32><<<grid, 256, smem, st>>>(a); break;
+            case 1: gather_fwd_vec_kernel<1, 2><<<grid, 256, smem, st>>>(a); break;
+            case 2: gather_fwd_vec_kernel<2, 2><<<grid, 256, smem, st>>>(a); break;
+            case 4: gather_fwd_vec_kernel<4, 2><<<grid, 256, smem, st>>>(a); break;
+            case 8: gather_fwd_vec_kernel<8, 2><<<grid, 256, smem, st>>>(a); break;
+            case 16: gather_fwd_vec_kernel<16, 2><<<grid, 256, smem, st>>>(a); break;
+            default: gather_fwd_vec_kernel<32, 2><<<grid, 256, smem, st>>>(a); break;
         }
         CTR_LAUNCH_OK("gather_fwd_vec_kernel");
     } else {
@@ -670,11 +685,12 @@ static int launch_scatter(ScatterArgs& a, bool rowwise, cudaStream_t st, bool fo
     const bool aligned =
         (!a.blk || (a.ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.blk) & 15) == 0)) &&
         (!a.d_blk || (a.ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.d_blk) & 15) == 0));
-    const unsigned grid = sample_grid(a.B, 8, 8);
+    const unsigned grid = sample_grid((a.B + 1) / 2, 8, 8);
+    const unsigned grid_vec = sample_grid((a.B + 1) / 2, 4, 12);
     if (lpr > 0 && aligned && !force_generic) {
 #define LAUNCH_SC(L)                                                                     \
-    if (rowwise) scatter_bwd_vec_kernel<L, true><<<grid, 256, 0, st>>>(a);               \
-    else scatter_bwd_vec_kernel<L, false><<<grid, 256, 0, st>>>(a);
+    if (rowwise) scatter_bwd_vec_kernel<L, true, 2><<<grid_vec, 128, 0, st>>>(a);        \
+    else scatter_bwd_vec_kernel<L, false, 2><<<grid_vec, 128, 0, st>>>(a);
         switch (lpr) {
             case 1: LAUNCH_SC(1) break;
             case 2: LAUNCH_SC(2) break;
