@@ -62,6 +62,7 @@ SIGNATURES = {
     "ctr_bilinear_fwd": [_P, c_i64, c_int, c_int, _P, c_int, _P, c_i64, c_i64, _P],
     "ctr_bilinear_bwd": [_P, c_i64, c_int, c_int, _P, c_int, _P, c_i64, _P, c_i64, _P, c_i64, _P],
     "ctr_sumsq_acc": [_P, c_i64, c_f32, _P, _P],
+    "ctr_debug_set_buffer": [_P],
     "ctr_varlen_pool_fwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,
                             c_i64, _P, _P],
     "ctr_varlen_pool_bwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,

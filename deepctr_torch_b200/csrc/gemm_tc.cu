@@ -37,6 +37,7 @@ constexpr int TC_THREADS = (TC_PROD_WARPS + 1) * 32;
 enum { LD_SCALAR = 0, LD_KVEC = 1, LD_TRANS = 2 };
 
 struct TcParams {
+    unsigned long long* dbg;   // optional timeline buffer (ctr_debug_set_buffer), CTA (0,0,0) only
     GemmArgs g;
     int64_t k_chunk;      // K range per split (multiple of TC_BK)
     int BN;               // N tile (multiple of 32)
@@ -54,15 +55,17 @@ struct OperandView {
 constexpr int kMaxItems = 8;   // float4 registers per operand per stage (R <= 256)
 constexpr int kItemsA = 4;     // the A tile always has 128 rows
 
-// ---- phase 1: issue every global load of this stage into registers.
-// The loads are UNCONDITIONAL (indices are clamped to a valid element, out-of-range lanes are zeroed
-// with selects afterwards): a load inside a data-dependent branch forces the compiler to wait for it
-// at the join, which serialises the ~12 loads of a stage (measured: 12-16k cycles per stage).
-// Preconditions checked by pick_mode(): KVEC/TRANS operands are readable up to the next multiple of
-// 4 elements along their contiguous axis (leading dimension >= round_up(extent, 4)).
+// ---- phase 1: issue every global load of a stage into registers — loads ONLY, nothing here reads
+// the loaded values.  They are consumed one pipeline iteration later by tile_store(), so the memory
+// latency (measured: ~3.4k cycles per stage when exposed) overlaps the MMA of the previous stage.
+// The loads are UNCONDITIONAL: indices are clamped to a valid element and out-of-range lanes are
+// zeroed with selects in tile_store() (a load inside a data-dependent branch is waited for at the
+// join).  Preconditions checked by pick_mode(): KVEC/TRANS operands are readable up to the next
+// multiple of 4 elements along their contiguous axis (leading dimension >= round_up(extent, 4)).
 __device__ __forceinline__ float4 sel4(float4 v, bool k0, bool k1, bool k2, bool k3) {
     return make_float4(k0 ? v.x : 0.f, k1 ? v.y : 0.f, k2 ? v.z : 0.f, k3 ? v.w : 0.f);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int MODE, int NIT, bool MASK>
 __device__ __forceinline__ void tile_load(const OperandView& o, int R, int64_t k0, int64_t kend, int warp,
@@ -76,16 +79,11 @@ __device__ __forceinline__ void tile_load(const OperandView& o, int R, int64_t k
             const bool live = U < (R / 32) * 2;
             const int64_t row = o.row0 + ((U >> 1) * 8 + rq_l) * 4;
             const int64_t k = k0 + ((U & 1) * 4 + c_l) * 4;
-            const bool row_in = live && row < o.n_rows;
-            const int64_t rowc = row_in ? row : 0;
-            const bool r0 = row_in, r1 = row_in && row + 1 < o.n_rows, r2 = row_in && row + 2 < o.n_rows,
-                       r3 = row_in && row + 3 < o.n_rows;
+            const int64_t rowc = (live && row < o.n_rows) ? row : 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const bool k_in = k + e < kend;
-                const int64_t kc = k_in ? k + e : k0;
-                float4 x = __ldg(reinterpret_cast<const float4*>(o.P + rowc + kc * o.s_k));
-                v[it * 4 + e] = sel4(x, r0 && k_in, r1 && k_in, r2 && k_in, r3 && k_in);
+                const int64_t kc = (k + e < kend) ? k + e : k0;
+                v[it * 4 + e] = __ldg(reinterpret_cast<const float4*>(o.P + rowc + kc * o.s_k));
                 if (MASK) vm[it * 4 + e] = __ldg(reinterpret_cast<const float4*>(o.mask + rowc + kc * o.m_k));
             }
         }
@@ -99,29 +97,45 @@ __device__ __forceinline__ void tile_load(const OperandView& o, int R, int64_t k
             const int64_t k = k0 + ((U & 1) * 4 + c_l) * 4;
             const bool ok = live && row < o.n_rows && k < kend;
             const int64_t rowc = ok ? row : o.row0, kc = ok ? k : k0;
-            const bool e1 = ok && k + 1 < kend, e2 = ok && k + 2 < kend, e3 = ok && k + 3 < kend;
             if (MODE == LD_KVEC) {
-                float4 x = __ldg(reinterpret_cast<const float4*>(o.P + rowc * o.s_row + kc));
-                v[it] = sel4(x, ok, e1, e2, e3);
+                v[it] = __ldg(reinterpret_cast<const float4*>(o.P + rowc * o.s_row + kc));
                 if (MASK) vm[it] = __ldg(reinterpret_cast<const float4*>(o.mask + rowc * o.m_row + kc));
             } else {
+                const bool e1 = ok && k + 1 < kend, e2 = ok && k + 2 < kend, e3 = ok && k + 3 < kend;
                 const float* src = o.P + rowc * o.s_row + kc * o.s_k;
-                float4 x;
-                x.x = __ldg(src);
-                x.y = __ldg(src + (e1 ? o.s_k : 0));
-                x.z = __ldg(src + (e2 ? 2 * o.s_k : 0));
-                x.w = __ldg(src + (e3 ? 3 * o.s_k : 0));
-                v[it] = sel4(x, ok, e1, e2, e3);
+                v[it].x = __ldg(src);
+                v[it].y = __ldg(src + (e1 ? o.s_k : 0));
+                v[it].z = __ldg(src + (e2 ? 2 * o.s_k : 0));
+                v[it].w = __ldg(src + (e3 ? 3 * o.s_k : 0));
                 if (MASK) {
                     const float* ms = o.mask + rowc * o.m_row + kc * o.m_k;
-                    float4 y;
-                    y.x = __ldg(ms);
-                    y.y = __ldg(ms + (e1 ? o.m_k : 0));
-                    y.z = __ldg(ms + (e2 ? 2 * o.m_k : 0));
-                    y.w = __ldg(ms + (e3 ? 3 * o.m_k : 0));
-                    vm[it] = y;
+                    vm[it].x = __ldg(ms);
+                    vm[it].y = __ldg(ms + (e1 ? o.m_k : 0));
+                    vm[it].z = __ldg(ms + (e2 ? 2 * o.m_k : 0));
+                    vm[it].w = __ldg(ms + (e3 ? 3 * o.m_k : 0));
                 }
             }
+        }
+    }
+}
+
+// L2 prefetch of a future stage's operand lines (fire and forget; one request per 128-byte line)
+template <int MODE>
+__device__ __forceinline__ void tile_prefetch(const OperandView& o, int R, int64_t k0, int64_t kend, int warp,
+                                              int lane) {
+    if (k0 >= kend) return;
+    if (MODE == LD_TRANS) {
+        // rows are contiguous: one line = 32 rows of one k; lanes 0..(R/32-1) x 32 k rows
+        const int k_l = lane;                       // 32 k per stage
+        for (int blk = warp; blk < R / 32; blk += TC_PROD_WARPS) {
+            const int64_t row = o.row0 + blk * 32;
+            if (row < o.n_rows && k0 + k_l < kend) prefetch_l2(o.P + row + (k0 + k_l) * o.s_k);
+        }
+    } else if (MODE == LD_KVEC) {
+        // one line = the 32 k of one row
+        for (int r = warp * 32 + lane; r < R; r += TC_PROD_WARPS * 32) {
+            const int64_t row = o.row0 + r;
+            if (row < o.n_rows) prefetch_l2(o.P + row * o.s_row + k0);
         }
     }
 }
@@ -135,9 +149,9 @@ __device__ __forceinline__ float4 apply_mask(float4 x, float4 y, int act) {
     return x;
 }
 
-// ---- phase 2: mask, split into hi/lo, store into the tile
+// ---- phase 2 (one iteration later): zero the out-of-range lanes, mask, split into hi/lo, store
 template <int MODE, int NIT, bool MASK>
-__device__ __forceinline__ void tile_store(const OperandView& o, int R, int warp, int lane,
+__device__ __forceinline__ void tile_store(const OperandView& o, int R, int64_t k0, int64_t kend, int warp, int lane,
                                            float4 (&v)[NIT], float4 (&vm)[NIT], float* hi, float* lo) {
     if (MODE == LD_TRANS) {
         const int rq_l = (lane >> 3) * 2 + (lane & 1), c_l = (lane >> 1) & 3;
@@ -146,18 +160,20 @@ __device__ __forceinline__ void tile_store(const OperandView& o, int R, int warp
             const int U = warp + TC_PROD_WARPS * it;
             if (U < (R / 32) * 2) {
                 const int r = ((U >> 1) * 8 + rq_l) * 4, c = (U & 1) * 4 + c_l;
-                float4 x0 = v[it * 4 + 0], x1 = v[it * 4 + 1], x2 = v[it * 4 + 2], x3 = v[it * 4 + 3];
-                if (MASK) {
-                    x0 = apply_mask(x0, vm[it * 4 + 0], o.mask_act);
-                    x1 = apply_mask(x1, vm[it * 4 + 1], o.mask_act);
-                    x2 = apply_mask(x2, vm[it * 4 + 2], o.mask_act);
-                    x3 = apply_mask(x3, vm[it * 4 + 3], o.mask_act);
+                const int64_t row = o.row0 + r, k = k0 + c * 4;
+                const bool r0 = row < o.n_rows, r1 = row + 1 < o.n_rows, r2 = row + 2 < o.n_rows, r3 = row + 3 < o.n_rows;
+                float4 x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool k_in = k + e < kend;
+                    x[e] = sel4(v[it * 4 + e], r0 && k_in, r1 && k_in, r2 && k_in, r3 && k_in);
+                    if (MASK) x[e] = apply_mask(x[e], vm[it * 4 + e], o.mask_act);
                 }
                 // 4x4 register transpose: row r+i gets (k, k+1, k+2, k+3)
-                split_store(hi + tile_off(R, r + 0, c), lo + tile_off(R, r + 0, c), make_float4(x0.x, x1.x, x2.x, x3.x));
-                split_store(hi + tile_off(R, r + 1, c), lo + tile_off(R, r + 1, c), make_float4(x0.y, x1.y, x2.y, x3.y));
-                split_store(hi + tile_off(R, r + 2, c), lo + tile_off(R, r + 2, c), make_float4(x0.z, x1.z, x2.z, x3.z));
-                split_store(hi + tile_off(R, r + 3, c), lo + tile_off(R, r + 3, c), make_float4(x0.w, x1.w, x2.w, x3.w));
+                split_store(hi + tile_off(R, r + 0, c), lo + tile_off(R, r + 0, c), make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
+                split_store(hi + tile_off(R, r + 1, c), lo + tile_off(R, r + 1, c), make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
+                split_store(hi + tile_off(R, r + 2, c), lo + tile_off(R, r + 2, c), make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
+                split_store(hi + tile_off(R, r + 3, c), lo + tile_off(R, r + 3, c), make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
             }
         }
     } else {
@@ -167,7 +183,9 @@ __device__ __forceinline__ void tile_store(const OperandView& o, int R, int warp
             const int U = warp + TC_PROD_WARPS * it;
             if (U < (R / 8) * 2) {
                 const int r = (U >> 1) * 8 + r_l, c = (U & 1) * 4 + c_l;
-                float4 x = v[it];
+                const int64_t row = o.row0 + r, k = k0 + c * 4;
+                const bool ok = row < o.n_rows && k < kend;
+                float4 x = sel4(v[it], ok, ok && k + 1 < kend, ok && k + 2 < kend, ok && k + 3 < kend);
                 if (MASK) x = apply_mask(x, vm[it], o.mask_act);
                 split_store(hi + tile_off(R, r, c), lo + tile_off(R, r, c), x);
             }
@@ -225,33 +243,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         // ------------------------------ producers ------------------------------------------
         OperandView oa{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, m0, g.M};
         OperandView ob{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, n0, g.N};
+        const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+        if (dbg) p.dbg[0] = clock64();
+        float4 va[kItemsA], vam[kItemsA], vb[kMaxItems], vbm[kMaxItems];
+#define TC_LOAD_A(MODE, MK) tile_load<MODE, kItemsA, MK>(oa, TC_BM, kl, kend, warp, lane, va, vam)
+#define TC_LOAD_B(MODE, MK) tile_load<MODE, kMaxItems, MK>(ob, BN, kl, kend, warp, lane, vb, vbm)
+#define TC_STORE_A(MODE, MK) tile_store<MODE, kItemsA, MK>(oa, TC_BM, k0, kend, warp, lane, va, vam, a_hi, a_lo)
+#define TC_STORE_B(MODE, MK) tile_store<MODE, kMaxItems, MK>(ob, BN, k0, kend, warp, lane, vb, vbm, b_hi, b_lo)
+#define TC_PF_A(MODE, MK) tile_prefetch<MODE>(oa, TC_BM, kp, kend, warp, lane)
+#define TC_PF_B(MODE, MK) tile_prefetch<MODE>(ob, BN, kp, kend, warp, lane)
+        {   // prologue: L2 prefetch of the first stages, register loads of stage 0
+            for (int d = 1; d <= 3; ++d) {
+                const int64_t kp = kbeg + (int64_t)d * TC_BK;
+                TC_MODE_SWITCH(p.a_mode, false, TC_PF_A);
+                TC_MODE_SWITCH(p.b_mode, false, TC_PF_B);
+            }
+            const int64_t kl = kbeg;
+            TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_LOAD_A);
+            TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_LOAD_B);
+        }
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
             const int64_t k0 = kbeg + (int64_t)kb * TC_BK;
-            float4 va[kItemsA], vam[kItemsA], vb[kMaxItems], vbm[kMaxItems];
-            // all global loads of the stage are in flight before anything waits on them (and before
-            // this warp blocks on the stage's empty barrier)
-#define TC_LOAD_A(MODE, MK) tile_load<MODE, kItemsA, MK>(oa, TC_BM, k0, kend, warp, lane, va, vam)
-#define TC_LOAD_B(MODE, MK) tile_load<MODE, kMaxItems, MK>(ob, BN, k0, kend, warp, lane, vb, vbm)
-            TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_LOAD_A);
-            TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_LOAD_B);
+            if (dbg && kb < 30) p.dbg[8 + kb * 8 + 0] = clock64();
             mbar_wait(&empty_bar[s], ph ^ 1u);
+            if (dbg && kb < 30) p.dbg[8 + kb * 8 + 2] = clock64();
             unsigned char* st = tiles + (size_t)s * stage_bytes;
             float* a_hi = reinterpret_cast<float*>(st);
             float* a_lo = reinterpret_cast<float*>(st + a_tile);
             float* b_hi = reinterpret_cast<float*>(st + 2 * a_tile);
             float* b_lo = reinterpret_cast<float*>(st + 2 * a_tile + b_tile);
-#define TC_STORE_A(MODE, MK) tile_store<MODE, kItemsA, MK>(oa, TC_BM, warp, lane, va, vam, a_hi, a_lo)
-#define TC_STORE_B(MODE, MK) tile_store<MODE, kMaxItems, MK>(ob, BN, warp, lane, vb, vbm, b_hi, b_lo)
+            // consume the registers loaded one iteration ago
             TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_STORE_A);
             TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_STORE_B);
+            if (dbg && kb < 30) p.dbg[8 + kb * 8 + 3] = clock64();
             fence_async_smem();                                           // generic -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (dbg && kb < 30) p.dbg[8 + kb * 8 + 4] = clock64();
+            // issue the next stage's loads (consumed after the next empty-barrier wait) and the L2
+            // prefetch of the stage four ahead
+            if (kb + 1 < nkb) {
+                const int64_t kl = k0 + TC_BK;
+                TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_LOAD_A);
+                TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_LOAD_B);
+                const int64_t kp = k0 + 4 * TC_BK;
+                TC_MODE_SWITCH(p.a_mode, false, TC_PF_A);
+                TC_MODE_SWITCH(p.b_mode, false, TC_PF_B);
+            }
+            if (dbg && kb < 30) p.dbg[8 + kb * 8 + 1] = clock64();
         }
         // ------------------------------ epilogue -------------------------------------------
+        if (dbg) p.dbg[1] = clock64();
         mbar_wait(accum_bar, 0);
+        if (dbg) p.dbg[2] = clock64();
         tc_fence_after();
         const int quad = warp & 3;                       // TMEM lane quadrant of this warp
         const int half = warp >> 2;                      // column half
@@ -308,8 +354,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
             }
         }
         tc_fence_before();
+        if (dbg) p.dbg[3] = clock64();
     } else {
         // ------------------------------ MMA issuer -----------------------------------------
+        const bool dbgm = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
         const uint32_t idesc = tf32_idesc(BN);
         // per K atom (8 k = two 16-byte chunks) the tiles advance by 2 * (R+1) * 16 bytes
         const uint32_t a_lbo = (TC_BM + 1) * 16u, b_lbo = ((uint32_t)BN + 1) * 16u;
@@ -318,6 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
             mbar_wait(&full_bar[s], ph);
+            if (dbgm && kb < 30) p.dbg[8 + kb * 8 + 5] = clock64();
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
@@ -336,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
                 }
                 umma_commit(&empty_bar[s]);              // frees the stage when these MMAs retire
                 if (kb == nkb - 1) umma_commit(accum_bar);
+                if (dbgm && kb < 30) p.dbg[8 + kb * 8 + 6] = clock64();
             }
             __syncwarp();
         }
@@ -368,8 +418,15 @@ int pick_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int
 
 }  // namespace
 
+static unsigned long long* g_dbg_buf = nullptr;
+extern "C" int ctr_debug_set_buffer(void* ptr) {
+    g_dbg_buf = reinterpret_cast<unsigned long long*>(ptr);
+    return 0;
+}
+
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     TcParams p;
+    p.dbg = g_dbg_buf;
     p.g = g;
     int BN;
     if (g.N >= 256) {

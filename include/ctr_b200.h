@@ -29,6 +29,7 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------------- */
 int         ctr_version(void);            /* ABI version, currently 1 */
 const char* ctr_last_error(void);
+int         ctr_debug_set_buffer(void* dev_u64_buffer);   /* optional: per-stage clock64 timeline of the tensor-core GEMM (>= 256 u64), NULL = off */
 int64_t     ctr_launch_count(void);       /* kernels launched by this library so far (process-wide) */
 
 /* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
