@@ -31,8 +31,10 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements of K per stage
-constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_PROD_WARPS + 1) * 32;
+constexpr int TC_PROD_WARPS = 8;          // producer warps per group
+constexpr int TC_GROUPS = 2;              // producer groups working on alternating K stages
+constexpr int TC_MMA_WARP = TC_PROD_WARPS * TC_GROUPS;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
 
 enum { LD_SCALAR = 0, LD_KVEC = 1, LD_TRANS = 2 };
 
@@ -219,7 +221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     uint64_t* accum_bar = empty_bar + S;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int group = wid / TC_PROD_WARPS;    // producer group (TC_GROUPS = the MMA warp)
+    const int warp = wid % TC_PROD_WARPS;     // warp index inside the group (item mapping)
     const int64_t m0 = (int64_t)blockIdx.y * TC_BM, n0 = (int64_t)blockIdx.x * BN;
     const int64_t kbeg = (int64_t)blockIdx.z * p.k_chunk;
     const int64_t kend = (kbeg + p.k_chunk < g.K) ? kbeg + p.k_chunk : g.K;
@@ -233,17 +237,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_PROD_WARPS) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
+    if (wid == TC_MMA_WARP) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < TC_PROD_WARPS) {
+    if (wid < TC_MMA_WARP) {
         // ------------------------------ producers ------------------------------------------
+        // group g stages the K blocks kb = g, g + TC_GROUPS, ...: while one group waits for its loads
+        // the other one is splitting/storing, so two stages of global loads are always in flight
         OperandView oa{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, m0, g.M};
         OperandView ob{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, n0, g.N};
         const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+        constexpr int NG = TC_GROUPS;
         if (dbg) p.dbg[0] = clock64();
         float4 va[kItemsA], vam[kItemsA], vb[kMaxItems], vbm[kMaxItems];
 #define TC_LOAD_A(MODE, MK) tile_load<MODE, kItemsA, MK>(oa, TC_BM, kl, kend, warp, lane, va, vam)
@@ -252,17 +259,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 #define TC_STORE_B(MODE, MK) tile_store<MODE, kMaxItems, MK>(ob, BN, k0, kend, warp, lane, vb, vbm, b_hi, b_lo)
 #define TC_PF_A(MODE, MK) tile_prefetch<MODE>(oa, TC_BM, kp, kend, warp, lane)
 #define TC_PF_B(MODE, MK) tile_prefetch<MODE>(ob, BN, kp, kend, warp, lane)
-        {   // prologue: L2 prefetch of the first stages, register loads of stage 0
-            for (int d = 1; d <= 3; ++d) {
-                const int64_t kp = kbeg + (int64_t)d * TC_BK;
+        if (group < nkb) {   // prologue: L2 prefetch of this group's next stages, register loads of its first
+            for (int d = 1; d <= 2; ++d) {
+                const int64_t kp = kbeg + (int64_t)(group + d * NG) * TC_BK;
                 TC_MODE_SWITCH(p.a_mode, false, TC_PF_A);
                 TC_MODE_SWITCH(p.b_mode, false, TC_PF_B);
             }
-            const int64_t kl = kbeg;
+            const int64_t kl = kbeg + (int64_t)group * TC_BK;
             TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_LOAD_A);
             TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_LOAD_B);
         }
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = group; kb < nkb; kb += NG) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
             const int64_t k0 = kbeg + (int64_t)kb * TC_BK;
@@ -284,18 +291,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
             if (dbg && kb < 30) p.dbg[8 + kb * 8 + 4] = clock64();
             // issue the next stage's loads (consumed after the next empty-barrier wait) and the L2
             // prefetch of the stage four ahead
-            if (kb + 1 < nkb) {
-                const int64_t kl = k0 + TC_BK;
+            if (kb + NG < nkb) {
+                const int64_t kl = k0 + (int64_t)NG * TC_BK;
                 TC_MODE_SWITCH(p.a_mode, oa.mask != nullptr, TC_LOAD_A);
                 TC_MODE_SWITCH(p.b_mode, ob.mask != nullptr, TC_LOAD_B);
-                const int64_t kp = k0 + 4 * TC_BK;
+                const int64_t kp = k0 + (int64_t)3 * NG * TC_BK;
                 TC_MODE_SWITCH(p.a_mode, false, TC_PF_A);
                 TC_MODE_SWITCH(p.b_mode, false, TC_PF_B);
             }
             if (dbg && kb < 30) p.dbg[8 + kb * 8 + 1] = clock64();
         }
-        // ------------------------------ epilogue -------------------------------------------
+        // ------------------------------ epilogue (group 0) ---------------------------------
         if (dbg) p.dbg[1] = clock64();
+        if (group == 0) {
         mbar_wait(accum_bar, 0);
         if (dbg) p.dbg[2] = clock64();
         tc_fence_after();
@@ -355,6 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         }
         tc_fence_before();
         if (dbg) p.dbg[3] = clock64();
+        }
     } else {
         // ------------------------------ MMA issuer -----------------------------------------
         const bool dbgm = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         }
     }
     __syncthreads();
-    if (warp == TC_PROD_WARPS) {
+    if (wid == TC_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
     }

@@ -117,6 +117,11 @@ class GatherPlan:
             self._ws = {B: ws}
         return ws
 
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def check_ids(self):
         """Raise IndexError (like nn.Embedding on CPU) if any id was out of range.  Synchronises."""
         if int(self.err_flag.item()) != 0:
@@ -143,6 +148,21 @@ class _FusedInput(torch.autograd.Function):
                   plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
                   _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
                   plan.n_shards, _stream())
+        ctx.plan_event = None
+        if grad_mode in ("rowwise", "sharded") and torch.is_grad_enabled() and B > 0:
+            # the duplicate-free plan of the backward depends only on X: build it now on a side stream
+            # so that it overlaps the forward tower instead of sitting on the backward's critical path
+            ws = plan.workspace(B)
+            side = plan.side_stream()
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, len(plan.plan_cols_host),
+                          _ptr(plan.plan_cols), _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]),
+                          ws["H"], _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                          _ptr(plan.err_flag), _stream())
+                ctx.plan_event = torch.cuda.Event()
+                ctx.plan_event.record(side)
         ctx.plan, ctx.grad_mode = plan, grad_mode
         ctx.want_blk, ctx.want_fm = want_blk, want_fm
         ctx.has_ldw = lin_dense_w is not None
@@ -192,10 +212,13 @@ class _FusedInput(torch.autograd.Function):
         else:  # row-wise: (unique ids, summed row grads) per table, returned as sparse COO
             ws = plan.workspace(B)
             n_plan = len(plan.plan_cols_host)
-            _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, n_plan, _ptr(plan.plan_cols),
-                      _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]), ws["H"],
-                      _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
-                      _ptr(plan.err_flag), _stream())
+            if ctx.plan_event is not None:
+                torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+            else:
+                _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, n_plan, _ptr(plan.plan_cols),
+                          _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]), ws["H"],
+                          _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                          _ptr(plan.err_flag), _stream())
             rg_emb = torch.empty(max(n_emb, 1), B, max(plan.D, 1), device=dev, dtype=torch.float32)
             rg_lin = torch.empty(max(plan.n_lin, 1), B, device=dev, dtype=torch.float32)
             _lib.call("ctr_scatter_bwd_rowwise", B, n_plan, _ptr(ws["inv"]), _ptr(ws["cnt"]),
