@@ -298,7 +298,15 @@ def run_gpu_arm(args):
         return ms
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms = timed(step_resident, args.steps, args.warmup)
+    prof_region = os.environ.get("CTR_PROFILE_REGION") == "1"   # `ncu --profile-from-start off`: timed region only
+    if prof_region:
+        for i in range(args.warmup):
+            step_resident(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+    ms = timed(step_resident, args.steps, 0 if prof_region else args.warmup)
+    if prof_region:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     launches = timed.launches
     model.check_ids()
