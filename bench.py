@@ -260,6 +260,7 @@ def run_gpu_arm(args):
         return float(loss.item())          # device -> host read of the step's result
 
     use_graph = (world == 1) and not args.no_graph
+    gstep = None
     if use_graph:
         # the whole fwd+loss+bwd step captured once as a CUDA graph and replayed (public API:
         # model.make_graphed_step); removes the ~30 per-launch host overheads from the step
@@ -282,14 +283,16 @@ def run_gpu_arm(args):
         for i in range(warmup):
             step_fn(i)
         barrier()
-        l0 = _lib.launch_count()
+        l0 = _lib.launch_count() + (gstep.replays * gstep.launches_per_replay if use_graph else 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             step_fn(warmup + i)
         e1.record()
         barrier()
-        timed.launches = _lib.launch_count() - l0
+        # kernels of libctr_b200.so inside the timed region: eager launches are counted by the library,
+        # graph replays launch the kernel nodes recorded at capture time
+        timed.launches = _lib.launch_count() + (gstep.replays * gstep.launches_per_replay if use_graph else 0) - l0
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)

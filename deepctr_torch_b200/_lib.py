@@ -63,6 +63,7 @@ SIGNATURES = {
     "ctr_bilinear_bwd": [_P, c_i64, c_int, c_int, _P, c_int, _P, c_i64, _P, c_i64, _P, c_i64, _P],
     "ctr_sumsq_acc": [_P, c_i64, c_f32, _P, _P],
     "ctr_debug_set_buffer": [_P],
+    "ctr_set_scratch": [_P, c_i64],
     "ctr_varlen_pool_fwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,
                             c_i64, _P, _P],
     "ctr_varlen_pool_bwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,
@@ -73,6 +74,7 @@ SPECIAL = {
     "ctr_last_error": ([], ctypes.c_char_p),
     "ctr_unique_plan_hash_slots": ([c_i64], c_i64),
     "ctr_launch_count": ([], c_i64),
+    "ctr_gemm_scratch_bytes": ([c_i64, c_i64, c_i64], c_i64),
 }
 
 

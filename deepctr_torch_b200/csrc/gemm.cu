@@ -306,14 +306,18 @@ __global__ void __launch_bounds__(256) predict_bwd_kernel(const float* __restric
 
 }  // namespace
 
-// CTR_GEMM=simt | tc forces one engine (tests, A/B profiling); default: tensor cores (3xTF32
-// split, gemm_tc.cu) for everything but tiny problems, FP32 FFMA tiles below that.
+// Engines: 0 = FP32 FFMA tiles (tiny problems), 1 = tcgen05 3xTF32 with in-kernel operand split
+// (gemm_tc.cu; needs no scratch), 2 = tcgen05 3xTF32 over pre-split packed operands (gemm_pk.cu;
+// the default whenever the caller registered enough scratch).  CTR_GEMM=simt | tc1 | pk forces one
+// (tests, A/B profiling).
 static int gemm_engine(const GemmArgs& g) {
     const char* e = getenv("CTR_GEMM");
     if (e && e[0] == 's') return 0;
     if (e && e[0] == 't') return 1;
+    if (e && e[0] == 'p') return 2;
     const double macs = (double)g.M * (double)g.N * (double)g.K;
-    return macs >= 2097152.0 ? 1 : 0;
+    if (macs < 2097152.0) return 0;
+    return gemm_pk_has_scratch(g.M, g.N, g.K) ? 2 : 1;
 }
 
 int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
@@ -324,7 +328,9 @@ int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
             CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
         return 0;
     }
-    if (gemm_engine(g) == 1) return launch_gemm_tc(g, st);
+    const int engine = gemm_engine(g);
+    if (engine == 2) return launch_gemm_pk(g, st);
+    if (engine == 1) return launch_gemm_tc(g, st);
     const bool big = (g.M >= 128 && g.N >= 96) || (g.N >= 128 && g.M >= 96);
     const int BM = big ? 128 : 64, BN = big ? 128 : 64, BK = 16;
     const int64_t gm = ceil_div64(g.M, BM), gn = ceil_div64(g.N, BN);

@@ -38,6 +38,10 @@ inline GemmArgs gemm_args_default() {
 // 3xTF32 kernel (gemm_tc.cu) and the FP32 FFMA tiles (gemm.cu)
 int launch_sgemm(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+// packed-operand engine (gemm_pk.cu): needs the scratch registered with ctr_set_scratch
+int launch_gemm_pk(const GemmArgs& g, cudaStream_t st);
+int64_t gemm_pk_scratch_bytes(int64_t M, int64_t N, int64_t K);
+bool gemm_pk_has_scratch(int64_t M, int64_t N, int64_t K);
 
 // out[n] = sum_m A[m*sam + n*san] * (mask ? act'(mask[m*smm + n*smn]) : 1) * (w ? w[m] : 1)
 int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, int64_t smm,

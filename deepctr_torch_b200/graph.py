@@ -36,8 +36,13 @@ class GraphedStep:
         model.check_ids()
         model.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        l0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.loss, self.y_pred = self._body()
+        # kernels of libctr_b200.so recorded as graph nodes: each replay launches exactly these
+        self.launches_per_replay = _lib.launch_count() - l0
+        self.replays = 0
 
     def _body(self):
         y_pred = self.model(self.X)
@@ -53,4 +58,5 @@ class GraphedStep:
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y.reshape(-1), non_blocking=True)
         self.graph.replay()
+        self.replays += 1
         return self.loss

@@ -44,6 +44,32 @@ def _round4(n):
     return (n + 3) // 4 * 4
 
 
+# ----------------------------------------------------------------------------------------------
+# scratch of the tensor-core GEMM engine (csrc/gemm_pk.cu): one caller-owned buffer per device,
+# grown to the largest requirement seen; the library only ever borrows it (ctr_set_scratch)
+# ----------------------------------------------------------------------------------------------
+_scratch_buf = {}
+_scratch_need = {}
+
+
+def ensure_gemm_scratch(dev, B, K, N):
+    """Make sure the registered scratch covers the three GEMMs of a [B,K] x [N,K]^T layer
+    (forward, input gradient, weight gradient)."""
+    key = (int(B), int(K), int(N))
+    need = _scratch_need.get(key)
+    if need is None:
+        fn = _lib.load().ctr_gemm_scratch_bytes
+        need = max(fn(B, N, K), fn(B, K, N), fn(N, K, B), fn(K, N, B))
+        _scratch_need[key] = need
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf = _scratch_buf.get(idx)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=dev)
+        _scratch_buf[idx] = buf
+        with torch.cuda.device(idx):
+            _lib.call("ctr_set_scratch", _ptr(buf), buf.numel())
+
+
 def act_code(name):
     if isinstance(name, str) and name.lower() in ACT_CODES:
         return ACT_CODES[name.lower()]
@@ -324,6 +350,7 @@ class _DnnLayer(torch.autograd.Function):
                 raise ValueError("dnn_layer: input width %d does not match weight width %d" % (K, Kw))
         swn, swk = (1, N) if w_kn else (Wc.shape[1], 1)
         y = torch.empty(B, N, device=x.device, dtype=torch.float32)
+        ensure_gemm_scratch(x.device, B, K, N)
         _lib.call("ctr_dnn_layer_fwd", _ptr(x), x.stride(0), _ptr(Wc), swn, swk, _ptr(bias),
                   _ptr(y), N, B, K, N, act, _stream())
         ctx.act, ctx.w_kn, ctx.has_bias = act, w_kn, bias is not None
@@ -548,6 +575,7 @@ class _CrossMatrix(torch.autograd.Function):
         W = kernels.contiguous()
         bv = bias.reshape(L, n).contiguous()
         xs, Us = [x], []
+        ensure_gemm_scratch(x.device, B, n, n)
         for l in range(L):
             U = torch.empty(B, n, device=x.device, dtype=torch.float32)
             nxt = torch.empty(B, n, device=x.device, dtype=torch.float32)

@@ -165,6 +165,16 @@ int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, int64_t swn, 
                       float* dW, int64_t sdwn, int64_t sdwk, float* db,
                       int64_t B, int K, int N, int act, void* stream);
 
+/* Scratch for the tensor-core GEMM engine (csrc/gemm_pk.cu): every GEMM-shaped entry point
+ * (ctr_dnn_layer_*, ctr_sgemm, ctr_cross_matrix_*, CrossNetMix projections) first re-tiles its two
+ * operands into pre-split (hi, lo) TF32 tiles inside a CALLER-OWNED device buffer.  The library
+ * never allocates: register one buffer per device with ctr_set_scratch (128-byte aligned; it must
+ * stay alive and must not be shared by launches that may run concurrently on different streams);
+ * ctr_gemm_scratch_bytes gives the requirement of one C[M,N] = A[M,K] B[N,K]^T.  Without enough
+ * scratch the GEMMs run on the slower in-kernel-split engine (csrc/gemm_tc.cu). */
+int64_t ctr_gemm_scratch_bytes(int64_t M, int64_t N, int64_t K);
+int ctr_set_scratch(void* ptr, int64_t bytes);
+
 /* generic fp32 GEMM used by the layer kernels and exposed for composition:
  *   C[m,n] (+)= sum_k A[m*sam + k*sak] * Bm[n*sbn + k*sbk]      (any strides, in elements) */
 int ctr_sgemm(int64_t M, int64_t N, int64_t K,

@@ -10,7 +10,7 @@ cols = [O.sparse_col("C%d" % i, 20000, 16) for i in range(26)] + [O.dense_col("I
 cfg = O.make_cfg("DeepFM", cols, cols, init_std=0.05, l2_reg_linear=0, l2_reg_embedding=0, dnn_hidden_units=[256, 128])
 X, y = O.synthetic_batch(cfg, 4096, seed=11, zipf_alpha=1.05)
 ref = None
-for engine in ("simt", "tc"):
+for engine in ("simt", "tc1", "pk"):
     for mode in ("rowwise", "dense"):
         os.environ["CTR_GEMM"] = engine
         m = build_model(cfg, "cuda:0", table_grad=mode)

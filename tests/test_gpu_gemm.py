@@ -1,4 +1,5 @@
-"""The two GEMM engines behind every dense op (tcgen05 3xTF32 split / FP32 FFMA tiles) against
+"""The GEMM engines behind every dense op (tcgen05 3xTF32 over packed operands / tcgen05 3xTF32 with
+in-kernel split / FP32 FFMA tiles) against
 an fp64 torch reference, for the operand layouts the tower uses (NT forward, NN dgrad, TN wgrad
 with split-K), odd sizes, strided leading dimensions and the fused prologue/epilogues."""
 import os
@@ -16,12 +17,13 @@ DEV = "cuda:0"
 def _sgemm(A, sam, sak, Bm, sbn, sbk, M, N, K, accumulate=False, C=None):
     if C is None:
         C = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.ensure_gemm_scratch(torch.device(DEV), M, K, N)
     _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), sam, sak, ops._ptr(Bm), sbn, sbk, ops._ptr(C), C.stride(0),
               1 if accumulate else 0, ops._stream())
     return C
 
 
-@pytest.fixture(params=["tc", "simt"])
+@pytest.fixture(params=["pk", "tc1", "simt"])
 def engine(request):
     old = os.environ.get("CTR_GEMM")
     os.environ["CTR_GEMM"] = request.param
