@@ -37,7 +37,8 @@ namespace {
 
 constexpr int PK_KB = 16;            // k per packed tile (4 chunks of 16 bytes)
 constexpr int PK_AR = 128;           // rows of an A tile (one UMMA M)
-constexpr int PK_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
+constexpr int PK_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int PK_STG_PITCH = 36;     // floats per row of an epilogue staging tile (32 + 4: conflict-free)
 
 // ---------------------------------------------------------------------------------------------
 // phase 1: pack
@@ -76,40 +77,56 @@ __device__ __forceinline__ float4 pk_mask4(float4 x, float4 y, int act) {
 }
 
 // K-contiguous operand (s_k == 1): one thread = (row, 16-k block): 64 contiguous bytes in, 8 x 16
-// bytes out; lanes map to consecutive rows so every store instruction writes 512 contiguous bytes.
-__global__ void __launch_bounds__(256) pack_kvec_kernel(PackArgs a) {
+// bytes out.  Lanes map to consecutive rows, so every store instruction writes 512 contiguous bytes;
+// a block owns 128 rows x 4 consecutive k blocks and its two halves read neighbouring 64-byte
+// pieces of the same rows at the same time, so every 128-byte line of the source is consumed while
+// it is hot (sweeping one k block over all rows first re-fetched each line 27 / 2 times apart and
+// ran at 3.8 TB/s).
+constexpr int PKV_KG = 4;     // k blocks per CTA item
+template <bool MASK>
+__global__ void __launch_bounds__(256, 2) pack_kvec_kernel(PackArgs a) {
     const int64_t rows_pad = a.n_rb * a.R;
-    const int64_t total = rows_pad * a.nkb;
+    const int64_t n_rg = (rows_pad + 127) / 128;
+    const int64_t n_kg = (a.nkb + PKV_KG - 1) / PKV_KG;
+    const int r_l = threadIdx.x & 127, kpar = threadIdx.x >> 7;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t kb = i / rows_pad, row = i - kb * rows_pad;
+    for (int64_t item = blockIdx.x; item < n_rg * n_kg; item += gridDim.x) {
+        const int64_t rg = item / n_kg, kg = item - rg * n_kg;
+        const int64_t row = rg * 128 + r_l;
+        if (row >= rows_pad) continue;
         const int64_t rb = row / a.R;
         const int r = (int)(row - rb * a.R);
-        const int64_t k0 = kb * PK_KB;
-        float4 v[4];
-        if (row < a.n_rows) {
-            const float* src = a.P + row * a.s_row + k0;
-            const float* msk = a.mask ? a.mask + row * a.m_row + k0 : nullptr;
+        const bool row_ok = row < a.n_rows;
+        const float* src = a.P + (row_ok ? row : 0) * a.s_row;
+        const float* msk = MASK ? a.mask + (row_ok ? row : 0) * a.m_row : nullptr;
+        float4 v[PKV_KG / 2][4], mv[MASK ? PKV_KG / 2 : 1][4];
+#pragma unroll
+        for (int j = 0; j < PKV_KG / 2; ++j) {
+            const int64_t kb = kg * PKV_KG + kpar + 2 * j;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int64_t k = k0 + c * 4;
-                if (k < a.K) {      // whole 16-byte groups are readable (host checks ld >= round4(K))
-                    v[c] = __ldg(reinterpret_cast<const float4*>(src + c * 4));
-                    if (msk) v[c] = pk_mask4(v[c], __ldg(reinterpret_cast<const float4*>(msk + c * 4)), a.mask_act);
-                    if (k + 1 >= a.K) v[c].y = 0.f;
-                    if (k + 2 >= a.K) v[c].z = 0.f;
-                    if (k + 3 >= a.K) v[c].w = 0.f;
-                } else {
-                    v[c] = z;
-                }
+                const int64_t k = kb * PK_KB + c * 4;
+                const bool ok = row_ok && k < a.K;       // whole 16-byte groups are readable (host: ld >= round4(K))
+                v[j][c] = ok ? __ldg(reinterpret_cast<const float4*>(src + k)) : z;
+                if (MASK) mv[j][c] = ok ? __ldg(reinterpret_cast<const float4*>(msk + k)) : z;
             }
-        } else {
-            v[0] = v[1] = v[2] = v[3] = z;
         }
-        const int64_t base = pk_tile_base(a, rb, kb);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pk_store(a.out, base, a.R, c, r, v[c]);
+        for (int j = 0; j < PKV_KG / 2; ++j) {
+            const int64_t kb = kg * PKV_KG + kpar + 2 * j;
+            if (kb >= a.nkb) continue;
+            const int64_t base = pk_tile_base(a, rb, kb);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t k = kb * PK_KB + c * 4;
+                float4 x = v[j][c];
+                if (MASK) x = pk_mask4(x, mv[j][c], a.mask_act);
+                if (k + 1 >= a.K) x.y = 0.f;
+                if (k + 2 >= a.K) x.z = 0.f;
+                if (k + 3 >= a.K) x.w = 0.f;
+                pk_store(a.out, base, a.R, c, r, x);
+            }
+        }
     }
 }
 
@@ -187,9 +204,10 @@ int launch_pack(const PackArgs& a, cudaStream_t st) {
                        (!a.mask || (a.m_row == 1 && a.m_k % 4 == 0 && a.m_k >= R4 && pk_al16(a.mask)));
     const int64_t cap = (int64_t)ctr_sm_count() * 8;
     if (kvec) {
-        int64_t blocks = ceil_div64(a.n_rb * a.R * a.nkb, 256);
+        int64_t blocks = ceil_div64(a.n_rb * a.R, 128) * ceil_div64(a.nkb, PKV_KG);
         if (blocks > cap) blocks = cap;
-        pack_kvec_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+        if (a.mask) pack_kvec_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+        else pack_kvec_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
         CTR_LAUNCH_OK("pack_kvec_kernel");
     } else if (trans) {
         int64_t blocks = ceil_div64(a.n_rb * a.R * a.nkb, 256);
@@ -227,6 +245,87 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// 4 consecutive floats of one row with the same (warp-uniform) addressing rules: 128-bit access when
+// the 4 elements exist and the address is 16-byte aligned, element-wise otherwise
+__device__ __forceinline__ float4 ld4_or_scalar(const float* p, int nvalid, bool vec) {
+    if (vec && nvalid == 4) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.x = __ldg(p);
+    if (nvalid > 1) r.y = __ldg(p + 1);
+    if (nvalid > 2) r.z = __ldg(p + 2);
+    if (nvalid > 3) r.w = __ldg(p + 3);
+    return r;
+}
+__device__ __forceinline__ void st4_or_scalar(float* p, float4 v, int nvalid, bool vec) {
+    if (vec && nvalid == 4) {
+        *reinterpret_cast<float4*>(p) = v;
+        return;
+    }
+    p[0] = v.x;
+    if (nvalid > 1) p[1] = v.y;
+    if (nvalid > 2) p[2] = v.z;
+    if (nvalid > 3) p[3] = v.w;
+}
+__device__ __forceinline__ bool row_vec_ok(const float* base, int64_t ld, int64_t n) {
+    return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (ld % 4 == 0) && (n % 4 == 0);
+}
+
+// epilogue of 4 consecutive outputs C[m, n..n+3] (nvalid of them exist)
+template <int EPI>
+__device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, int64_t m, int64_t n, int nvalid, bool split) {
+    if (EPI == EPI_BIAS_ACT) {
+        if (g.bias) {
+            const float4 b = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        v.x = act_apply(g.act, v.x); v.y = act_apply(g.act, v.y);
+        v.z = act_apply(g.act, v.z); v.w = act_apply(g.act, v.w);
+    } else if (EPI == EPI_MUL_ACTGRAD) {
+        const float4 y = ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n));
+        v.x *= act_grad_from_y(g.act, y.x); v.y *= act_grad_from_y(g.act, y.y);
+        v.z *= act_grad_from_y(g.act, y.z); v.w *= act_grad_from_y(g.act, y.w);
+    } else if (EPI == EPI_CROSS) {
+        const float4 b = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
+        const float4 u = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+        if (g.out2) st4_or_scalar(g.out2 + m * g.ldout2 + n, u, nvalid, row_vec_ok(g.out2, g.ldout2, n));
+        const float4 x0 = ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n));
+        const float4 xl = ld4_or_scalar(g.aux2 + m * g.ldaux2 + n, nvalid, row_vec_ok(g.aux2, g.ldaux2, n));
+        v = make_float4(x0.x * u.x + xl.x, x0.y * u.y + xl.y, x0.z * u.z + xl.z, x0.w * u.w + xl.w);
+    }
+    float* crow = g.C + m * g.ldc + n;
+    const bool cvec = row_vec_ok(g.C, g.ldc, n);
+    if (split) {
+        if (cvec && nvalid == 4) {
+            red_add4(crow, v);
+        } else {
+            atomicAdd(crow, v.x);
+            if (nvalid > 1) atomicAdd(crow + 1, v.y);
+            if (nvalid > 2) atomicAdd(crow + 2, v.z);
+            if (nvalid > 3) atomicAdd(crow + 3, v.w);
+        }
+    } else {
+        if (g.accumulate) {
+            const float4 c = ld4_or_scalar(crow, nvalid, cvec);
+            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+        }
+        st4_or_scalar(crow, v, nvalid, cvec);
+    }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
@@ -244,6 +343,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const int64_t kb_beg = (int64_t)blockIdx.z * p.kb_per_split;
     const int64_t kb_end = (kb_beg + p.kb_per_split < p.nkb) ? kb_beg + p.kb_per_split : p.nkb;
     const int nkb = (int)(kb_end - kb_beg);
+    const bool split = gridDim.z > 1;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -308,64 +408,51 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             __syncwarp();
         }
     } else {
-        // ------------------------------ epilogue (4 warps) ----------------------------------
+        // ------------------------------ epilogue (8 warps) ----------------------------------
+        // Two warps per TMEM lane quadrant, alternating 32-column chunks.  tcgen05.ld hands every
+        // thread ONE row (32 consecutive columns); written like that to C a warp would touch 32
+        // different rows per store.  So each chunk is transposed through a padded per-warp staging
+        // tile in shared memory (the pipeline stages are free once accum_bar fires) and the epilogue
+        // math + stores run in the coalesced domain: 8 lanes cover 128 contiguous bytes of a row.
+        const int ew = wid - 2;
+        const int quad = wid & 3;                         // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;
+        float* stg = reinterpret_cast<float*>(smem_raw) + (size_t)ew * (32 * PK_STG_PITCH);
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int quad = wid & 3;                         // TMEM lane quadrant this warp may read
-        const bool split = gridDim.z > 1;
-        const bool vec_store = !split && !g.accumulate && (g.ldc % 4 == 0) &&
-                               ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && g.epilogue != EPI_CROSS;
         const int64_t n0 = nblk * BN;
+        const int nchunks = (BN + 31) / 32;
         for (int mt = 0; mt < MT; ++mt) {
-            const int64_t m = (mblk * MT + mt) * PK_AR + quad * 32 + lane;
-            if ((mblk * MT + mt) * PK_AR >= g.M) break;   // whole tile out of range (warp-uniform)
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            const int64_t m_base = (mblk * MT + mt) * PK_AR + quad * 32;
+            if (m_base >= g.M) break;                     // warp-uniform
+            for (int ci = half; ci < nchunks; ci += 2) {
+                const int c0 = ci * 32;
                 if (n0 + c0 >= g.N) break;                // warp-uniform
-                uint32_t raw[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c0), raw);
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c0), raw);
                 tmem_ld_wait();
-                if (m < g.M) {
-                    float out[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int64_t n = n0 + c0 + j;
-                        float v = __uint_as_float(raw[j]);
-                        if (n < g.N) {
-                            switch (g.epilogue) {
-                                case EPI_BIAS_ACT:
-                                    if (g.bias) v += __ldg(g.bias + n);
-                                    v = act_apply(g.act, v);
-                                    break;
-                                case EPI_MUL_ACTGRAD:
-                                    v *= act_grad_from_y(g.act, __ldg(g.aux + m * g.ldaux + n));
-                                    break;
-                                case EPI_CROSS: {
-                                    const float u = v + __ldg(g.bias + n);
-                                    if (g.out2) g.out2[m * g.ldout2 + n] = u;
-                                    v = __ldg(g.aux + m * g.ldaux + n) * u + __ldg(g.aux2 + m * g.ldaux2 + n);
-                                    break;
-                                }
-                                default: break;
-                            }
-                        }
-                        out[j] = v;
-                    }
-                    float* crow = g.C + m * g.ldc + n0 + c0;
-                    if (vec_store && n0 + c0 + 15 < g.N) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(crow + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (n0 + c0 + j < g.N) {
-                                if (split) atomicAdd(crow + j, out[j]);
-                                else if (g.accumulate) crow[j] += out[j];
-                                else crow[j] = out[j];
-                            }
-                        }
-                    }
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * PK_STG_PITCH + 4 * j) =
+                        make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+                __syncwarp();
+                const int colq = lane & 7;
+                const int col = c0 + 4 * colq;            // column inside the CTA's N tile
+                const int64_t n = n0 + col;
+                // columns of this chunk that belong to the tile AND to the matrix
+                int nvalid = 0;
+                if (col < BN && n < g.N) {
+                    nvalid = BN - col < 4 ? BN - col : 4;
+                    if (g.N - n < nvalid) nvalid = (int)(g.N - n);
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3);
+                    const int64_t m = m_base + r;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + r * PK_STG_PITCH + 4 * colq);
+                    if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, m, n, nvalid, split);
+                }
+                __syncwarp();
             }
         }
         tc_fence_before();
@@ -500,11 +587,20 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const size_t smem = (size_t)c.stages * stage_bytes + (2 * c.stages + 1) * sizeof(uint64_t) + 16;
     static bool configured = false;
     if (!configured) {
-        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        const int max_smem = 220 * 1024;
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
     dim3 grid((unsigned)c.gn, (unsigned)c.gm, (unsigned)c.splits);
-    gemm_pk_kernel<<<grid, PK_THREADS, smem, st>>>(p);
+    switch (g.epilogue) {
+        case EPI_BIAS_ACT: gemm_pk_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_MUL_ACTGRAD: gemm_pk_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_CROSS: gemm_pk_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
+        default: gemm_pk_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
+    }
     CTR_LAUNCH_OK("gemm_pk_kernel");
     return 0;
 }

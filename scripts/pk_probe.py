@@ -46,6 +46,27 @@ if what == "check":
             worst = max(worst, e if e == e else 1e9)
     sys.exit(0 if worst < 5e-6 else 1)
 
+if what == "bias":
+    # Is the tensor core's fp32 accumulation rounding symmetric?  C(+A) + C(-A) is exactly 0 for
+    # round-to-nearest / toward-zero, and about -2 x bias for a floor-like (toward -inf) truncation.
+    for engine in ("pk", "simt"):
+        os.environ["CTR_GEMM"] = engine
+        for (M, N, K, pos) in [(256, 256, 512, True), (256, 256, 512, False), (1024, 256, 128, False)]:
+            A = torch.rand(M, K, device="cuda", generator=g) if pos else torch.randn(M, K, device="cuda", generator=g)
+            Bm = torch.rand(N, K, device="cuda", generator=g) if pos else torch.randn(N, K, device="cuda", generator=g)
+            C1 = gemm(A, K, 1, Bm, K, 1, M, N, K).clone()
+            An = (-A).contiguous()
+            C2 = gemm(An, K, 1, Bm, K, 1, M, N, K).clone()
+            torch.cuda.synchronize()
+            ref = A.double() @ Bm.double().t()
+            scale = float(ref.abs().mean())
+            e1 = (C1.double() - ref) / scale
+            e2 = (C2.double() + ref) / scale
+            print("%s M=%d N=%d K=%d %s: mean signed err C(+A) %+.3e  C(-A) %+.3e  mean(C(+A)+C(-A)) %+.3e  rms err %.3e"
+                  % (engine, M, N, K, "positive" if pos else "gaussian", float(e1.mean()), float(e2.mean()),
+                     float(((C1 + C2).double() / scale).mean()), float(e1.pow(2).mean().sqrt())), flush=True)
+    sys.exit(0)
+
 B = 65536
 cases = [("fwd L1  C[B,256]   = X[B,432] W1^T", "nt", B, 256, 432),
          ("fwd L2  C[B,128]   = H[B,256] W2^T", "nt", B, 128, 256),
