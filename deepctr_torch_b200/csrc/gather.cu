@@ -566,28 +566,42 @@ __global__ void __launch_bounds__(256) plan_finalize_kernel(int64_t B, int n_col
     }
 }
 
+// dw[k] = sum_b g[b] * X[b, cols[k]]: one thread per sample (grid-stride), up to 16 columns per pass in
+// registers, warp-shuffle + shared-memory reduction, one atomicAdd per column and block
 __global__ void __launch_bounds__(256) lin_dense_wgrad_kernel(const float* __restrict__ X,
                                                               int64_t ldx, int64_t B, int n,
                                                               const int32_t* __restrict__ cols,
                                                               const float* __restrict__ g, float* dw) {
-    // thread k of each group of n accumulates column k over a strided set of samples
-    extern __shared__ float s_acc[];
-    for (int k = threadIdx.x; k < n; k += blockDim.x) s_acc[k] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int k0 = 0; k0 < n; k0 += 32) {
-        const int k = k0 + lane;
-        float acc = 0.f;
-        if (k < n) {
-            const int c = cols[k];
-            for (int64_t b = warp0; b < B; b += nwarps) acc += __ldg(g + b) * __ldg(X + b * ldx + c);
-            atomicAdd(&s_acc[k], acc);
+    __shared__ float s_part[8][16];
+    __shared__ int s_col[16];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        const int nk = (n - k0 < 16) ? n - k0 : 16;
+        __syncthreads();
+        if (threadIdx.x < 16) s_col[threadIdx.x] = cols[k0 + (threadIdx.x < nk ? threadIdx.x : 0)];
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+            const float gb = __ldg(g + b);
+            const float* xrow = X + b * ldx;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (k < nk) acc[k] += gb * __ldg(xrow + s_col[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float v = warp_sum(acc[k]);
+            if (lane == 0) s_part[wid][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < nk) {
+            float v = 0.f;
+            for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
+            atomicAdd(dw + k0 + threadIdx.x, v);
         }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(dw + k, s_acc[k]);
 }
 
 int lpr_for_dim(int D) {
@@ -812,7 +826,7 @@ extern "C" int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n
     cudaStream_t st = as_stream(stream);
     CTR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n, st));
     if (B == 0) return 0;
-    lin_dense_wgrad_kernel<<<sample_grid(B, 8 * 64, 2), 256, sizeof(float) * n, st>>>(X, ldx, B, n, cols, g, dw);
+    lin_dense_wgrad_kernel<<<sample_grid(B, 256, 2), 256, 0, st>>>(X, ldx, B, n, cols, g, dw);
     CTR_LAUNCH_OK("lin_dense_wgrad_kernel");
     return 0;
 }

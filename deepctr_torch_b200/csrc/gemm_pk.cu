@@ -283,23 +283,29 @@ __device__ __forceinline__ bool row_vec_ok(const float* base, int64_t ld, int64_
     return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (ld % 4 == 0) && (n % 4 == 0);
 }
 
-// epilogue of 4 consecutive outputs C[m, n..n+3] (nvalid of them exist)
+__device__ __forceinline__ float4 act4(int act, float4 v) {
+    if (act == CTR_ACT_RELU) return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    if (act == CTR_ACT_LINEAR) return v;
+    return make_float4(act_apply(act, v.x), act_apply(act, v.y), act_apply(act, v.z), act_apply(act, v.w));
+}
+__device__ __forceinline__ float4 actgrad4(int act, float4 v, float4 y) {
+    if (act == CTR_ACT_RELU)
+        return make_float4(y.x > 0.f ? v.x : 0.f, y.y > 0.f ? v.y : 0.f, y.z > 0.f ? v.z : 0.f, y.w > 0.f ? v.w : 0.f);
+    if (act == CTR_ACT_LINEAR) return v;
+    return make_float4(v.x * act_grad_from_y(act, y.x), v.y * act_grad_from_y(act, y.y), v.z * act_grad_from_y(act, y.z),
+                       v.w * act_grad_from_y(act, y.w));
+}
+
+// epilogue of 4 consecutive outputs C[m, n..n+3] (nvalid of them exist); b4 = bias[n..n+3] (or zeros)
 template <int EPI>
-__device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, int64_t m, int64_t n, int nvalid, bool split) {
+__device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, float4 b4, int64_t m, int64_t n, int nvalid,
+                                          bool split) {
     if (EPI == EPI_BIAS_ACT) {
-        if (g.bias) {
-            const float4 b = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
-        v.x = act_apply(g.act, v.x); v.y = act_apply(g.act, v.y);
-        v.z = act_apply(g.act, v.z); v.w = act_apply(g.act, v.w);
+        v = act4(g.act, make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w));
     } else if (EPI == EPI_MUL_ACTGRAD) {
-        const float4 y = ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n));
-        v.x *= act_grad_from_y(g.act, y.x); v.y *= act_grad_from_y(g.act, y.y);
-        v.z *= act_grad_from_y(g.act, y.z); v.w *= act_grad_from_y(g.act, y.w);
+        v = actgrad4(g.act, v, ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n)));
     } else if (EPI == EPI_CROSS) {
-        const float4 b = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
-        const float4 u = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+        const float4 u = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
         if (g.out2) st4_or_scalar(g.out2 + m * g.ldout2 + n, u, nvalid, row_vec_ok(g.out2, g.ldout2, n));
         const float4 x0 = ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n));
         const float4 xl = ld4_or_scalar(g.aux2 + m * g.ldaux2 + n, nvalid, row_vec_ok(g.aux2, g.ldaux2, n));
@@ -445,12 +451,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                     nvalid = BN - col < 4 ? BN - col : 4;
                     if (g.N - n < nvalid) nvalid = (int)(g.N - n);
                 }
-#pragma unroll
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((EPI == EPI_BIAS_ACT || EPI == EPI_CROSS) && g.bias && nvalid > 0)
+                    b4 = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
+                // not unrolled on purpose: the body (with its activation variants) stays a few dozen
+                // instructions, so the whole epilogue fits the instruction cache
+#pragma unroll 1
                 for (int i = 0; i < 8; ++i) {
                     const int r = 4 * i + (lane >> 3);
                     const int64_t m = m_base + r;
                     const float4 v = *reinterpret_cast<const float4*>(stg + r * PK_STG_PITCH + 4 * colq);
-                    if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, m, n, nvalid, split);
+                    if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, b4, m, n, nvalid, split);
                 }
                 __syncwarp();
             }
