@@ -226,14 +226,140 @@ int launch_pack(const PackArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // phase 2: GEMM over packed tiles
 // ---------------------------------------------------------------------------------------------
-struct PkParams {
-    GemmArgs g;                  // M, N, epilogue fields (A/B pointers unused here)
-    const float* Ap;             // packed A: row blocks of 128
-    const float* Bp;             // packed B: row blocks of BN
-    int64_t nkb;                 // K blocks of 16 in the packed operands
-    int64_t kb_per_split;
-    int BN, MT, stages, tmem_cols;
+enum { OP_PACKED = 0, OP_KVEC = 1, OP_TRANS = 2, OP_SCALAR = 3 };
+
+// An operand that is converted INSIDE the GEMM (mode != OP_PACKED): the converter warps fetch fp32
+// pieces with cp.async straight into shared memory, split them into hi/lo and write the MMA-ready
+// tile — no packed copy of the operand ever exists in HBM.
+struct StreamOp {
+    const float* P; int64_t s_row, s_k;            // P(row,k) = P[row*s_row + k*s_k]
+    const float* mask; int64_t m_row, m_k; int mask_act;
+    int64_t n_rows;
+    int mode;
 };
+
+struct PkParams {
+    GemmArgs g;                  // M, N, K, epilogue fields
+    const float* Ap;             // packed A (row blocks of 128) when sa.mode == OP_PACKED
+    const float* Bp;             // packed B (row blocks of BN)  when sb.mode == OP_PACKED
+    StreamOp sa, sb;
+    int64_t nkb;                 // K blocks of 16
+    int64_t kb_per_split;
+    int BN, MT, SA, SB, depth, tmem_cols;
+    uint32_t off_b, off_raw, off_bar;     // shared-memory layout (bytes): A ring at 0
+    int slots_a, slots_b;                 // 16-byte raw slots per converter thread and depth
+};
+
+constexpr int PK_CONV_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// address (floats) of chunk c of row r inside an MMA tile made of sub-tiles of `sub` rows
+// ([hi | lo] x [4 chunks] x [sub rows] x 16 bytes per sub-tile)
+__device__ __forceinline__ int tile_float_off(int sub, int r, int c) {
+    const int st = r / sub, rr = r - st * sub;
+    return st * (sub * 32) + (c * sub + rr) * 4;
+}
+__device__ __forceinline__ void split_to_tile(float* tile, int sub, int r, int c, float4 v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    float* ph = tile + tile_float_off(sub, r, c);
+    *reinterpret_cast<float4*>(ph) = hi;
+    *reinterpret_cast<float4*>(ph + sub * 16) = lo;
+}
+
+// ---- converter, phase 1: issue the cp.async's of one 16-k stage of one operand.  `slots` are this
+// thread's raw slots of the stage (slot q at slots[q * 256]: [0,4) data, [4,8) mask, so that
+// consecutive lanes touch consecutive 16-byte words); every slot is written by exactly one
+// thread and later read by the same thread, so no barrier is needed between the two phases.
+// Out-of-range rows / k are zero-filled by the copy itself (src-size < cp-size).
+__device__ __forceinline__ void stream_issue(const StreamOp& o, int R, int64_t row0, int64_t k0, int64_t K,
+                                             float4* slots, int ct) {
+    if (o.mode == OP_TRANS) {
+        // one group per thread: 4 consecutive rows x 4 consecutive k (4 x 16 bytes along the rows)
+        const int RQ = R >> 2;
+        const int rq = ct % RQ, c = ct / RQ;
+        const int64_t row = row0 + 4 * rq;
+        const bool live = ct < R;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t k = k0 + 4 * c + e;
+            int bytes = 0;
+            if (live && k < K && row < o.n_rows) bytes = (o.n_rows - row >= 4) ? 16 : (int)(o.n_rows - row) * 4;
+            cp_async16(&slots[(e) * PK_CONV_THREADS], bytes ? o.P + row + k * o.s_k : o.P, bytes);
+            if (o.mask) cp_async16(&slots[(4 + e) * PK_CONV_THREADS], bytes ? o.mask + row + k * o.m_k : o.mask, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = ct + PK_CONV_THREADS * j;
+            const int c = idx / R, r = idx - c * R;
+            const int64_t row = row0 + r, k = k0 + 4 * c;
+            const bool live = c < 4 && row < o.n_rows;
+            if (o.mode == OP_KVEC) {
+                int bytes = 0;
+                if (live && k < K) bytes = (K - k >= 4) ? 16 : (int)(K - k) * 4;
+                cp_async16(&slots[(j) * PK_CONV_THREADS], bytes ? o.P + row * o.s_row + k : o.P, bytes);
+                if (o.mask) cp_async16(&slots[(4 + j) * PK_CONV_THREADS], bytes ? o.mask + row * o.m_row + k : o.mask, bytes);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = live && k + e < K;
+                    cp_async4(reinterpret_cast<float*>(&slots[(j) * PK_CONV_THREADS]) + e, ok ? o.P + row * o.s_row + (k + e) * o.s_k : o.P, ok ? 4 : 0);
+                    if (o.mask)
+                        cp_async4(reinterpret_cast<float*>(&slots[(4 + j) * PK_CONV_THREADS]) + e,
+                                  ok ? o.mask + row * o.m_row + (k + e) * o.m_k : o.mask, ok ? 4 : 0);
+                }
+            }
+        }
+    }
+}
+
+// ---- converter, phase 2: own raw slots -> (mask) -> hi/lo split -> MMA tile
+__device__ __forceinline__ void stream_convert(const StreamOp& o, int R, int sub, float* tile, const float4* slots, int ct) {
+    if (o.mode == OP_TRANS) {
+        if (ct >= R) return;
+        const int RQ = R >> 2;
+        const int rq = ct % RQ, c = ct / RQ;
+        float4 x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            x[e] = slots[e * PK_CONV_THREADS];
+            if (o.mask) x[e] = pk_mask4(x[e], slots[(4 + e) * PK_CONV_THREADS], o.mask_act);
+        }
+        // 4x4 register transpose: row 4rq+i gets (k, k+1, k+2, k+3); the starting row is rotated by the
+        // lane so that neighbouring lanes (64 bytes apart) do not hit the same banks
+        const float4 t0 = make_float4(x[0].x, x[1].x, x[2].x, x[3].x), t1 = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
+        const float4 t2 = make_float4(x[0].z, x[1].z, x[2].z, x[3].z), t3 = make_float4(x[0].w, x[1].w, x[2].w, x[3].w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ii = (i + rq) & 3;
+            const float4 t = ii == 0 ? t0 : (ii == 1 ? t1 : (ii == 2 ? t2 : t3));
+            split_to_tile(tile, sub, 4 * rq + ii, c, t);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = ct + PK_CONV_THREADS * j;
+            const int c = idx / R, r = idx - c * R;
+            if (c >= 4) break;
+            float4 v = slots[j * PK_CONV_THREADS];
+            if (o.mask) v = pk_mask4(v, slots[(4 + j) * PK_CONV_THREADS], o.mask_act);
+            split_to_tile(tile, sub, r, c, v);
+        }
+    }
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -335,13 +461,17 @@ template <int EPI>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
-    const int BN = p.BN, MT = p.MT, S = p.stages;
+    const int BN = p.BN, MT = p.MT, SA = p.SA, SB = p.SB;
     const uint32_t a_tile = PK_AR * 128u;                 // hi+lo of a 128 x 16 tile
-    const uint32_t b_tile = (uint32_t)BN * 128u;
-    const uint32_t stage_bytes = (uint32_t)MT * a_tile + b_tile;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * stage_bytes);
-    uint64_t* empty_bar = full_bar + S;
-    uint64_t* accum_bar = empty_bar + S;
+    const uint32_t a_stage = (uint32_t)MT * a_tile;
+    const uint32_t b_stage = (uint32_t)BN * 128u;
+    unsigned char* ringA = smem_raw;
+    unsigned char* ringB = smem_raw + p.off_b;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw + p.off_bar);
+    uint64_t* a_empty = a_full + SA;
+    uint64_t* b_full = a_empty + SA;
+    uint64_t* b_empty = b_full + SB;
+    uint64_t* accum_bar = b_empty + SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -350,11 +480,18 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const int64_t kb_end = (kb_beg + p.kb_per_split < p.nkb) ? kb_beg + p.kb_per_split : p.nkb;
     const int nkb = (int)(kb_end - kb_beg);
     const bool split = gridDim.z > 1;
+    const bool a_stream = p.sa.mode != OP_PACKED, b_stream = p.sb.mode != OP_PACKED;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+        // a stage is full after the 8 converter warps arrived (streamed operand) or after the TMA
+        // transaction armed by the producer completed (packed operand)
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(&a_full[s], a_stream ? 8 : 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(&b_full[s], b_stream ? 8 : 1);
+            mbar_init(&b_empty[s], 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -366,20 +503,26 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (wid == 0) {
-        // ------------------------------ TMA producer (one lane) ----------------------------
-        if (lane == 0) {
+        // ------------------------------ TMA producer (one lane): packed operands ------------
+        if (lane == 0 && (!a_stream || !b_stream)) {
             const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.Ap);
             const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % S;
-                mbar_wait(&empty_bar[s], ((uint32_t)(i / S) & 1u) ^ 1u);
-                unsigned char* st = smem_raw + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
                 const int64_t kb = kb_beg + i;
-                for (int mt = 0; mt < MT; ++mt)
-                    bulk_g2s(st + (size_t)mt * a_tile, a_src + ((mblk * MT + mt) * p.nkb + kb) * (int64_t)a_tile, a_tile,
-                             &full_bar[s]);
-                bulk_g2s(st + (size_t)MT * a_tile, b_src + (nblk * p.nkb + kb) * (int64_t)b_tile, b_tile, &full_bar[s]);
+                if (!a_stream) {
+                    const int s = i % SA;
+                    mbar_wait(&a_empty[s], ((uint32_t)(i / SA) & 1u) ^ 1u);
+                    mbar_expect_tx(&a_full[s], a_stage);
+                    for (int mt = 0; mt < MT; ++mt)
+                        bulk_g2s(ringA + (size_t)s * a_stage + (size_t)mt * a_tile,
+                                 a_src + ((mblk * MT + mt) * p.nkb + kb) * (int64_t)a_tile, a_tile, &a_full[s]);
+                }
+                if (!b_stream) {
+                    const int s = i % SB;
+                    mbar_wait(&b_empty[s], ((uint32_t)(i / SB) & 1u) ^ 1u);
+                    mbar_expect_tx(&b_full[s], b_stage);
+                    bulk_g2s(ringB + (size_t)s * b_stage, b_src + (nblk * p.nkb + kb) * (int64_t)b_stage, b_stage, &b_full[s]);
+                }
             }
         }
         __syncwarp();
@@ -388,18 +531,19 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         const uint32_t idesc = tf32_idesc(BN);
         const uint32_t a_lbo = PK_AR * 16u, b_lbo = (uint32_t)BN * 16u;     // between the two chunks of a K atom
         for (int i = 0; i < nkb; ++i) {
-            const int s = i % S;
-            mbar_wait(&full_bar[s], (uint32_t)(i / S) & 1u);
+            const int sa = i % SA, sb = i % SB;
+            mbar_wait(&a_full[sa], (uint32_t)(i / SA) & 1u);
+            mbar_wait(&b_full[sb], (uint32_t)(i / SB) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t base = smem_u32(smem_raw + (size_t)s * stage_bytes);
-                const uint32_t b_hi = base + (uint32_t)MT * a_tile, b_lo = b_hi + b_tile / 2;
+                const uint32_t a_base = smem_u32(ringA + (size_t)sa * a_stage);
+                const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
 #pragma unroll
                 for (int j = 0; j < PK_KB / 8; ++j) {
                     const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
                     const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
                     for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t a_hi = base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo;
+                        const uint32_t a_hi = a_base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo;
                         const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
                         const uint64_t dal = make_smem_desc(a_hi + a_tile / 2, a_lbo, 128);
                         const uint32_t d = tmem_base + (uint32_t)(mt * BN);
@@ -408,12 +552,56 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                         umma_tf32(d, dah, dbh, idesc, 1u);
                     }
                 }
-                umma_commit(&empty_bar[s]);               // frees the stage when these MMAs retire
+                umma_commit(&a_empty[sa]);                // frees the stages when these MMAs retire
+                umma_commit(&b_empty[sb]);
                 if (i == nkb - 1) umma_commit(accum_bar);
             }
             __syncwarp();
         }
     } else {
+        // ------------------------------ converters (8 warps), then epilogue -----------------
+        if (a_stream || b_stream) {
+            const int ct = tid - 64;
+            const int nslots = p.slots_a + p.slots_b;
+            float4* raw = reinterpret_cast<float4*>(smem_raw + p.off_raw);
+            // slot q of depth d of thread ct lives at raw[(d*nslots + q)*256 + ct]
+            const int64_t a_row0 = mblk * (int64_t)MT * PK_AR, b_row0 = nblk * (int64_t)BN;
+            auto issue = [&](int i) {
+                if (i < nkb) {
+                    const int d = i % p.depth;
+                    const int64_t k0 = (kb_beg + i) * PK_KB;
+                    float4* base = raw + (size_t)d * nslots * PK_CONV_THREADS + ct;
+                    if (a_stream) stream_issue(p.sa, MT * PK_AR, a_row0, k0, g.K, base, ct);
+                    if (b_stream) stream_issue(p.sb, BN, b_row0, k0, g.K, base + (size_t)p.slots_a * PK_CONV_THREADS, ct);
+                }
+                cp_async_commit();
+            };
+            for (int i = 0; i < p.depth; ++i) issue(i);
+            for (int i = 0; i < nkb; ++i) {
+                if (p.depth == 3) cp_async_wait<2>();
+                else cp_async_wait<1>();
+                const int d = i % p.depth;
+                const float4* base = raw + (size_t)d * nslots * PK_CONV_THREADS + ct;
+                if (a_stream) {
+                    const int s = i % SA;
+                    mbar_wait(&a_empty[s], ((uint32_t)(i / SA) & 1u) ^ 1u);
+                    stream_convert(p.sa, MT * PK_AR, PK_AR, reinterpret_cast<float*>(ringA + (size_t)s * a_stage), base, ct);
+                }
+                if (b_stream) {
+                    const int s = i % SB;
+                    mbar_wait(&b_empty[s], ((uint32_t)(i / SB) & 1u) ^ 1u);
+                    stream_convert(p.sb, BN, BN, reinterpret_cast<float*>(ringB + (size_t)s * b_stage), base + (size_t)p.slots_a * PK_CONV_THREADS, ct);
+                }
+                fence_async_smem();                       // generic-proxy stores -> async proxy (tcgen05.mma)
+                __syncwarp();
+                if (lane == 0) {
+                    if (a_stream) mbar_arrive(&a_full[i % SA]);
+                    if (b_stream) mbar_arrive(&b_full[i % SB]);
+                }
+                issue(i + p.depth);
+            }
+            cp_async_wait<0>();
+        }
         // ------------------------------ epilogue (8 warps) ----------------------------------
         // Two warps per TMEM lane quadrant, alternating 32-column chunks.  tcgen05.ld hands every
         // thread ONE row (32 consecutive columns); written like that to C a warp would touch 32
@@ -479,13 +667,31 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
 // configuration shared by the launcher and the scratch-size query
 // ---------------------------------------------------------------------------------------------
 struct PkConfig {
-    int BN, MT, stages, tmem_cols;
+    int BN, MT, SA, SB, depth, tmem_cols;
+    int a_mode, b_mode, slots_a, slots_b;
     int64_t gm, gn, splits, nkb, kb_per_split;
-    int64_t a_bytes, b_bytes;    // packed operand sizes
+    int64_t a_bytes, b_bytes;    // scratch for the packed operands (0 when streamed)
+    uint32_t off_b, off_raw, off_bar, smem;
+    bool ok;
 };
 
-PkConfig pk_config(int64_t M, int64_t N, int64_t K, bool allow_split) {
-    PkConfig c;
+bool pk_al16(const void* p);
+
+// how the converters fetch a streamed operand (see stream_issue)
+int stream_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int64_t m_row, int64_t m_k) {
+    if (s_k == 1 && s_row % 4 == 0 && pk_al16(P) && (!mask || (m_k == 1 && m_row % 4 == 0 && pk_al16(mask)))) return OP_KVEC;
+    if (s_row == 1 && s_k % 4 == 0 && pk_al16(P) && (!mask || (m_row == 1 && m_k % 4 == 0 && pk_al16(mask)))) return OP_TRANS;
+    return OP_SCALAR;
+}
+
+// Operands whose packed image would be larger than this are converted inside the GEMM instead of
+// being packed into the scratch first (activations); small ones (weights) are packed once per call
+// and fetched by TMA.  CTR_PK_STREAM=0 forces the packed path for everything (A/B profiling).
+constexpr int64_t kStreamThresholdBytes = 4 << 20;
+
+PkConfig pk_config(const GemmArgs& g, bool allow_split) {
+    PkConfig c{};
+    const int64_t M = g.M, N = g.N, K = g.K;
     const int64_t ntiles = ceil_div64(N, 256);
     c.BN = (int)(ceil_div64(ceil_div64(N, ntiles), 16) * 16);
     if (c.BN < 16) c.BN = 16;
@@ -508,13 +714,56 @@ PkConfig pk_config(int64_t M, int64_t N, int64_t K, bool allow_split) {
     }
     c.kb_per_split = ceil_div64(c.nkb, c.splits);
     c.splits = ceil_div64(c.nkb, c.kb_per_split);
-    const int64_t stage_bytes = (int64_t)c.MT * PK_AR * 128 + (int64_t)c.BN * 128;
-    c.stages = (int)((200 * 1024) / stage_bytes);
-    if (c.stages > 6) c.stages = 6;
     c.tmem_cols = 32;
     while (c.tmem_cols < c.MT * c.BN) c.tmem_cols <<= 1;
+
+    const char* e = getenv("CTR_PK_STREAM");
+    const bool stream_ok = !(e && e[0] == '0');
     c.a_bytes = c.gm * c.MT * c.nkb * (int64_t)PK_AR * 128;
     c.b_bytes = c.gn * c.nkb * (int64_t)c.BN * 128;
+    c.a_mode = (stream_ok && c.a_bytes > kStreamThresholdBytes) ? stream_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk) : OP_PACKED;
+    c.b_mode = (stream_ok && c.b_bytes > kStreamThresholdBytes) ? stream_mode(g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk) : OP_PACKED;
+    if (c.a_mode != OP_PACKED) c.a_bytes = 0;
+    if (c.b_mode != OP_PACKED) c.b_bytes = 0;
+    c.slots_a = c.a_mode == OP_PACKED ? 0 : (g.amask ? 8 : 4);
+    c.slots_b = c.b_mode == OP_PACKED ? 0 : (g.bmask ? 8 : 4);
+
+    // shared-memory plan: [A ring | B ring | raw cp.async slots | barriers]
+    const int64_t a_stage = (int64_t)c.MT * PK_AR * 128, b_stage = (int64_t)c.BN * 128;
+    const int64_t raw_per_depth = (int64_t)(c.slots_a + c.slots_b) * PK_CONV_THREADS * 16;
+    const int64_t budget = 220 * 1024 - 512;
+    const int64_t stg = 8 * 32 * PK_STG_PITCH * 4;       // epilogue staging overlays the rings
+    c.ok = false;
+    if (raw_per_depth == 0) {
+        int S = (int)(budget / (a_stage + b_stage));
+        if (S > 6) S = 6;
+        while (S >= 2 && (int64_t)S * (a_stage + b_stage) < stg && S < 6) ++S;
+        if (S >= 2) {
+            c.SA = c.SB = S;
+            c.depth = 0;
+            c.ok = true;
+        }
+    } else {
+        const int opts[5][3] = {{3, 4, 3}, {3, 3, 3}, {2, 3, 3}, {2, 2, 3}, {2, 2, 2}};
+        for (int i = 0; i < 5 && !c.ok; ++i) {
+            const int64_t need = opts[i][0] * a_stage + opts[i][1] * b_stage + opts[i][2] * raw_per_depth;
+            if (need <= budget) {
+                c.SA = opts[i][0];
+                c.SB = opts[i][1];
+                c.depth = opts[i][2];
+                c.ok = true;
+            }
+        }
+    }
+    if (c.ok) {
+        int64_t rings = c.SA * a_stage + c.SB * b_stage;
+        c.off_b = (uint32_t)(c.SA * a_stage);
+        if (rings < stg) rings = stg;
+        c.off_raw = (uint32_t)rings;
+        c.off_bar = (uint32_t)(rings + c.depth * raw_per_depth);
+        c.smem = c.off_bar + (uint32_t)((2 * c.SA + 2 * c.SB + 1) * sizeof(uint64_t) + 16);
+        if (c.smem > 225 * 1024) c.ok = false;
+    }
     return c;
 }
 
@@ -534,9 +783,21 @@ int current_device() {
 
 int64_t gemm_pk_scratch_bytes(int64_t M, int64_t N, int64_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    const PkConfig a = pk_config(M, N, K, false), b = pk_config(M, N, K, true);
-    const int64_t x = a.a_bytes + a.b_bytes, y = b.a_bytes + b.b_bytes;
-    return (x > y ? x : y) + 256;
+    // layout-independent upper bound: an operand is either streamed (no scratch) or at most
+    // kStreamThresholdBytes when packed; with CTR_PK_STREAM=0 both operands are packed in full
+    GemmArgs g = gemm_args_default();
+    g.M = M; g.N = N; g.K = K;
+    int64_t worst = 0;
+    for (int sp = 0; sp < 2; ++sp) {
+        const PkConfig c = pk_config(g, sp != 0);
+        const int64_t full_a = c.gm * c.MT * c.nkb * (int64_t)PK_AR * 128, full_b = c.gn * c.nkb * (int64_t)c.BN * 128;
+        const char* e = getenv("CTR_PK_STREAM");
+        const bool stream_ok = !(e && e[0] == '0');
+        const int64_t a = (stream_ok && full_a > kStreamThresholdBytes) ? 0 : full_a;
+        const int64_t b = (stream_ok && full_b > kStreamThresholdBytes) ? 0 : full_b;
+        if (a + b > worst) worst = a + b;
+    }
+    return worst + 256;
 }
 
 bool gemm_pk_has_scratch(int64_t M, int64_t N, int64_t K) {
@@ -557,15 +818,15 @@ extern "C" int ctr_set_scratch(void* ptr, int64_t bytes) {
 
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
-    const PkConfig c = pk_config(g.M, g.N, g.K, allow_split);
-    if (c.stages < 2) {
+    const PkConfig c = pk_config(g, allow_split);
+    if (!c.ok) {
         ctr_set_error("launch_gemm_pk: tile does not fit shared memory");
         return -1;
     }
     const int64_t need = c.a_bytes + c.b_bytes;
     const int dev = current_device();
     void* scratch = g_scratch[dev];
-    if (!scratch || g_scratch_bytes[dev] < need) {
+    if (need > 0 && (!scratch || g_scratch_bytes[dev] < need)) {
         ctr_set_error("launch_gemm_pk: scratch of %lld bytes required for M=%lld N=%lld K=%lld, %lld registered "
                       "(ctr_set_scratch / ctr_gemm_scratch_bytes)",
                       (long long)need, (long long)g.M, (long long)g.N, (long long)g.K, (long long)g_scratch_bytes[dev]);
@@ -578,27 +839,39 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     float* Ap = reinterpret_cast<float*>(scratch);
     float* Bp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + c.a_bytes);
     int rc;
-    PackArgs pa{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, g.M, g.K, PK_AR, c.gm * c.MT, c.nkb, Ap};
-    if ((rc = launch_pack(pa, st)) != 0) return rc;
-    PackArgs pb{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, g.N, g.K, c.BN, c.gn, c.nkb, Bp};
-    if ((rc = launch_pack(pb, st)) != 0) return rc;
+    if (c.a_mode == OP_PACKED) {
+        PackArgs pa{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, g.M, g.K, PK_AR, c.gm * c.MT, c.nkb, Ap};
+        if ((rc = launch_pack(pa, st)) != 0) return rc;
+    }
+    if (c.b_mode == OP_PACKED) {
+        PackArgs pb{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, g.N, g.K, c.BN, c.gn, c.nkb, Bp};
+        if ((rc = launch_pack(pb, st)) != 0) return rc;
+    }
     if (c.splits > 1 && !g.accumulate)
         CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
-    PkParams p;
+    PkParams p{};
     p.g = g;
     p.Ap = Ap;
     p.Bp = Bp;
+    p.sa = StreamOp{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, g.M, c.a_mode};
+    p.sb = StreamOp{g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk, g.bmask_act, g.N, c.b_mode};
     p.nkb = c.nkb;
     p.kb_per_split = c.kb_per_split;
     p.BN = c.BN;
     p.MT = c.MT;
-    p.stages = c.stages;
+    p.SA = c.SA;
+    p.SB = c.SB;
+    p.depth = c.depth;
     p.tmem_cols = c.tmem_cols;
-    const size_t stage_bytes = (size_t)c.MT * PK_AR * 128 + (size_t)c.BN * 128;
-    const size_t smem = (size_t)c.stages * stage_bytes + (2 * c.stages + 1) * sizeof(uint64_t) + 16;
+    p.off_b = c.off_b;
+    p.off_raw = c.off_raw;
+    p.off_bar = c.off_bar;
+    p.slots_a = c.slots_a;
+    p.slots_b = c.slots_b;
+    const size_t smem = c.smem;
     static bool configured = false;
     if (!configured) {
-        const int max_smem = 220 * 1024;
+        const int max_smem = 225 * 1024;
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

@@ -27,7 +27,7 @@ if what == "check":
     os.environ["CTR_GEMM"] = "pk"
     worst = 0.0
     for (M, N, K) in [(128, 32, 32), (128, 256, 64), (1000, 256, 432), (300, 448, 96), (77, 36, 20), (513, 96, 1664),
-                      (256, 429, 3000)]:
+                      (256, 429, 3000), (8192, 256, 432), (4096, 448, 100), (300, 200, 20000)]:
         K4, M4 = (K + 3) // 4 * 4, (M + 3) // 4 * 4
         A = torch.randn(M, K4, device="cuda", generator=g)
         Bm = torch.randn(N, K4, device="cuda", generator=g)

@@ -23,19 +23,28 @@ def _sgemm(A, sam, sak, Bm, sbn, sbk, M, N, K, accumulate=False, C=None):
     return C
 
 
-@pytest.fixture(params=["pk", "tc1", "simt"])
+@pytest.fixture(params=["pk", "pk-packed", "tc1", "simt"])
 def engine(request):
-    old = os.environ.get("CTR_GEMM")
-    os.environ["CTR_GEMM"] = request.param
-    yield request.param
-    if old is None:
-        os.environ.pop("CTR_GEMM", None)
+    """pk: large operands are converted inside the GEMM (cp.async -> split), small ones packed;
+    pk-packed: every operand goes through the pack kernels + TMA (CTR_PK_STREAM=0)."""
+    old = {k: os.environ.get(k) for k in ("CTR_GEMM", "CTR_PK_STREAM")}
+    os.environ["CTR_GEMM"] = request.param.split("-")[0]
+    if request.param == "pk-packed":
+        os.environ["CTR_PK_STREAM"] = "0"
     else:
-        os.environ["CTR_GEMM"] = old
+        os.environ.pop("CTR_PK_STREAM", None)
+    ops._scratch_need.clear()
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    ops._scratch_need.clear()
 
 
 SHAPES = [(128, 256, 32), (1000, 256, 429), (4096, 128, 256), (77, 33, 19), (256, 429, 3000), (130, 520, 64),
-          (5, 7, 3), (513, 96, 1664)]
+          (5, 7, 3), (513, 96, 1664), (40000, 256, 432)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
