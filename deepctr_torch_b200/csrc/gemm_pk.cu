@@ -268,95 +268,124 @@ __device__ __forceinline__ int tile_float_off(int sub, int r, int c) {
     const int st = r / sub, rr = r - st * sub;
     return st * (sub * 32) + (c * sub + rr) * 4;
 }
-__device__ __forceinline__ void split_to_tile(float* tile, int sub, int r, int c, float4 v) {
-    float4 hi, lo;
-    split_tf32(v.x, hi.x, lo.x);
-    split_tf32(v.y, hi.y, lo.y);
-    split_tf32(v.z, hi.z, lo.z);
-    split_tf32(v.w, hi.w, lo.w);
-    float* ph = tile + tile_float_off(sub, r, c);
-    *reinterpret_cast<float4*>(ph) = hi;
-    *reinterpret_cast<float4*>(ph + sub * 16) = lo;
-}
+// ---- converter state: every converter thread owns up to 4 pieces (16 bytes each) per operand and
+// stage.  Everything that does not change from one 16-k stage to the next — source pointers, the
+// destination offsets inside the MMA tile, the row validity — is computed ONCE here; per stage the
+// thread only bumps its pointers (the first version recomputed idx / R, 64-bit addresses and bounds
+// for every piece of every stage and was instruction-bound: 32 % issue utilisation, tensor pipe 28 %).
+struct PieceSet {
+    const float* src[4];     // piece source at the CTA's first k block
+    const float* msk[4];
+    int toff[4];             // float offset of the destination chunk inside the MMA tile, < 0: no store
+    int koff[4];             // k offset of the piece inside a stage
+    int maxb[4];             // bytes the row geometry allows (0: outside the matrix -> zero fill)
+    int64_t step, mstep;     // element step of src / msk per stage
+};
 
-// ---- converter, phase 1: issue the cp.async's of one 16-k stage of one operand.  `slots` are this
-// thread's raw slots of the stage (slot q at slots[q * 256]: [0,4) data, [4,8) mask, so that
-// consecutive lanes touch consecutive 16-byte words); every slot is written by exactly one
-// thread and later read by the same thread, so no barrier is needed between the two phases.
-// Out-of-range rows / k are zero-filled by the copy itself (src-size < cp-size).
-__device__ __forceinline__ void stream_issue(const StreamOp& o, int R, int64_t row0, int64_t k0, int64_t K,
-                                             float4* slots, int ct) {
+__device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, int64_t row0, int64_t k_first, int ct,
+                                            PieceSet& ps) {
     if (o.mode == OP_TRANS) {
-        // one group per thread: 4 consecutive rows x 4 consecutive k (4 x 16 bytes along the rows)
+        // one group per thread: 4 consecutive rows (16 bytes along the rows) x 4 consecutive k
         const int RQ = R >> 2;
         const int rq = ct % RQ, c = ct / RQ;
         const int64_t row = row0 + 4 * rq;
         const bool live = ct < R;
+        int rb = 0;
+        if (live && row < o.n_rows) rb = (o.n_rows - row >= 4) ? 16 : (int)(o.n_rows - row) * 4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int64_t k = k0 + 4 * c + e;
-            int bytes = 0;
-            if (live && k < K && row < o.n_rows) bytes = (o.n_rows - row >= 4) ? 16 : (int)(o.n_rows - row) * 4;
-            cp_async16(&slots[(e) * PK_CONV_THREADS], bytes ? o.P + row + k * o.s_k : o.P, bytes);
-            if (o.mask) cp_async16(&slots[(4 + e) * PK_CONV_THREADS], bytes ? o.mask + row + k * o.m_k : o.mask, bytes);
+            ps.koff[e] = 4 * c + e;
+            ps.maxb[e] = rb;
+            ps.src[e] = o.P + (rb ? row + (k_first + 4 * c + e) * o.s_k : 0);
+            ps.msk[e] = o.mask ? o.mask + (rb ? row + (k_first + 4 * c + e) * o.m_k : 0) : nullptr;
+            // destination of output row 4rq+e (the transpose happens in registers)
+            ps.toff[e] = live ? tile_float_off(sub, 4 * rq + e, c) : -1;
         }
+        ps.step = PK_KB * o.s_k;
+        ps.mstep = PK_KB * o.m_k;
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int idx = ct + PK_CONV_THREADS * j;
             const int c = idx / R, r = idx - c * R;
-            const int64_t row = row0 + r, k = k0 + 4 * c;
-            const bool live = c < 4 && row < o.n_rows;
-            if (o.mode == OP_KVEC) {
-                int bytes = 0;
-                if (live && k < K) bytes = (K - k >= 4) ? 16 : (int)(K - k) * 4;
-                cp_async16(&slots[(j) * PK_CONV_THREADS], bytes ? o.P + row * o.s_row + k : o.P, bytes);
-                if (o.mask) cp_async16(&slots[(4 + j) * PK_CONV_THREADS], bytes ? o.mask + row * o.m_row + k : o.mask, bytes);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool ok = live && k + e < K;
-                    cp_async4(reinterpret_cast<float*>(&slots[(j) * PK_CONV_THREADS]) + e, ok ? o.P + row * o.s_row + (k + e) * o.s_k : o.P, ok ? 4 : 0);
-                    if (o.mask)
-                        cp_async4(reinterpret_cast<float*>(&slots[(4 + j) * PK_CONV_THREADS]) + e,
-                                  ok ? o.mask + row * o.m_row + (k + e) * o.m_k : o.mask, ok ? 4 : 0);
-                }
-            }
+            const int64_t row = row0 + r;
+            const bool in_tile = c < 4, ok = in_tile && row < o.n_rows;
+            ps.koff[j] = 4 * c;
+            ps.maxb[j] = ok ? 16 : 0;
+            ps.src[j] = o.P + (ok ? row * o.s_row + (k_first + 4 * c) * o.s_k : 0);
+            ps.msk[j] = o.mask ? o.mask + (ok ? row * o.m_row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
+            ps.toff[j] = in_tile ? tile_float_off(sub, r, c) : -1;
         }
+        ps.step = PK_KB * o.s_k;
+        ps.mstep = PK_KB * o.m_k;
     }
 }
 
-// ---- converter, phase 2: own raw slots -> (mask) -> hi/lo split -> MMA tile
-__device__ __forceinline__ void stream_convert(const StreamOp& o, int R, int sub, float* tile, const float4* slots, int ct) {
+// phase 1: cp.async of one stage (krem = K - k0 of the stage).  Slot q of this thread is slots[q * 256]
+// ([0,4) data, [4,8) mask); dead pieces / k tails are zero-filled by the copy itself (src-size < 16).
+__device__ __forceinline__ void stream_issue(const StreamOp& o, PieceSet& ps, int64_t krem, float4* slots) {
+    const int kr = krem > 64 ? 64 : (int)krem;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (o.mode == OP_SCALAR) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool ok = ps.maxb[q] && ps.koff[q] + e < kr;
+                cp_async4(reinterpret_cast<float*>(&slots[q * PK_CONV_THREADS]) + e, ok ? ps.src[q] + e * o.s_k : o.P, ok ? 4 : 0);
+                if (o.mask)
+                    cp_async4(reinterpret_cast<float*>(&slots[(4 + q) * PK_CONV_THREADS]) + e, ok ? ps.msk[q] + e * o.m_k : o.mask,
+                              ok ? 4 : 0);
+            }
+        } else {
+            int bytes;
+            if (o.mode == OP_KVEC) {
+                bytes = (kr - ps.koff[q]) * 4;
+                bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                if (!ps.maxb[q]) bytes = 0;
+            } else {
+                bytes = ps.koff[q] < kr ? ps.maxb[q] : 0;
+            }
+            cp_async16(&slots[q * PK_CONV_THREADS], bytes ? ps.src[q] : o.P, bytes);
+            if (o.mask) cp_async16(&slots[(4 + q) * PK_CONV_THREADS], bytes ? ps.msk[q] : o.mask, bytes);
+        }
+        ps.src[q] += ps.step;
+        if (o.mask) ps.msk[q] += ps.mstep;
+    }
+}
+
+__device__ __forceinline__ void split_store(float* tile, int off, int lo_off, float4 v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(tile + off) = hi;
+    *reinterpret_cast<float4*>(tile + off + lo_off) = lo;
+}
+
+// phase 2: own raw slots -> (mask) -> hi/lo split -> MMA tile (sub = rows of a sub-tile: lo part at +sub*16 floats)
+__device__ __forceinline__ void stream_convert(const StreamOp& o, const PieceSet& ps, int sub, float* tile, const float4* slots) {
+    const int lo_off = sub * 16;
     if (o.mode == OP_TRANS) {
-        if (ct >= R) return;
-        const int RQ = R >> 2;
-        const int rq = ct % RQ, c = ct / RQ;
+        if (ps.toff[0] < 0) return;
         float4 x[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             x[e] = slots[e * PK_CONV_THREADS];
             if (o.mask) x[e] = pk_mask4(x[e], slots[(4 + e) * PK_CONV_THREADS], o.mask_act);
         }
-        // 4x4 register transpose: row 4rq+i gets (k, k+1, k+2, k+3); the starting row is rotated by the
-        // lane so that neighbouring lanes (64 bytes apart) do not hit the same banks
-        const float4 t0 = make_float4(x[0].x, x[1].x, x[2].x, x[3].x), t1 = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
-        const float4 t2 = make_float4(x[0].z, x[1].z, x[2].z, x[3].z), t3 = make_float4(x[0].w, x[1].w, x[2].w, x[3].w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ii = (i + rq) & 3;
-            const float4 t = ii == 0 ? t0 : (ii == 1 ? t1 : (ii == 2 ? t2 : t3));
-            split_to_tile(tile, sub, 4 * rq + ii, c, t);
-        }
+        // 4x4 register transpose: output row i gets (k, k+1, k+2, k+3)
+        split_store(tile, ps.toff[0], lo_off, make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
+        split_store(tile, ps.toff[1], lo_off, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
+        split_store(tile, ps.toff[2], lo_off, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
+        split_store(tile, ps.toff[3], lo_off, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = ct + PK_CONV_THREADS * j;
-            const int c = idx / R, r = idx - c * R;
-            if (c >= 4) break;
-            float4 v = slots[j * PK_CONV_THREADS];
-            if (o.mask) v = pk_mask4(v, slots[(4 + j) * PK_CONV_THREADS], o.mask_act);
-            split_to_tile(tile, sub, r, c, v);
+        for (int q = 0; q < 4; ++q) {
+            if (ps.toff[q] < 0) continue;
+            float4 v = slots[q * PK_CONV_THREADS];
+            if (o.mask) v = pk_mask4(v, slots[(4 + q) * PK_CONV_THREADS], o.mask_act);
+            split_store(tile, ps.toff[q], lo_off, v);
         }
     }
 }
@@ -566,13 +595,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             float4* raw = reinterpret_cast<float4*>(smem_raw + p.off_raw);
             // slot q of depth d of thread ct lives at raw[(d*nslots + q)*256 + ct]
             const int64_t a_row0 = mblk * (int64_t)MT * PK_AR, b_row0 = nblk * (int64_t)BN;
+            PieceSet pa, pb;
+            if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, kb_beg * PK_KB, ct, pa);
+            if (b_stream) piece_setup(p.sb, BN, BN, b_row0, kb_beg * PK_KB, ct, pb);
             auto issue = [&](int i) {
                 if (i < nkb) {
                     const int d = i % p.depth;
-                    const int64_t k0 = (kb_beg + i) * PK_KB;
+                    const int64_t krem = g.K - (kb_beg + i) * PK_KB;
                     float4* base = raw + (size_t)d * nslots * PK_CONV_THREADS + ct;
-                    if (a_stream) stream_issue(p.sa, MT * PK_AR, a_row0, k0, g.K, base, ct);
-                    if (b_stream) stream_issue(p.sb, BN, b_row0, k0, g.K, base + (size_t)p.slots_a * PK_CONV_THREADS, ct);
+                    if (a_stream) stream_issue(p.sa, pa, krem, base);
+                    if (b_stream) stream_issue(p.sb, pb, krem, base + (size_t)p.slots_a * PK_CONV_THREADS);
                 }
                 cp_async_commit();
             };
@@ -585,12 +617,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                 if (a_stream) {
                     const int s = i % SA;
                     mbar_wait(&a_empty[s], ((uint32_t)(i / SA) & 1u) ^ 1u);
-                    stream_convert(p.sa, MT * PK_AR, PK_AR, reinterpret_cast<float*>(ringA + (size_t)s * a_stage), base, ct);
+                    stream_convert(p.sa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)s * a_stage), base);
                 }
                 if (b_stream) {
                     const int s = i % SB;
                     mbar_wait(&b_empty[s], ((uint32_t)(i / SB) & 1u) ^ 1u);
-                    stream_convert(p.sb, BN, BN, reinterpret_cast<float*>(ringB + (size_t)s * b_stage), base + (size_t)p.slots_a * PK_CONV_THREADS, ct);
+                    stream_convert(p.sb, pb, BN, reinterpret_cast<float*>(ringB + (size_t)s * b_stage),
+                                   base + (size_t)p.slots_a * PK_CONV_THREADS);
                 }
                 fence_async_smem();                       // generic-proxy stores -> async proxy (tcgen05.mma)
                 __syncwarp();

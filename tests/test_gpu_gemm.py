@@ -56,21 +56,21 @@ def test_nt_nn_tn_layouts(engine, M, N, K):
     Bm = torch.randn(N, K, device=DEV, generator=g)
     C = _sgemm(Abuf, lda, 1, Bm, K, 1, M, N, K)
     ref = Abuf[:, :K].double() @ Bm.double().t()
-    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    assert rel_err(C.cpu(), ref.cpu()) <= 4e-6
     # NN (dgrad): B stored [K, N] row-major
     Bkn = torch.randn(K, N, device=DEV, generator=g)
     C = _sgemm(Abuf, lda, 1, Bkn, 1, N, M, N, K)
     ref = Abuf[:, :K].double() @ Bkn.double()
-    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    assert rel_err(C.cpu(), ref.cpu()) <= 4e-6
     # TN (wgrad): A stored [K, M], B stored [K, N]; split-K path when K is large
     Akm = torch.randn(K, M, device=DEV, generator=g)
     C = _sgemm(Akm, 1, M, Bkn, 1, N, M, N, K)
     ref = Akm.double().t() @ Bkn.double()
-    assert rel_err(C.cpu(), ref.cpu()) <= 2e-6
+    assert rel_err(C.cpu(), ref.cpu()) <= 4e-6
     # accumulate into C
     C0 = torch.randn(M, N, device=DEV, generator=g)
     C = _sgemm(Akm, 1, M, Bkn, 1, N, M, N, K, accumulate=True, C=C0.clone())
-    assert rel_err(C.cpu(), (ref + C0.double()).cpu()) <= 2e-6
+    assert rel_err(C.cpu(), (ref + C0.double()).cpu()) <= 4e-6
 
 
 def test_wgrad_shape_split_k(engine):
