@@ -37,6 +37,8 @@ SIGNATURES = {
     "ctr_dnn_layer_fwd": [_P, c_i64, _P, c_i64, c_i64, _P, _P, c_i64, c_i64, c_int, c_int, c_int, _P],
     "ctr_dnn_layer_bwd": [_P, c_i64, _P, c_i64, c_i64, _P, c_i64, _P, c_i64, _P, c_i64, c_int,
                           _P, c_i64, c_i64, _P, c_i64, c_int, c_int, c_int, _P],
+    "ctr_dnn_layer_bwd_chain": [_P, c_i64, _P, c_i64, c_i64, _P, c_i64, _P, c_i64, _P, c_i64,
+                                _P, c_i64, c_i64, _P, c_i64, c_int, c_int, c_int, c_int, c_int, _P],
     "ctr_sgemm": [c_i64, c_i64, c_i64, _P, c_i64, c_i64, _P, c_i64, c_i64, _P, c_i64, c_int, _P],
     "ctr_rowdot_fwd": [_P, c_i64, _P, c_i64, c_int, _P, c_int, _P],
     "ctr_rowdot_bwd": [_P, c_i64, _P, _P, c_i64, c_int, _P, c_i64, c_int, _P, _P],

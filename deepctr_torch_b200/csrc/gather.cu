@@ -496,7 +496,10 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 
 // Thread mapping is column-major (i = c*B + b): the lanes of a warp work on the same id column, so
 // the "next unique index" counter of that column is bumped once per warp (ballot-aggregated)
-// instead of once per inserted key.
+// instead of once per inserted key.  The kernel is a chain of dependent L2 round trips per key
+// (id -> CAS -> next probe ...), so each thread keeps PLAN_ILP independent keys in flight and the
+// first probe is the CAS itself (no read-before-CAS): measured 140 us -> see profiles/.
+constexpr int PLAN_ILP = 4;
 __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restrict__ X, int64_t ldx,
                                                           int64_t B, int n_cols,
                                                           const int32_t* __restrict__ cols,
@@ -507,48 +510,63 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
     const int64_t total = B * n_cols;
     const uint32_t mask = (uint32_t)(H - 1);
     const int lane = threadIdx.x & 31;
-    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
-    for (int64_t base = first; base < total; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = base + lane;
-        const bool valid = i < total;
-        int c = 0;
-        int64_t b = 0;
-        bool won = false;
-        uint32_t slot = 0;
-        int32_t key = 0;
-        if (valid) {
-            c = (int)(i / B);
-            b = i - (int64_t)c * B;
-            key = (int32_t)decode_id(__ldg(X + b * ldx + cols[c]), vocab[c], err_flag);
-            int32_t* kc = keys + (int64_t)c * H;
-            slot = mix32((uint32_t)key) & mask;
-            while (true) {
-                int32_t k = __ldcg(kc + slot);
-                if (k == -1) {
-                    const int32_t old = atomicCAS(kc + slot, -1, key);
-                    if (old == -1) {
-                        won = true;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * (32 * PLAN_ILP); base < total; base += nwarps * (32 * PLAN_ILP)) {
+        int c[PLAN_ILP];
+        int64_t b[PLAN_ILP];
+        bool valid[PLAN_ILP], won[PLAN_ILP];
+        uint32_t slot[PLAN_ILP];
+        int32_t key[PLAN_ILP], old[PLAN_ILP];
+        float xv[PLAN_ILP];
+#pragma unroll
+        for (int t = 0; t < PLAN_ILP; ++t) {                 // all id loads in flight
+            const int64_t i = base + t * 32 + lane;
+            valid[t] = i < total;
+            const int64_t ic = valid[t] ? i : 0;
+            c[t] = (int)(ic / B);
+            b[t] = ic - (int64_t)c[t] * B;
+            xv[t] = __ldg(X + b[t] * ldx + cols[c[t]]);
+        }
+#pragma unroll
+        for (int t = 0; t < PLAN_ILP; ++t) {                 // all first probes (CAS) in flight
+            key[t] = (int32_t)decode_id(xv[t], vocab[c[t]], valid[t] ? err_flag : nullptr);
+            slot[t] = mix32((uint32_t)key[t]) & mask;
+            old[t] = valid[t] ? atomicCAS(keys + (int64_t)c[t] * H + slot[t], -1, key[t]) : key[t];
+        }
+#pragma unroll
+        for (int t = 0; t < PLAN_ILP; ++t) {
+            won[t] = false;
+            if (valid[t]) {
+                int32_t* kc = keys + (int64_t)c[t] * H;
+                int32_t o = old[t];
+                while (true) {
+                    if (o == -1) {
+                        won[t] = true;
                         break;
                     }
-                    k = old;
+                    if (o == key[t]) break;
+                    slot[t] = (slot[t] + 1) & mask;            // linear probing (rare at load factor <= 0.5)
+                    o = atomicCAS(kc + slot[t], -1, key[t]);
                 }
-                if (k == key) break;
-                slot = (slot + 1) & mask;
+                inv[b[t] * n_cols + c[t]] = (int32_t)slot[t];  // replaced by the unique index in plan_finalize_kernel
             }
-            inv[b * n_cols + c] = (int32_t)slot;  // replaced by the unique index in plan_finalize_kernel
         }
         __syncwarp();
-        // lanes that inserted a key of the same column share one atomicAdd
-        const unsigned winners = __ballot_sync(0xffffffffu, won);
-        if (won) {
-            const unsigned peers = __match_any_sync(winners, c) ;
-            const int leader = __ffs(peers) - 1;
-            int32_t base_u = 0;
-            if (lane == leader) base_u = atomicAdd(n_uniq + c, __popc(peers));
-            base_u = __shfl_sync(peers, base_u, leader);
-            const int32_t u = base_u + __popc(peers & ((1u << lane) - 1u));
-            vals[(int64_t)c * H + slot] = u;
-            uniq[(int64_t)c * B + u] = key;
+#pragma unroll
+        for (int t = 0; t < PLAN_ILP; ++t) {
+            // lanes that inserted a key of the same column share one atomicAdd
+            const unsigned winners = __ballot_sync(0xffffffffu, won[t]);
+            if (won[t]) {
+                const unsigned peers = __match_any_sync(winners, c[t]);
+                const int leader = __ffs(peers) - 1;
+                int32_t base_u = 0;
+                if (lane == leader) base_u = atomicAdd(n_uniq + c[t], __popc(peers));
+                base_u = __shfl_sync(peers, base_u, leader);
+                const int32_t u = base_u + __popc(peers & ((1u << lane) - 1u));
+                vals[(int64_t)c[t] * H + slot[t]] = u;
+                uniq[(int64_t)c[t] * B + u] = key[t];
+            }
         }
     }
 }

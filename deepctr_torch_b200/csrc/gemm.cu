@@ -427,25 +427,26 @@ extern "C" int ctr_dnn_layer_fwd(const float* X, int64_t ldx, const float* W, in
     return launch_sgemm(g, as_stream(stream));
 }
 
-extern "C" int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, int64_t swn,
-                                 int64_t swk, const float* Y, int64_t ldy, const float* dY,
-                                 int64_t lddy, float* dX, int64_t lddx, int accumulate_dx, float* dW,
-                                 int64_t sdwn, int64_t sdwk, float* db, int64_t B, int K, int N,
-                                 int act, void* stream) {
-    CTR_ARG(W && dY && B >= 0 && K > 0 && N > 0, "ctr_dnn_layer_bwd: bad arguments");
-    CTR_ARG(act == CTR_ACT_LINEAR || Y, "ctr_dnn_layer_bwd: Y required for a non-linear activation");
-    CTR_ARG(!dW || X, "ctr_dnn_layer_bwd: X required for dW");
-    CTR_ARG(!dW || sdwn == 1 || sdwk == 1, "ctr_dnn_layer_bwd: dW must be contiguous along n or k");
-    cudaStream_t st = as_stream(stream);
-    const float* mask = (act == CTR_ACT_LINEAR) ? nullptr : Y;
+static int dnn_layer_bwd_impl(const float* X, int64_t ldx, const float* W, int64_t swn, int64_t swk,
+                              const float* Y, int64_t ldy, const float* dY, int64_t lddy, float* dX,
+                              int64_t lddx, int accumulate_dx, float* dW, int64_t sdwn, int64_t sdwk,
+                              float* db, int64_t B, int K, int N, int act, int dy_is_dz, int dx_act,
+                              cudaStream_t st) {
+    // dZ = dY (.) act'(Y) is applied on the fly (operand prologue) unless the caller already holds dZ
+    const float* mask = (act == CTR_ACT_LINEAR || dy_is_dz) ? nullptr : Y;
     int rc;
-    if (dX) {  // dX[b,k] (+)= sum_n dZ[b,n] W(n,k)
+    if (dX) {  // dX[b,k] (+)= sum_n dZ[b,n] W(n,k)   [ (.) dx_act'(X[b,k]) : the previous layer's dZ ]
         GemmArgs g = gemm_args_default();
         g.M = B; g.N = K; g.K = N;
         g.A = dY; g.sam = lddy; g.sak = 1;
         g.amask = mask; g.smm = ldy; g.smk = 1; g.amask_act = act;
         g.B = W; g.sbn = swk; g.sbk = swn;
         g.C = dX; g.ldc = lddx; g.accumulate = accumulate_dx;
+        if (dx_act != CTR_ACT_LINEAR) {
+            g.epilogue = EPI_MUL_ACTGRAD;
+            g.act = dx_act;
+            g.aux = X; g.ldaux = ldx;
+        }
         if ((rc = launch_sgemm(g, st)) != 0) return rc;
     }
     if (dW) {  // dW(n,k) = sum_b dZ[b,n] X[b,k]
@@ -471,6 +472,34 @@ extern "C" int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, in
         if ((rc = launch_colsum(dY, lddy, 1, mask, ldy, 1, act, nullptr, B, N, db, st)) != 0) return rc;
     }
     return 0;
+}
+
+extern "C" int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, int64_t swn,
+                                 int64_t swk, const float* Y, int64_t ldy, const float* dY,
+                                 int64_t lddy, float* dX, int64_t lddx, int accumulate_dx, float* dW,
+                                 int64_t sdwn, int64_t sdwk, float* db, int64_t B, int K, int N,
+                                 int act, void* stream) {
+    CTR_ARG(W && dY && B >= 0 && K > 0 && N > 0, "ctr_dnn_layer_bwd: bad arguments");
+    CTR_ARG(act == CTR_ACT_LINEAR || Y, "ctr_dnn_layer_bwd: Y required for a non-linear activation");
+    CTR_ARG(!dW || X, "ctr_dnn_layer_bwd: X required for dW");
+    CTR_ARG(!dW || sdwn == 1 || sdwk == 1, "ctr_dnn_layer_bwd: dW must be contiguous along n or k");
+    return dnn_layer_bwd_impl(X, ldx, W, swn, swk, Y, ldy, dY, lddy, dX, lddx, accumulate_dx, dW, sdwn, sdwk, db, B,
+                              K, N, act, 0, CTR_ACT_LINEAR, as_stream(stream));
+}
+
+extern "C" int ctr_dnn_layer_bwd_chain(const float* X, int64_t ldx, const float* W, int64_t swn,
+                                       int64_t swk, const float* Y, int64_t ldy, const float* dY,
+                                       int64_t lddy, float* dX, int64_t lddx, float* dW, int64_t sdwn,
+                                       int64_t sdwk, float* db, int64_t B, int K, int N, int act,
+                                       int dy_is_dz, int dx_act, void* stream) {
+    CTR_ARG(W && dY && B >= 0 && K > 0 && N > 0, "ctr_dnn_layer_bwd_chain: bad arguments");
+    CTR_ARG(act == CTR_ACT_LINEAR || dy_is_dz || Y, "ctr_dnn_layer_bwd_chain: Y required for a non-linear activation");
+    CTR_ARG(!dW || X, "ctr_dnn_layer_bwd_chain: X required for dW");
+    CTR_ARG(dx_act == CTR_ACT_LINEAR || (X && dX), "ctr_dnn_layer_bwd_chain: X and dX required when dx_act is set");
+    CTR_ARG(dx_act >= CTR_ACT_LINEAR && dx_act <= CTR_ACT_TANH, "ctr_dnn_layer_bwd_chain: unknown dx_act %d", dx_act);
+    CTR_ARG(!dW || sdwn == 1 || sdwk == 1, "ctr_dnn_layer_bwd_chain: dW must be contiguous along n or k");
+    return dnn_layer_bwd_impl(X, ldx, W, swn, swk, Y, ldy, dY, lddy, dX, lddx, 0, dW, sdwn, sdwk, db, B, K, N, act,
+                              dy_is_dz, dx_act, as_stream(stream));
 }
 
 extern "C" int ctr_rowdot_fwd(const float* H, int64_t ldh, const float* w, int64_t B, int N,

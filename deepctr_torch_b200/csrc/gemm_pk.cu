@@ -37,7 +37,8 @@ namespace {
 
 constexpr int PK_KB = 16;            // k per packed tile (4 chunks of 16 bytes)
 constexpr int PK_AR = 128;           // rows of an A tile (one UMMA M)
-constexpr int PK_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int PK_CONV_WARPS = 16;    // converter warps (they also run the epilogue)
+constexpr int PK_THREADS = 64 + PK_CONV_WARPS * 32;   // + TMA producer warp + MMA warp
 constexpr int PK_STG_PITCH = 36;     // floats per row of an epilogue staging tile (32 + 4: conflict-free)
 
 // ---------------------------------------------------------------------------------------------
@@ -247,10 +248,11 @@ struct PkParams {
     int64_t kb_per_split;
     int BN, MT, SA, SB, depth, tmem_cols;
     uint32_t off_b, off_raw, off_bar;     // shared-memory layout (bytes): A ring at 0
-    int slots_a, slots_b;                 // 16-byte raw slots per converter thread and depth
+    uint32_t raw_a_bytes, raw_b_bytes;    // raw cp.async region of each streamed operand, per depth
+    int t0_b;                             // first converter thread of B's OP_TRANS groups
 };
 
-constexpr int PK_CONV_THREADS = 256;
+constexpr int PK_CONV_THREADS = PK_CONV_WARPS * 32;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
@@ -268,88 +270,104 @@ __device__ __forceinline__ int tile_float_off(int sub, int r, int c) {
     const int st = r / sub, rr = r - st * sub;
     return st * (sub * 32) + (c * sub + rr) * 4;
 }
-// ---- converter state: every converter thread owns up to 4 pieces (16 bytes each) per operand and
-// stage.  Everything that does not change from one 16-k stage to the next — source pointers, the
-// destination offsets inside the MMA tile, the row validity — is computed ONCE here; per stage the
-// thread only bumps its pointers (the first version recomputed idx / R, 64-bit addresses and bounds
-// for every piece of every stage and was instruction-bound: 32 % issue utilisation, tensor pipe 28 %).
+// ---- converter state.  512 converter threads share one 16-k stage of an operand:
+//   OP_KVEC / OP_SCALAR : 4*R pieces of 16 bytes (row r, chunk c) -> up to 2 per thread
+//                         (idx = ct + 512 q: c = idx / R, r = idx % R: lanes = consecutive rows)
+//   OP_TRANS            : R groups (4 consecutive rows x 4 consecutive k) -> one group for each of
+//                         the 256 threads starting at thread t0 (A: 0, B: 256 when both operands are
+//                         transposed streams, so the two operands use disjoint halves of the warps)
+// Everything that does not change from one stage to the next — source pointers, destination
+// offsets inside the MMA tile, row validity — is computed ONCE; per stage a thread only bumps its
+// pointers (the first version recomputed idx / R, 64-bit addresses and bounds for every piece of
+// every stage: instruction-bound at 32 % issue utilisation, tensor pipe 28 %).
 struct PieceSet {
-    const float* src[4];     // piece source at the CTA's first k block
-    const float* msk[4];
-    int toff[4];             // float offset of the destination chunk inside the MMA tile, < 0: no store
-    int koff[4];             // k offset of the piece inside a stage
-    int maxb[4];             // bytes the row geometry allows (0: outside the matrix -> zero fill)
+    const float* src[2];     // piece source at the CTA's first k block (TRANS: src[0] = first k of the group)
+    const float* msk[2];
+    int toff[2];             // float offset of the destination chunk inside the MMA tile, < 0: nothing to store
+    int koff[2];             // k offset of the piece inside a stage
+    int maxb[2];             // bytes the row geometry allows (0: outside the matrix -> zero fill)
     int64_t step, mstep;     // element step of src / msk per stage
+    int tloc, nthr;          // thread index inside the operand's raw-slot region, threads in that region
 };
 
-__device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, int64_t row0, int64_t k_first, int ct,
+__device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, int64_t row0, int64_t k_first, int ct, int t0,
                                             PieceSet& ps) {
+    ps.step = PK_KB * o.s_k;
+    ps.mstep = PK_KB * o.m_k;
     if (o.mode == OP_TRANS) {
-        // one group per thread: 4 consecutive rows (16 bytes along the rows) x 4 consecutive k
+        const int t = ct - t0;
         const int RQ = R >> 2;
-        const int rq = ct % RQ, c = ct / RQ;
+        const bool live = t >= 0 && t < R;
+        const int tt = live ? t : 0;
+        const int rq = tt % RQ, c = tt / RQ;
         const int64_t row = row0 + 4 * rq;
-        const bool live = ct < R;
         int rb = 0;
         if (live && row < o.n_rows) rb = (o.n_rows - row >= 4) ? 16 : (int)(o.n_rows - row) * 4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            ps.koff[e] = 4 * c + e;
-            ps.maxb[e] = rb;
-            ps.src[e] = o.P + (rb ? row + (k_first + 4 * c + e) * o.s_k : 0);
-            ps.msk[e] = o.mask ? o.mask + (rb ? row + (k_first + 4 * c + e) * o.m_k : 0) : nullptr;
-            // destination of output row 4rq+e (the transpose happens in registers)
-            ps.toff[e] = live ? tile_float_off(sub, 4 * rq + e, c) : -1;
-        }
-        ps.step = PK_KB * o.s_k;
-        ps.mstep = PK_KB * o.m_k;
+        ps.koff[0] = 4 * c;
+        ps.maxb[0] = rb;
+        ps.src[0] = o.P + (rb ? row + (k_first + 4 * c) * o.s_k : 0);
+        ps.msk[0] = o.mask ? o.mask + (rb ? row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
+        ps.toff[0] = live ? tile_float_off(sub, 4 * rq, c) : -1;     // rows 4rq+e follow at +4 floats each
+        ps.tloc = (t >= 0 && t < 256) ? t : 0;
+        ps.nthr = 256;
+        ps.koff[1] = 0; ps.maxb[1] = 0; ps.src[1] = o.P; ps.msk[1] = o.mask; ps.toff[1] = -1;
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = ct + PK_CONV_THREADS * j;
+        for (int q = 0; q < 2; ++q) {
+            const int idx = ct + PK_CONV_THREADS * q;
             const int c = idx / R, r = idx - c * R;
             const int64_t row = row0 + r;
             const bool in_tile = c < 4, ok = in_tile && row < o.n_rows;
-            ps.koff[j] = 4 * c;
-            ps.maxb[j] = ok ? 16 : 0;
-            ps.src[j] = o.P + (ok ? row * o.s_row + (k_first + 4 * c) * o.s_k : 0);
-            ps.msk[j] = o.mask ? o.mask + (ok ? row * o.m_row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
-            ps.toff[j] = in_tile ? tile_float_off(sub, r, c) : -1;
+            ps.koff[q] = 4 * c;
+            ps.maxb[q] = ok ? 16 : 0;
+            ps.src[q] = o.P + (ok ? row * o.s_row + (k_first + 4 * c) * o.s_k : 0);
+            ps.msk[q] = o.mask ? o.mask + (ok ? row * o.m_row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
+            ps.toff[q] = in_tile ? tile_float_off(sub, r, c) : -1;
         }
-        ps.step = PK_KB * o.s_k;
-        ps.mstep = PK_KB * o.m_k;
+        ps.tloc = ct;
+        ps.nthr = PK_CONV_THREADS;
     }
 }
 
-// phase 1: cp.async of one stage (krem = K - k0 of the stage).  Slot q of this thread is slots[q * 256]
-// ([0,4) data, [4,8) mask); dead pieces / k tails are zero-filled by the copy itself (src-size < 16).
-__device__ __forceinline__ void stream_issue(const StreamOp& o, PieceSet& ps, int64_t krem, float4* slots) {
-    const int kr = krem > 64 ? 64 : (int)krem;
+// phase 1: cp.async of one stage (kr = min(K - k0, 64) of the stage).  `slots` = the operand's raw
+// region of this depth + tloc; slot q is slots[q * nthr] (data first, then the mask slots); dead
+// pieces / k tails are zero-filled by the copy itself (src-size < cp-size).
+__device__ __forceinline__ void stream_issue(const StreamOp& o, PieceSet& ps, int kr, float4* slots) {
+    const int nthr = ps.nthr;
+    if (o.mode == OP_TRANS) {
+        if (ps.toff[0] < 0) return;          // thread outside the operand's group range: owns no slot
+        const int rb = ps.maxb[0];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (o.mode == OP_SCALAR) {
+        for (int e = 0; e < 4; ++e) {
+            const int bytes = (ps.koff[0] + e < kr) ? rb : 0;
+            cp_async16(&slots[e * nthr], bytes ? ps.src[0] + e * o.s_k : o.P, bytes);
+            if (o.mask) cp_async16(&slots[(4 + e) * nthr], bytes ? ps.msk[0] + e * o.m_k : o.mask, bytes);
+        }
+        ps.src[0] += ps.step;
+        if (o.mask) ps.msk[0] += ps.mstep;
+    } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool ok = ps.maxb[q] && ps.koff[q] + e < kr;
-                cp_async4(reinterpret_cast<float*>(&slots[q * PK_CONV_THREADS]) + e, ok ? ps.src[q] + e * o.s_k : o.P, ok ? 4 : 0);
-                if (o.mask)
-                    cp_async4(reinterpret_cast<float*>(&slots[(4 + q) * PK_CONV_THREADS]) + e, ok ? ps.msk[q] + e * o.m_k : o.mask,
-                              ok ? 4 : 0);
-            }
-        } else {
-            int bytes;
+        for (int q = 0; q < 2; ++q) {
+            if (ps.toff[q] < 0) continue;     // piece outside the tile (R < 256)
             if (o.mode == OP_KVEC) {
-                bytes = (kr - ps.koff[q]) * 4;
+                int bytes = (kr - ps.koff[q]) * 4;
                 bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
                 if (!ps.maxb[q]) bytes = 0;
+                cp_async16(&slots[q * nthr], bytes ? ps.src[q] : o.P, bytes);
+                if (o.mask) cp_async16(&slots[(2 + q) * nthr], bytes ? ps.msk[q] : o.mask, bytes);
             } else {
-                bytes = ps.koff[q] < kr ? ps.maxb[q] : 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = ps.maxb[q] && ps.koff[q] + e < kr;
+                    cp_async4(reinterpret_cast<float*>(&slots[q * nthr]) + e, ok ? ps.src[q] + e * o.s_k : o.P, ok ? 4 : 0);
+                    if (o.mask)
+                        cp_async4(reinterpret_cast<float*>(&slots[(2 + q) * nthr]) + e, ok ? ps.msk[q] + e * o.m_k : o.mask,
+                                  ok ? 4 : 0);
+                }
             }
-            cp_async16(&slots[q * PK_CONV_THREADS], bytes ? ps.src[q] : o.P, bytes);
-            if (o.mask) cp_async16(&slots[(4 + q) * PK_CONV_THREADS], bytes ? ps.msk[q] : o.mask, bytes);
+            ps.src[q] += ps.step;
+            if (o.mask) ps.msk[q] += ps.mstep;
         }
-        ps.src[q] += ps.step;
-        if (o.mask) ps.msk[q] += ps.mstep;
     }
 }
 
@@ -366,25 +384,26 @@ __device__ __forceinline__ void split_store(float* tile, int off, int lo_off, fl
 // phase 2: own raw slots -> (mask) -> hi/lo split -> MMA tile (sub = rows of a sub-tile: lo part at +sub*16 floats)
 __device__ __forceinline__ void stream_convert(const StreamOp& o, const PieceSet& ps, int sub, float* tile, const float4* slots) {
     const int lo_off = sub * 16;
+    const int nthr = ps.nthr;
     if (o.mode == OP_TRANS) {
         if (ps.toff[0] < 0) return;
         float4 x[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            x[e] = slots[e * PK_CONV_THREADS];
-            if (o.mask) x[e] = pk_mask4(x[e], slots[(4 + e) * PK_CONV_THREADS], o.mask_act);
+            x[e] = slots[e * nthr];
+            if (o.mask) x[e] = pk_mask4(x[e], slots[(4 + e) * nthr], o.mask_act);
         }
         // 4x4 register transpose: output row i gets (k, k+1, k+2, k+3)
         split_store(tile, ps.toff[0], lo_off, make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
-        split_store(tile, ps.toff[1], lo_off, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
-        split_store(tile, ps.toff[2], lo_off, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
-        split_store(tile, ps.toff[3], lo_off, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
+        split_store(tile, ps.toff[0] + 4, lo_off, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
+        split_store(tile, ps.toff[0] + 8, lo_off, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
+        split_store(tile, ps.toff[0] + 12, lo_off, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             if (ps.toff[q] < 0) continue;
-            float4 v = slots[q * PK_CONV_THREADS];
-            if (o.mask) v = pk_mask4(v, slots[(4 + q) * PK_CONV_THREADS], o.mask_act);
+            float4 v = slots[q * nthr];
+            if (o.mask) v = pk_mask4(v, slots[(2 + q) * nthr], o.mask_act);
             split_store(tile, ps.toff[q], lo_off, v);
         }
     }
@@ -512,14 +531,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const bool a_stream = p.sa.mode != OP_PACKED, b_stream = p.sb.mode != OP_PACKED;
 
     if (tid == 0) {
-        // a stage is full after the 8 converter warps arrived (streamed operand) or after the TMA
+        // a stage is full after all converter warps arrived (streamed operand) or after the TMA
         // transaction armed by the producer completed (packed operand)
         for (int s = 0; s < SA; ++s) {
-            mbar_init(&a_full[s], a_stream ? 8 : 1);
+            mbar_init(&a_full[s], a_stream ? PK_CONV_WARPS : 1);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < SB; ++s) {
-            mbar_init(&b_full[s], b_stream ? 8 : 1);
+            mbar_init(&b_full[s], b_stream ? PK_CONV_WARPS : 1);
             mbar_init(&b_empty[s], 1);
         }
         mbar_init(accum_bar, 1);
@@ -536,21 +555,23 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         if (lane == 0 && (!a_stream || !b_stream)) {
             const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.Ap);
             const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
+            int sa = 0, sb = 0;
+            uint32_t pha = 1, phb = 1;                    // parity of the "empty" phase to wait for
             for (int i = 0; i < nkb; ++i) {
                 const int64_t kb = kb_beg + i;
                 if (!a_stream) {
-                    const int s = i % SA;
-                    mbar_wait(&a_empty[s], ((uint32_t)(i / SA) & 1u) ^ 1u);
-                    mbar_expect_tx(&a_full[s], a_stage);
+                    mbar_wait(&a_empty[sa], pha);
+                    mbar_expect_tx(&a_full[sa], a_stage);
                     for (int mt = 0; mt < MT; ++mt)
-                        bulk_g2s(ringA + (size_t)s * a_stage + (size_t)mt * a_tile,
-                                 a_src + ((mblk * MT + mt) * p.nkb + kb) * (int64_t)a_tile, a_tile, &a_full[s]);
+                        bulk_g2s(ringA + (size_t)sa * a_stage + (size_t)mt * a_tile,
+                                 a_src + ((mblk * MT + mt) * p.nkb + kb) * (int64_t)a_tile, a_tile, &a_full[sa]);
+                    if (++sa == SA) { sa = 0; pha ^= 1u; }
                 }
                 if (!b_stream) {
-                    const int s = i % SB;
-                    mbar_wait(&b_empty[s], ((uint32_t)(i / SB) & 1u) ^ 1u);
-                    mbar_expect_tx(&b_full[s], b_stage);
-                    bulk_g2s(ringB + (size_t)s * b_stage, b_src + (nblk * p.nkb + kb) * (int64_t)b_stage, b_stage, &b_full[s]);
+                    mbar_wait(&b_empty[sb], phb);
+                    mbar_expect_tx(&b_full[sb], b_stage);
+                    bulk_g2s(ringB + (size_t)sb * b_stage, b_src + (nblk * p.nkb + kb) * (int64_t)b_stage, b_stage, &b_full[sb]);
+                    if (++sb == SB) { sb = 0; phb ^= 1u; }
                 }
             }
         }
@@ -559,10 +580,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         // ------------------------------ MMA issuer ------------------------------------------
         const uint32_t idesc = tf32_idesc(BN);
         const uint32_t a_lbo = PK_AR * 16u, b_lbo = (uint32_t)BN * 16u;     // between the two chunks of a K atom
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
         for (int i = 0; i < nkb; ++i) {
-            const int sa = i % SA, sb = i % SB;
-            mbar_wait(&a_full[sa], (uint32_t)(i / SA) & 1u);
-            mbar_wait(&b_full[sb], (uint32_t)(i / SB) & 1u);
+            mbar_wait(&a_full[sa], pha);
+            mbar_wait(&b_full[sb], phb);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(ringA + (size_t)sa * a_stage);
@@ -586,64 +608,72 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                 if (i == nkb - 1) umma_commit(accum_bar);
             }
             __syncwarp();
+            if (++sa == SA) { sa = 0; pha ^= 1u; }
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
         }
     } else {
-        // ------------------------------ converters (8 warps), then epilogue -----------------
+        // ------------------------------ converters (16 warps), then epilogue ----------------
         if (a_stream || b_stream) {
             const int ct = tid - 64;
-            const int nslots = p.slots_a + p.slots_b;
-            float4* raw = reinterpret_cast<float4*>(smem_raw + p.off_raw);
-            // slot q of depth d of thread ct lives at raw[(d*nslots + q)*256 + ct]
+            unsigned char* raw = smem_raw + p.off_raw;
+            const uint32_t raw_depth = p.raw_a_bytes + p.raw_b_bytes;
             const int64_t a_row0 = mblk * (int64_t)MT * PK_AR, b_row0 = nblk * (int64_t)BN;
             PieceSet pa, pb;
-            if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, kb_beg * PK_KB, ct, pa);
-            if (b_stream) piece_setup(p.sb, BN, BN, b_row0, kb_beg * PK_KB, ct, pb);
-            auto issue = [&](int i) {
-                if (i < nkb) {
-                    const int d = i % p.depth;
-                    const int64_t krem = g.K - (kb_beg + i) * PK_KB;
-                    float4* base = raw + (size_t)d * nslots * PK_CONV_THREADS + ct;
-                    if (a_stream) stream_issue(p.sa, pa, krem, base);
-                    if (b_stream) stream_issue(p.sb, pb, krem, base + (size_t)p.slots_a * PK_CONV_THREADS);
+            if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, kb_beg * PK_KB, ct, 0, pa);
+            if (b_stream) piece_setup(p.sb, BN, BN, b_row0, kb_beg * PK_KB, ct, p.t0_b, pb);
+            int64_t krem_issue = g.K - kb_beg * PK_KB;    // K left at the stage being issued
+            int issued = 0, d_issue = 0;
+            auto issue = [&]() {
+                if (issued < nkb) {
+                    const int kr = krem_issue > 64 ? 64 : (int)krem_issue;
+                    unsigned char* base = raw + (size_t)d_issue * raw_depth;
+                    if (a_stream) stream_issue(p.sa, pa, kr, reinterpret_cast<float4*>(base) + pa.tloc);
+                    if (b_stream) stream_issue(p.sb, pb, kr, reinterpret_cast<float4*>(base + p.raw_a_bytes) + pb.tloc);
                 }
                 cp_async_commit();
+                ++issued;
+                krem_issue -= PK_KB;
+                if (++d_issue == p.depth) d_issue = 0;
             };
-            for (int i = 0; i < p.depth; ++i) issue(i);
+            for (int i = 0; i < p.depth; ++i) issue();
+            int sa = 0, sb = 0, d = 0;
+            uint32_t pha = 1, phb = 1;
             for (int i = 0; i < nkb; ++i) {
                 if (p.depth == 3) cp_async_wait<2>();
                 else cp_async_wait<1>();
-                const int d = i % p.depth;
-                const float4* base = raw + (size_t)d * nslots * PK_CONV_THREADS + ct;
+                const unsigned char* base = raw + (size_t)d * raw_depth;
                 if (a_stream) {
-                    const int s = i % SA;
-                    mbar_wait(&a_empty[s], ((uint32_t)(i / SA) & 1u) ^ 1u);
-                    stream_convert(p.sa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)s * a_stage), base);
+                    mbar_wait(&a_empty[sa], pha);
+                    stream_convert(p.sa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)sa * a_stage),
+                                   reinterpret_cast<const float4*>(base) + pa.tloc);
                 }
                 if (b_stream) {
-                    const int s = i % SB;
-                    mbar_wait(&b_empty[s], ((uint32_t)(i / SB) & 1u) ^ 1u);
-                    stream_convert(p.sb, pb, BN, reinterpret_cast<float*>(ringB + (size_t)s * b_stage),
-                                   base + (size_t)p.slots_a * PK_CONV_THREADS);
+                    mbar_wait(&b_empty[sb], phb);
+                    stream_convert(p.sb, pb, BN, reinterpret_cast<float*>(ringB + (size_t)sb * b_stage),
+                                   reinterpret_cast<const float4*>(base + p.raw_a_bytes) + pb.tloc);
                 }
                 fence_async_smem();                       // generic-proxy stores -> async proxy (tcgen05.mma)
                 __syncwarp();
                 if (lane == 0) {
-                    if (a_stream) mbar_arrive(&a_full[i % SA]);
-                    if (b_stream) mbar_arrive(&b_full[i % SB]);
+                    if (a_stream) mbar_arrive(&a_full[sa]);
+                    if (b_stream) mbar_arrive(&b_full[sb]);
                 }
-                issue(i + p.depth);
+                if (++sa == SA) { sa = 0; pha ^= 1u; }
+                if (++sb == SB) { sb = 0; phb ^= 1u; }
+                if (++d == p.depth) d = 0;
+                issue();
             }
             cp_async_wait<0>();
         }
-        // ------------------------------ epilogue (8 warps) ----------------------------------
-        // Two warps per TMEM lane quadrant, alternating 32-column chunks.  tcgen05.ld hands every
+        // ------------------------------ epilogue (16 warps) ---------------------------------
+        // Four warps per TMEM lane quadrant, interleaved over the 32-column chunks.  tcgen05.ld hands every
         // thread ONE row (32 consecutive columns); written like that to C a warp would touch 32
         // different rows per store.  So each chunk is transposed through a padded per-warp staging
         // tile in shared memory (the pipeline stages are free once accum_bar fires) and the epilogue
         // math + stores run in the coalesced domain: 8 lanes cover 128 contiguous bytes of a row.
         const int ew = wid - 2;
         const int quad = wid & 3;                         // TMEM lane quadrant this warp may read
-        const int half = ew >> 2;
+        const int cgrp = ew >> 2;
         float* stg = reinterpret_cast<float*>(smem_raw) + (size_t)ew * (32 * PK_STG_PITCH);
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -652,7 +682,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         for (int mt = 0; mt < MT; ++mt) {
             const int64_t m_base = (mblk * MT + mt) * PK_AR + quad * 32;
             if (m_base >= g.M) break;                     // warp-uniform
-            for (int ci = half; ci < nchunks; ci += 2) {
+            for (int ci = cgrp; ci < nchunks; ci += PK_CONV_WARPS / 4) {
                 const int c0 = ci * 32;
                 if (n0 + c0 >= g.N) break;                // warp-uniform
                 uint32_t raw[32];
@@ -701,7 +731,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
 // ---------------------------------------------------------------------------------------------
 struct PkConfig {
     int BN, MT, SA, SB, depth, tmem_cols;
-    int a_mode, b_mode, slots_a, slots_b;
+    int a_mode, b_mode, t0_b;
+    uint32_t raw_a_bytes, raw_b_bytes;
     int64_t gm, gn, splits, nkb, kb_per_split;
     int64_t a_bytes, b_bytes;    // scratch for the packed operands (0 when streamed)
     uint32_t off_b, off_raw, off_bar, smem;
@@ -758,14 +789,17 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split) {
     c.b_mode = (stream_ok && c.b_bytes > kStreamThresholdBytes) ? stream_mode(g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk) : OP_PACKED;
     if (c.a_mode != OP_PACKED) c.a_bytes = 0;
     if (c.b_mode != OP_PACKED) c.b_bytes = 0;
-    c.slots_a = c.a_mode == OP_PACKED ? 0 : (g.amask ? 8 : 4);
-    c.slots_b = c.b_mode == OP_PACKED ? 0 : (g.bmask ? 8 : 4);
+    // raw cp.async region of a streamed operand per depth: 16 KB of data (+16 KB for its mask):
+    // KVEC/SCALAR = 2 slots x 512 threads, TRANS = 4 slots x 256 threads, 16 bytes each
+    c.raw_a_bytes = c.a_mode == OP_PACKED ? 0u : (g.amask ? 32768u : 16384u);
+    c.raw_b_bytes = c.b_mode == OP_PACKED ? 0u : (g.bmask ? 32768u : 16384u);
+    c.t0_b = (c.a_mode == OP_TRANS && c.b_mode == OP_TRANS) ? 256 : 0;
 
     // shared-memory plan: [A ring | B ring | raw cp.async slots | barriers]
     const int64_t a_stage = (int64_t)c.MT * PK_AR * 128, b_stage = (int64_t)c.BN * 128;
-    const int64_t raw_per_depth = (int64_t)(c.slots_a + c.slots_b) * PK_CONV_THREADS * 16;
+    const int64_t raw_per_depth = (int64_t)c.raw_a_bytes + c.raw_b_bytes;
     const int64_t budget = 220 * 1024 - 512;
-    const int64_t stg = 8 * 32 * PK_STG_PITCH * 4;       // epilogue staging overlays the rings
+    const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;       // epilogue staging overlays the rings
     c.ok = false;
     if (raw_per_depth == 0) {
         int S = (int)(budget / (a_stage + b_stage));
@@ -899,8 +933,9 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     p.off_b = c.off_b;
     p.off_raw = c.off_raw;
     p.off_bar = c.off_bar;
-    p.slots_a = c.slots_a;
-    p.slots_b = c.slots_b;
+    p.raw_a_bytes = c.raw_a_bytes;
+    p.raw_b_bytes = c.raw_b_bytes;
+    p.t0_b = c.t0_b;
     const size_t smem = c.smem;
     static bool configured = false;
     if (!configured) {

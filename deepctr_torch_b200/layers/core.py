@@ -42,6 +42,10 @@ class DNN(nn.Module):
 
     def forward(self, inputs):
         x = inputs
+        if not self.use_bn and not (self.dropout_rate > 0 and self.training):
+            # the whole stack as one autograd node: the backward hands dZ from layer to layer
+            return ops.dnn_tower(x, self.activation, [lin.weight for lin in self.linears],
+                                 [lin.bias for lin in self.linears])
         for i, lin in enumerate(self.linears):
             if self.use_bn:
                 x = ops.dnn_layer(x, lin.weight, lin.bias, "linear")

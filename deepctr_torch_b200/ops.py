@@ -387,6 +387,82 @@ def dnn_layer(x, W, bias, act="relu", w_kn=False):
     return _DnnLayer.apply(x, W, bias, act_code(act) if isinstance(act, str) else int(act), w_kn)
 
 
+class _DnnTower(torch.autograd.Function):
+    """A stack of Linear(+bias) -> activation layers as ONE autograd node (reference core.py:120-134
+    without batch-norm / dropout).  Forward = one fused GEMM+bias+activation launch per layer; the
+    backward chains ctr_dnn_layer_bwd_chain so that every layer writes the dZ of the layer below
+    directly (input gradient times act'(input) in the GEMM epilogue): only the top layer reads an
+    activation mask, and no dY (.) act'(Y) product is ever re-derived from two tensors."""
+
+    @staticmethod
+    def forward(ctx, x, act, *params):
+        _require_cuda(x, "DNN input")
+        x = _rowmajor(x)
+        L = len(params) // 2
+        xs, Ws, ys, kws = [], [], [], []
+        cur = x
+        for l in range(L):
+            W, b = params[2 * l], params[2 * l + 1]
+            B, K = cur.shape
+            Wc = W if W.is_contiguous() else W.contiguous()
+            N, Kw = Wc.shape
+            if Kw % 4 != 0:
+                Wc = torch.nn.functional.pad(Wc, (0, _round4(Kw) - Kw))
+            if K != Kw and K != _round4(Kw):
+                raise ValueError("dnn_tower: input width %d does not match weight width %d" % (K, Kw))
+            y = torch.empty(B, N, device=x.device, dtype=torch.float32)
+            ensure_gemm_scratch(x.device, B, K, N)
+            _lib.call("ctr_dnn_layer_fwd", _ptr(cur), cur.stride(0), _ptr(Wc), Wc.shape[1], 1, _ptr(b),
+                      _ptr(y), N, B, K, N, act, _stream())
+            xs.append(cur)
+            Ws.append(Wc)
+            ys.append(y)
+            kws.append(Kw)
+            cur = y
+        ctx.act, ctx.L, ctx.kws = act, L, kws
+        ctx.wshapes = [tuple(params[2 * l].shape) for l in range(L)]
+        ctx.save_for_backward(*xs, *Ws, *ys)
+        return cur
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = ctx.L
+        saved = ctx.saved_tensors
+        xs, Ws, ys = saved[:L], saved[L:2 * L], saved[2 * L:3 * L]
+        dev = dy.device
+        cur = _rowmajor(dy)
+        grads = [None] * (2 * L)
+        dx_out = None
+        for l in range(L - 1, -1, -1):
+            x, Wc, y = xs[l], Ws[l], ys[l]
+            B, K = x.shape
+            N = y.shape[1]
+            Kc = Wc.shape[1]                      # contraction width actually used (padded or not)
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            ldx = _round4(K)
+            dx_full = torch.empty(B, ldx, device=dev, dtype=torch.float32) if need_dx else None
+            dW = torch.empty(N, Kc, device=dev, dtype=torch.float32)
+            db = torch.empty(N, device=dev, dtype=torch.float32)
+            _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
+                      _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, _ptr(dW), Kc, 1, _ptr(db),
+                      B, K, N, ctx.act, 1 if l < L - 1 else 0,
+                      ctx.act if l > 0 else 0, _stream())
+            grads[2 * l] = dW[:, :ctx.kws[l]].contiguous() if Kc != ctx.kws[l] else dW
+            grads[2 * l + 1] = db
+            if need_dx:
+                cur = dx_full[:, :K] if ldx != K else dx_full
+                dx_out = cur
+        return (dx_out if ctx.needs_input_grad[0] else None, None) + tuple(grads)
+
+
+def dnn_tower(x, act, weights, biases):
+    """act(...act(x W0^T + b0)... W_{L-1}^T + b_{L-1}); every layer needs a bias (nn.Linear default)."""
+    params = []
+    for W, b in zip(weights, biases):
+        params += [W, b]
+    return _DnnTower.apply(x, act_code(act) if isinstance(act, str) else int(act), *params)
+
+
 class _RowDot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, H, w):

@@ -165,6 +165,18 @@ int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, int64_t swn, 
                       float* dW, int64_t sdwn, int64_t sdwk, float* db,
                       int64_t B, int K, int N, int act, void* stream);
 
+/* Backward of one layer INSIDE a tower (reference layers/core.py:120-134 stacks Linear -> act):
+ * like ctr_dnn_layer_bwd, plus the two fusions that remove the activation-mask traffic between
+ * consecutive layers:
+ *   dy_is_dz != 0 : dY already IS dZ of this layer (the layer above produced it), Y is not read;
+ *   dx_act        : activation of the layer BELOW (whose output is this layer's input X): the
+ *                   input gradient is written as dX (.) dx_act'(X), i.e. as the dZ of that layer
+ *                   (CTR_ACT_LINEAR = plain dX). */
+int ctr_dnn_layer_bwd_chain(const float* X, int64_t ldx, const float* W, int64_t swn, int64_t swk,
+                            const float* Y, int64_t ldy, const float* dY, int64_t lddy,
+                            float* dX, int64_t lddx, float* dW, int64_t sdwn, int64_t sdwk, float* db,
+                            int64_t B, int K, int N, int act, int dy_is_dz, int dx_act, void* stream);
+
 /* Scratch for the tensor-core GEMM engine (csrc/gemm_pk.cu): every GEMM-shaped entry point
  * (ctr_dnn_layer_*, ctr_sgemm, ctr_cross_matrix_*, CrossNetMix projections) first re-tiles its two
  * operands into pre-split (hi, lo) TF32 tiles inside a CALLER-OWNED device buffer.  The library
