@@ -329,7 +329,11 @@ int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
         return 0;
     }
     const int engine = gemm_engine(g);
-    if (engine == 2) return launch_gemm_pk(g, st);
+    if (engine == 2) {
+        const int rc = launch_gemm_pk(g, st);
+        if (rc != -3) return rc;          // -3: operand layout the packed/streaming engine does not take
+        return launch_gemm_tc(g, st);
+    }
     if (engine == 1) return launch_gemm_tc(g, st);
     const bool big = (g.M >= 128 && g.N >= 96) || (g.N >= 128 && g.M >= 96);
     const int BM = big ? 128 : 64, BN = big ? 128 : 64, BK = 16;

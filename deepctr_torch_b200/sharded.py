@@ -250,15 +250,25 @@ class ShardedRuntime:
         self.plan.recv_views(parity)[0].zero_()
 
 
+def localize_cfg(cfg, world):
+    """Copy of an oracle-style cfg whose sparse vocabularies are the per-rank row counts.  The same
+    column dict may be listed under both `linear_columns` and `dnn_columns` (deepcopy keeps that
+    sharing): every distinct column is localised exactly once."""
+    import copy
+    local_cfg = copy.deepcopy(cfg)
+    seen = set()
+    for col in local_cfg["linear_columns"] + local_cfg["dnn_columns"]:
+        if col["type"] == "sparse" and id(col) not in seen:
+            seen.add(id(col))
+            col["vocab"] = max_local_rows(col["vocab"], world)
+    return local_cfg
+
+
 def build_sharded(cfg, device, rank, world, batch=65536, group=None):
     """Build the model described by an oracle-style cfg with row-sharded tables on this rank."""
-    import copy
     from .config import model_from_cfg as build_model
 
-    local_cfg = copy.deepcopy(cfg)
-    for col in local_cfg["linear_columns"] + local_cfg["dnn_columns"]:
-        if col["type"] == "sparse":
-            col["vocab"] = max_local_rows(col["vocab"], world)
+    local_cfg = localize_cfg(cfg, world)
     model = build_model(local_cfg, device, table_grad="rowwise")
     attach_shards(model, cfg, rank, world, batch, group)
     return model, "dp%d: tower data-parallel (NCCL all-reduce), tables row-sharded (NVLink P2P gather/push)" % world

@@ -48,10 +48,7 @@ def main():
         if c["type"] == "sparse":
             table_vocab["embedding_dict.%s.weight" % c["name"]] = c["vocab"]
             table_vocab["linear_model.embedding_dict.%s.weight" % c["name"]] = c["vocab"]
-    local_cfg = copy.deepcopy(cfg)
-    for c in local_cfg["linear_columns"] + local_cfg["dnn_columns"]:
-        if c["type"] == "sparse":
-            c["vocab"] = sharded.max_local_rows(c["vocab"], world)
+    local_cfg = sharded.localize_cfg(cfg, world)
     sh = model_from_cfg(local_cfg, dev, table_grad="rowwise")
     sh.load_state_dict({k: v.to(dev) for k, v in sharded.scatter_full_state_dict(full_state, table_vocab, rank, world).items()})
     sharded.attach_shards(sh, cfg, rank, world, batch=B)

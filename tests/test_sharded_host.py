@@ -73,3 +73,19 @@ def test_state_dict_gather_scatter_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_localize_cfg_handles_columns_shared_between_linear_and_dnn():
+    """make_cfg(model, cols, cols) lists the SAME column dicts twice; each must be localised once."""
+    from oracle import ctr_oracle as O
+    cols = [O.sparse_col("C%d" % i, 1003 + 7 * i, 16) for i in range(3)] + [O.dense_col("I0")]
+    cfg = O.make_cfg("DeepFM", cols, cols, dnn_hidden_units=[8])
+    for world in (2, 8):
+        loc = sharded.localize_cfg(cfg, world)
+        for c_full, c_loc in zip(cfg["dnn_columns"], loc["dnn_columns"]):
+            if c_full["type"] == "sparse":
+                assert c_loc["vocab"] == sharded.max_local_rows(c_full["vocab"], world)
+        for c_full, c_loc in zip(cfg["linear_columns"], loc["linear_columns"]):
+            if c_full["type"] == "sparse":
+                assert c_loc["vocab"] == sharded.max_local_rows(c_full["vocab"], world)
+        assert cfg["dnn_columns"][0]["vocab"] == 1003           # the logical cfg is untouched
