@@ -250,7 +250,6 @@ struct PkParams {
     uint32_t off_b, off_raw, off_bar;     // shared-memory layout (bytes): A ring at 0
     uint32_t raw_a_bytes, raw_b_bytes;    // raw cp.async region of each streamed operand, per depth
     int t0_b;                             // first converter thread of B's OP_TRANS groups
-    int G;                                // converter groups (1 or 2)
 };
 
 constexpr int PK_CONV_THREADS = PK_CONV_WARPS * 32;
@@ -271,6 +270,11 @@ __device__ __forceinline__ int tile_float_off(int sub, int r, int c) {
     const int st = r / sub, rr = r - st * sub;
     return st * (sub * 32) + (c * sub + rr) * 4;
 }
+__device__ __forceinline__ void pin_op(StreamOp& o) {
+    // opaque to the optimiser: the values now live in registers, not in the parameter bank
+    asm volatile("" : "+l"(o.P), "+l"(o.mask), "+l"(o.s_k), "+l"(o.m_k), "+r"(o.mode), "+r"(o.mask_act));
+}
+
 // ---- converter state.  512 converter threads share one 16-k stage of an operand:
 //   OP_KVEC / OP_SCALAR : 4*R pieces of 16 bytes (row r, chunk c) -> up to 2 per thread
 //                         (idx = ct + 512 q: c = idx / R, r = idx % R: lanes = consecutive rows)
@@ -282,29 +286,21 @@ __device__ __forceinline__ int tile_float_off(int sub, int r, int c) {
 // pointers (the first version recomputed idx / R, 64-bit addresses and bounds for every piece of
 // every stage: instruction-bound at 32 % issue utilisation, tensor pipe 28 %).
 struct PieceSet {
-    const float* src[4];     // piece source at the group's first k block (TRANS: src[0] = first k of the 4x4 group)
-    int toff[4];             // float offset of the destination chunk inside the MMA tile, < 0: nothing to store
-    int koff[4];             // k offset of the piece inside a stage
-    int rb;                  // TRANS: bytes the row geometry allows (0: outside the matrix -> zero fill)
-    int64_t step;            // element step of src per handled stage
-    int64_t mdelta;          // mask element = source element + mdelta (the mask has the operand's strides)
-    int tloc, nthr, np;      // thread index / thread count of the operand's raw-slot region, pieces per thread
+    const float* src[2];     // piece source at the CTA's first k block (TRANS: src[0] = first k of the group)
+    const float* msk[2];
+    int toff[2];             // float offset of the destination chunk inside the MMA tile, < 0: nothing to store
+    int koff[2];             // k offset of the piece inside a stage
+    int maxb[2];             // bytes the row geometry allows (0: outside the matrix -> zero fill)
+    int64_t step, mstep;     // element step of src / msk per stage
+    int tloc, nthr;          // thread index inside the operand's raw-slot region, threads in that region
 };
 
-// gt / nthr: index of this thread inside its converter group and the size of the group; t0: first
-// thread of the operand's OP_TRANS groups; kstep: 16 x (number of converter groups)
-__device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, int64_t row0, int64_t k_first, int gt, int nthr,
-                                            int t0, int kstep, PieceSet& ps) {
-    ps.step = (int64_t)kstep * o.s_k;
-    ps.mdelta = o.mask ? (o.mask - o.P) : 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        ps.src[q] = o.P;
-        ps.toff[q] = -1;
-        ps.koff[q] = 1 << 20;        // dead piece: never inside the remaining K
-    }
+__device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, int64_t row0, int64_t k_first, int ct, int t0,
+                                            PieceSet& ps) {
+    ps.step = PK_KB * o.s_k;
+    ps.mstep = PK_KB * o.m_k;
     if (o.mode == OP_TRANS) {
-        const int t = gt - t0;
+        const int t = ct - t0;
         const int RQ = R >> 2;
         const bool live = t >= 0 && t < R;
         const int tt = live ? t : 0;
@@ -313,65 +309,69 @@ __device__ __forceinline__ void piece_setup(const StreamOp& o, int R, int sub, i
         int rb = 0;
         if (live && row < o.n_rows) rb = (o.n_rows - row >= 4) ? 16 : (int)(o.n_rows - row) * 4;
         ps.koff[0] = 4 * c;
-        ps.rb = rb;
+        ps.maxb[0] = rb;
         ps.src[0] = o.P + (rb ? row + (k_first + 4 * c) * o.s_k : 0);
+        ps.msk[0] = o.mask ? o.mask + (rb ? row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
         ps.toff[0] = live ? tile_float_off(sub, 4 * rq, c) : -1;     // rows 4rq+e follow at +4 floats each
-        ps.tloc = live ? t : 0;
+        ps.tloc = (t >= 0 && t < 256) ? t : 0;
         ps.nthr = 256;
-        ps.np = 4;
+        ps.koff[1] = 0; ps.maxb[1] = 0; ps.src[1] = o.P; ps.msk[1] = o.mask; ps.toff[1] = -1;
     } else {
-        ps.np = (4 * R + nthr - 1) / nthr;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int idx = gt + nthr * q;
+        for (int q = 0; q < 2; ++q) {
+            const int idx = ct + PK_CONV_THREADS * q;
             const int c = idx / R, r = idx - c * R;
             const int64_t row = row0 + r;
-            const bool in_tile = q < ps.np && c < 4, ok = in_tile && row < o.n_rows;
-            ps.koff[q] = ok ? 4 * c : (1 << 20);
+            const bool in_tile = c < 4, ok = in_tile && row < o.n_rows;
+            ps.koff[q] = 4 * c;
+            ps.maxb[q] = ok ? 16 : 0;
             ps.src[q] = o.P + (ok ? row * o.s_row + (k_first + 4 * c) * o.s_k : 0);
+            ps.msk[q] = o.mask ? o.mask + (ok ? row * o.m_row + (k_first + 4 * c) * o.m_k : 0) : nullptr;
             ps.toff[q] = in_tile ? tile_float_off(sub, r, c) : -1;
         }
-        ps.tloc = gt;
-        ps.nthr = nthr;
+        ps.tloc = ct;
+        ps.nthr = PK_CONV_THREADS;
     }
 }
 
 // phase 1: cp.async of one stage (kr = min(K - k0, 64) of the stage).  `slots` = the operand's raw
-// region of this depth + tloc; data slot q is slots[q * nthr], its mask slot slots[(np + q) * nthr];
-// dead pieces / k tails are zero-filled by the copy itself (src-size < cp-size).
+// region of this depth + tloc; slot q is slots[q * nthr] (data first, then the mask slots); dead
+// pieces / k tails are zero-filled by the copy itself (src-size < cp-size).
 __device__ __forceinline__ void stream_issue(const StreamOp& o, PieceSet& ps, int kr, float4* slots) {
     const int nthr = ps.nthr;
     if (o.mode == OP_TRANS) {
         if (ps.toff[0] < 0) return;          // thread outside the operand's group range: owns no slot
-        const int rb = ps.rb;
+        const int rb = ps.maxb[0];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int bytes = (ps.koff[0] + e < kr) ? rb : 0;
-            const float* sp = bytes ? ps.src[0] + e * o.s_k : o.P;
-            cp_async16(&slots[e * nthr], sp, bytes);
-            if (o.mask) cp_async16(&slots[(4 + e) * nthr], sp + ps.mdelta, bytes);
+            cp_async16(&slots[e * nthr], bytes ? ps.src[0] + e * o.s_k : o.P, bytes);
+            if (o.mask) cp_async16(&slots[(4 + e) * nthr], bytes ? ps.msk[0] + e * o.m_k : o.mask, bytes);
         }
         ps.src[0] += ps.step;
+        if (o.mask) ps.msk[0] += ps.mstep;
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (ps.toff[q] < 0) continue;     // no such piece in this configuration
+        for (int q = 0; q < 2; ++q) {
+            if (ps.toff[q] < 0) continue;     // piece outside the tile (R < 256)
             if (o.mode == OP_KVEC) {
                 int bytes = (kr - ps.koff[q]) * 4;
                 bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-                const float* sp = bytes ? ps.src[q] : o.P;
-                cp_async16(&slots[q * nthr], sp, bytes);
-                if (o.mask) cp_async16(&slots[(ps.np + q) * nthr], sp + ps.mdelta, bytes);
+                if (!ps.maxb[q]) bytes = 0;
+                cp_async16(&slots[q * nthr], bytes ? ps.src[q] : o.P, bytes);
+                if (o.mask) cp_async16(&slots[(2 + q) * nthr], bytes ? ps.msk[q] : o.mask, bytes);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool ok = ps.koff[q] + e < kr;
-                    const float* sp = ok ? ps.src[q] + e * o.s_k : o.P;
-                    cp_async4(reinterpret_cast<float*>(&slots[q * nthr]) + e, sp, ok ? 4 : 0);
-                    if (o.mask) cp_async4(reinterpret_cast<float*>(&slots[(ps.np + q) * nthr]) + e, sp + ps.mdelta, ok ? 4 : 0);
+                    const bool ok = ps.maxb[q] && ps.koff[q] + e < kr;
+                    cp_async4(reinterpret_cast<float*>(&slots[q * nthr]) + e, ok ? ps.src[q] + e * o.s_k : o.P, ok ? 4 : 0);
+                    if (o.mask)
+                        cp_async4(reinterpret_cast<float*>(&slots[(2 + q) * nthr]) + e, ok ? ps.msk[q] + e * o.m_k : o.mask,
+                                  ok ? 4 : 0);
                 }
             }
             ps.src[q] += ps.step;
+            if (o.mask) ps.msk[q] += ps.mstep;
         }
     }
 }
@@ -404,17 +404,12 @@ __device__ __forceinline__ void stream_convert(const StreamOp& o, const PieceSet
         split_store(tile, ps.toff[0] + 8, lo_off, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
         split_store(tile, ps.toff[0] + 12, lo_off, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
     } else {
-        float4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {          // all shared-memory loads first, then the ALU work
+        for (int q = 0; q < 2; ++q) {
             if (ps.toff[q] < 0) continue;
-            v[q] = slots[q * nthr];
-            if (o.mask) v[q] = pk_mask4(v[q], slots[(ps.np + q) * nthr], o.mask_act);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (ps.toff[q] < 0) continue;
-            split_store(tile, ps.toff[q], lo_off, v[q]);
+            float4 v = slots[q * nthr];
+            if (o.mask) v = pk_mask4(v, slots[(2 + q) * nthr], o.mask_act);
+            split_store(tile, ps.toff[q], lo_off, v);
         }
     }
 }
@@ -515,7 +510,7 @@ __device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, float4 b4
     }
 }
 
-template <int EPI, bool BSTREAM>
+template <int EPI>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
@@ -538,18 +533,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const int64_t kb_end = (kb_beg + p.kb_per_split < p.nkb) ? kb_beg + p.kb_per_split : p.nkb;
     const int nkb = (int)(kb_end - kb_beg);
     const bool split = gridDim.z > 1;
-    const bool a_stream = p.sa.mode != OP_PACKED;
-    constexpr bool b_stream = BSTREAM;
+    const bool a_stream = p.sa.mode != OP_PACKED, b_stream = p.sb.mode != OP_PACKED;
 
     if (tid == 0) {
         // a stage is full after all converter warps arrived (streamed operand) or after the TMA
         // transaction armed by the producer completed (packed operand)
         for (int s = 0; s < SA; ++s) {
-            mbar_init(&a_full[s], a_stream ? PK_CONV_WARPS / p.G : 1);
+            mbar_init(&a_full[s], a_stream ? PK_CONV_WARPS : 1);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < SB; ++s) {
-            mbar_init(&b_full[s], b_stream ? PK_CONV_WARPS / p.G : 1);
+            mbar_init(&b_full[s], b_stream ? PK_CONV_WARPS : 1);
             mbar_init(&b_empty[s], 1);
         }
         mbar_init(accum_bar, 1);
@@ -626,53 +620,46 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         // ------------------------------ converters (16 warps), then epilogue ----------------
         if (a_stream || b_stream) {
             const int ct = tid - 64;
-            // G converter groups work on alternating stages (group g: stages g, g+G, ...), so the fixed
-            // latencies of a stage (cp.async wait, slot wait, proxy fence, arrive) of one group overlap
-            // the conversion work of the other
-            const int G = p.G;
-            const int grp = (G == 2) ? (ct >> 8) : 0;
-            const int gt = (G == 2) ? (ct & 255) : ct;
-            const int nthr = PK_CONV_THREADS / G;
+            unsigned char* raw = smem_raw + p.off_raw;
             const uint32_t raw_depth = p.raw_a_bytes + p.raw_b_bytes;
-            unsigned char* raw = smem_raw + p.off_raw + (size_t)grp * p.depth * raw_depth;
             const int64_t a_row0 = mblk * (int64_t)MT * PK_AR, b_row0 = nblk * (int64_t)BN;
+            // operand descriptors in REGISTERS for the whole stage loop: read from the kernel-parameter
+            // bank they were re-fetched (LDCU) before every dependent branch, the top stall of run 18
+            StreamOp oa = p.sa, ob = p.sb;
+            pin_op(oa);
+            pin_op(ob);
             PieceSet pa, pb;
-            const int64_t k_first = (kb_beg + grp) * PK_KB;
-            if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, k_first, gt, nthr, 0, PK_KB * G, pa);
-            if (b_stream) piece_setup(p.sb, BN, BN, b_row0, k_first, gt, nthr, p.t0_b, PK_KB * G, pb);
-            int64_t krem_issue = g.K - k_first;          // K left at the stage being issued
-            int issued = grp, d_issue = 0;
+            if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, kb_beg * PK_KB, ct, 0, pa);
+            if (b_stream) piece_setup(p.sb, BN, BN, b_row0, kb_beg * PK_KB, ct, p.t0_b, pb);
+            int64_t krem_issue = g.K - kb_beg * PK_KB;    // K left at the stage being issued
+            int issued = 0, d_issue = 0;
             auto issue = [&]() {
                 if (issued < nkb) {
                     const int kr = krem_issue > 64 ? 64 : (int)krem_issue;
                     unsigned char* base = raw + (size_t)d_issue * raw_depth;
-                    if (a_stream) stream_issue(p.sa, pa, kr, reinterpret_cast<float4*>(base) + pa.tloc);
-                    if (b_stream) stream_issue(p.sb, pb, kr, reinterpret_cast<float4*>(base + p.raw_a_bytes) + pb.tloc);
+                    if (a_stream) stream_issue(oa, pa, kr, reinterpret_cast<float4*>(base) + pa.tloc);
+                    if (b_stream) stream_issue(ob, pb, kr, reinterpret_cast<float4*>(base + p.raw_a_bytes) + pb.tloc);
                 }
                 cp_async_commit();
-                issued += G;
-                krem_issue -= PK_KB * G;
+                ++issued;
+                krem_issue -= PK_KB;
                 if (++d_issue == p.depth) d_issue = 0;
             };
             for (int i = 0; i < p.depth; ++i) issue();
             int sa = 0, sb = 0, d = 0;
             uint32_t pha = 1, phb = 1;
-            if (grp == 1) {                               // second group starts at stage 1
-                if (++sa == SA) { sa = 0; pha ^= 1u; }
-                if (++sb == SB) { sb = 0; phb ^= 1u; }
-            }
-            for (int i = grp; i < nkb; i += G) {
+            for (int i = 0; i < nkb; ++i) {
                 if (p.depth == 3) cp_async_wait<2>();
                 else cp_async_wait<1>();
                 const unsigned char* base = raw + (size_t)d * raw_depth;
                 if (a_stream) {
                     mbar_wait(&a_empty[sa], pha);
-                    stream_convert(p.sa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)sa * a_stage),
+                    stream_convert(oa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)sa * a_stage),
                                    reinterpret_cast<const float4*>(base) + pa.tloc);
                 }
                 if (b_stream) {
                     mbar_wait(&b_empty[sb], phb);
-                    stream_convert(p.sb, pb, BN, reinterpret_cast<float*>(ringB + (size_t)sb * b_stage),
+                    stream_convert(ob, pb, BN, reinterpret_cast<float*>(ringB + (size_t)sb * b_stage),
                                    reinterpret_cast<const float4*>(base + p.raw_a_bytes) + pb.tloc);
                 }
                 fence_async_smem();                       // generic-proxy stores -> async proxy (tcgen05.mma)
@@ -681,10 +668,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                     if (a_stream) mbar_arrive(&a_full[sa]);
                     if (b_stream) mbar_arrive(&b_full[sb]);
                 }
-                for (int k = 0; k < G; ++k) {
-                    if (++sa == SA) { sa = 0; pha ^= 1u; }
-                    if (++sb == SB) { sb = 0; phb ^= 1u; }
-                }
+                if (++sa == SA) { sa = 0; pha ^= 1u; }
+                if (++sb == SB) { sb = 0; phb ^= 1u; }
                 if (++d == p.depth) d = 0;
                 issue();
             }
@@ -755,9 +740,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
 // configuration shared by the launcher and the scratch-size query
 // ---------------------------------------------------------------------------------------------
 struct PkConfig {
-    int BN, MT, SA, SB, depth, tmem_cols, G;
+    int BN, MT, SA, SB, depth, tmem_cols;
     int a_mode, b_mode, t0_b;
-    bool unsupported;            // a streamed operand whose mask has other strides than the operand
     uint32_t raw_a_bytes, raw_b_bytes;
     int64_t gm, gn, splits, nkb, kb_per_split;
     int64_t a_bytes, b_bytes;    // scratch for the packed operands (0 when streamed)
@@ -815,62 +799,47 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split) {
     c.b_mode = (stream_ok && c.b_bytes > kStreamThresholdBytes) ? stream_mode(g.B, g.sbn, g.sbk, g.bmask, g.sbmn, g.sbmk) : OP_PACKED;
     if (c.a_mode != OP_PACKED) c.a_bytes = 0;
     if (c.b_mode != OP_PACKED) c.b_bytes = 0;
-    c.unsupported = (c.a_mode != OP_PACKED && g.amask && (g.smm != g.sam || g.smk != g.sak)) ||
-                    (c.b_mode != OP_PACKED && g.bmask && (g.sbmn != g.sbn || g.sbmk != g.sbk));
-    // shared-memory plan: [A ring | B ring | raw cp.async slots (G groups x depth) | barriers]
+    // raw cp.async region of a streamed operand per depth: 16 KB of data (+16 KB for its mask):
+    // KVEC/SCALAR = 2 slots x 512 threads, TRANS = 4 slots x 256 threads, 16 bytes each
+    c.raw_a_bytes = c.a_mode == OP_PACKED ? 0u : (g.amask ? 32768u : 16384u);
+    c.raw_b_bytes = c.b_mode == OP_PACKED ? 0u : (g.bmask ? 32768u : 16384u);
+    c.t0_b = (c.a_mode == OP_TRANS && c.b_mode == OP_TRANS) ? 256 : 0;
+
+    // shared-memory plan: [A ring | B ring | raw cp.async slots | barriers]
     const int64_t a_stage = (int64_t)c.MT * PK_AR * 128, b_stage = (int64_t)c.BN * 128;
-    const int64_t budget = 232448 - 1024;                 // 227 KB opt-in maximum minus barriers / slack
+    const int64_t raw_per_depth = (int64_t)c.raw_a_bytes + c.raw_b_bytes;
+    const int64_t budget = 220 * 1024 - 512;
     const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;       // epilogue staging overlays the rings
     c.ok = false;
-    c.G = 1;
-    c.t0_b = 0;
-    c.raw_a_bytes = c.raw_b_bytes = 0;
-    if (c.a_mode == OP_PACKED && c.b_mode == OP_PACKED) {
+    if (raw_per_depth == 0) {
         int S = (int)(budget / (a_stage + b_stage));
         if (S > 6) S = 6;
+        while (S >= 2 && (int64_t)S * (a_stage + b_stage) < stg && S < 6) ++S;
         if (S >= 2) {
             c.SA = c.SB = S;
             c.depth = 0;
             c.ok = true;
         }
     } else {
-        // raw bytes of one stage of a streamed operand for a group of nthr threads
-        auto raw_bytes = [](int mode, int R, bool mask, int nthr) -> int64_t {
-            if (mode == OP_PACKED) return 0;
-            const int64_t np = (mode == OP_TRANS) ? 4 : (4 * R + nthr - 1) / nthr;
-            const int64_t thr = (mode == OP_TRANS) ? 256 : nthr;
-            return np * thr * 16 * (mask ? 2 : 1);
-        };
-        // {G, SA, SB, depth}: two converter groups need a third A (and streamed-B) slot
-        const int opts[7][4] = {{2, 3, 3, 2}, {2, 3, 2, 2}, {1, 3, 3, 3}, {1, 2, 3, 3}, {1, 2, 2, 3}, {1, 2, 2, 2}, {1, 2, 2, 2}};
-        for (int i = 0; i < 6 && !c.ok; ++i) {
-            const int G = opts[i][0];
-            if (G == 2 && c.b_mode != OP_PACKED && opts[i][2] < 3) continue;
-            const int nthr = PK_CONV_THREADS / G;
-            const int64_t ra = raw_bytes(c.a_mode, c.MT * PK_AR, g.amask != nullptr, nthr);
-            const int64_t rb = raw_bytes(c.b_mode, c.BN, g.bmask != nullptr, nthr);
-            const int64_t need = opts[i][1] * a_stage + opts[i][2] * b_stage + (int64_t)G * opts[i][3] * (ra + rb);
+        const int opts[5][3] = {{3, 4, 3}, {3, 3, 3}, {2, 3, 3}, {2, 2, 3}, {2, 2, 2}};
+        for (int i = 0; i < 5 && !c.ok; ++i) {
+            const int64_t need = opts[i][0] * a_stage + opts[i][1] * b_stage + opts[i][2] * raw_per_depth;
             if (need <= budget) {
-                c.G = G;
-                c.SA = opts[i][1];
-                c.SB = opts[i][2];
-                c.depth = opts[i][3];
-                c.raw_a_bytes = (uint32_t)ra;
-                c.raw_b_bytes = (uint32_t)rb;
-                c.t0_b = (G == 1 && c.a_mode == OP_TRANS && c.b_mode == OP_TRANS) ? 256 : 0;
+                c.SA = opts[i][0];
+                c.SB = opts[i][1];
+                c.depth = opts[i][2];
                 c.ok = true;
             }
         }
     }
-    const int64_t raw_total = (int64_t)c.G * c.depth * ((int64_t)c.raw_a_bytes + c.raw_b_bytes);
     if (c.ok) {
         int64_t rings = c.SA * a_stage + c.SB * b_stage;
         c.off_b = (uint32_t)(c.SA * a_stage);
         if (rings < stg) rings = stg;
         c.off_raw = (uint32_t)rings;
-        c.off_bar = (uint32_t)(rings + raw_total);
+        c.off_bar = (uint32_t)(rings + c.depth * raw_per_depth);
         c.smem = c.off_bar + (uint32_t)((2 * c.SA + 2 * c.SB + 1) * sizeof(uint64_t) + 16);
-        if (c.smem > 232448) c.ok = false;
+        if (c.smem > 225 * 1024) c.ok = false;
     }
     return c;
 }
@@ -927,7 +896,6 @@ extern "C" int ctr_set_scratch(void* ptr, int64_t bytes) {
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);
-    if (c.unsupported) return -3;    // caller falls back to the in-kernel-split engine (gemm_tc.cu)
     if (!c.ok) {
         ctr_set_error("launch_gemm_pk: tile does not fit shared memory");
         return -1;
@@ -978,33 +946,23 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     p.raw_a_bytes = c.raw_a_bytes;
     p.raw_b_bytes = c.raw_b_bytes;
     p.t0_b = c.t0_b;
-    p.G = c.G;
     const size_t smem = c.smem;
     static bool configured = false;
     if (!configured) {
-        const int max_smem = 232448;
-#define PK_SET_ATTR(E, BS) CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<E, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
-        PK_SET_ATTR(EPI_STORE, false); PK_SET_ATTR(EPI_STORE, true);
-        PK_SET_ATTR(EPI_BIAS_ACT, false); PK_SET_ATTR(EPI_BIAS_ACT, true);
-        PK_SET_ATTR(EPI_MUL_ACTGRAD, false); PK_SET_ATTR(EPI_MUL_ACTGRAD, true);
-        PK_SET_ATTR(EPI_CROSS, false); PK_SET_ATTR(EPI_CROSS, true);
-#undef PK_SET_ATTR
+        const int max_smem = 225 * 1024;
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
     dim3 grid((unsigned)c.gn, (unsigned)c.gm, (unsigned)c.splits);
-    const bool bs = c.b_mode != OP_PACKED;
-#define PK_LAUNCH(E)                                                                \
-    do {                                                                            \
-        if (bs) gemm_pk_kernel<E, true><<<grid, PK_THREADS, smem, st>>>(p);         \
-        else gemm_pk_kernel<E, false><<<grid, PK_THREADS, smem, st>>>(p);           \
-    } while (0)
     switch (g.epilogue) {
-        case EPI_BIAS_ACT: PK_LAUNCH(EPI_BIAS_ACT); break;
-        case EPI_MUL_ACTGRAD: PK_LAUNCH(EPI_MUL_ACTGRAD); break;
-        case EPI_CROSS: PK_LAUNCH(EPI_CROSS); break;
-        default: PK_LAUNCH(EPI_STORE); break;
+        case EPI_BIAS_ACT: gemm_pk_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_MUL_ACTGRAD: gemm_pk_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_CROSS: gemm_pk_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
+        default: gemm_pk_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
     }
-#undef PK_LAUNCH
     CTR_LAUNCH_OK("gemm_pk_kernel");
     return 0;
 }
