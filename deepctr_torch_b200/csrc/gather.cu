@@ -7,6 +7,8 @@
 //
 // Work decomposition: one warp per sample (grid-stride).  A row of D floats is moved by
 // LPR = D/4 lanes, each with one 128-bit load/store, so a warp moves 32/LPR rows per step.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -718,11 +720,23 @@ static int launch_scatter(ScatterArgs& a, bool rowwise, cudaStream_t st, bool fo
         (!a.blk || (a.ld_blk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.blk) & 15) == 0)) &&
         (!a.d_blk || (a.ld_dblk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.d_blk) & 15) == 0));
     const unsigned grid = sample_grid((a.B + 1) / 2, 8, 8);
-    const unsigned grid_vec = sample_grid((a.B + 1) / 2, 4, 12);
+    // samples per warp: 2 keeps more loads in flight per warp but needs 144 registers (18 % occupancy);
+    // 1 halves the register arrays.  CTR_SCATTER_SPW=1|2 selects (A/B profiling), default 2.
+    static int spw = 0;
+    if (spw == 0) {
+        const char* e = getenv("CTR_SCATTER_SPW");
+        spw = (e && e[0] == '1') ? 1 : 2;
+    }
+    const unsigned grid_vec = (spw == 1) ? sample_grid(a.B, 4, 16) : sample_grid((a.B + 1) / 2, 4, 12);
     if (lpr > 0 && aligned && !force_generic) {
 #define LAUNCH_SC(L)                                                                     \
-    if (rowwise) scatter_bwd_vec_kernel<L, true, 2><<<grid_vec, 128, 0, st>>>(a);        \
-    else scatter_bwd_vec_kernel<L, false, 2><<<grid_vec, 128, 0, st>>>(a);
+    if (spw == 1) {                                                                      \
+        if (rowwise) scatter_bwd_vec_kernel<L, true, 1><<<grid_vec, 128, 0, st>>>(a);    \
+        else scatter_bwd_vec_kernel<L, false, 1><<<grid_vec, 128, 0, st>>>(a);           \
+    } else {                                                                             \
+        if (rowwise) scatter_bwd_vec_kernel<L, true, 2><<<grid_vec, 128, 0, st>>>(a);    \
+        else scatter_bwd_vec_kernel<L, false, 2><<<grid_vec, 128, 0, st>>>(a);           \
+    }
         switch (lpr) {
             case 1: LAUNCH_SC(1) break;
             case 2: LAUNCH_SC(2) break;
