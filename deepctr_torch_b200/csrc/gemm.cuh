@@ -42,6 +42,9 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st);
 int64_t gemm_pk_scratch_bytes(int64_t M, int64_t N, int64_t K);
 bool gemm_pk_has_scratch(int64_t M, int64_t N, int64_t K);
+void* gemm_scratch_ptr(int64_t need_bytes);      // registered scratch if it holds need_bytes, else NULL
+int gemm_pack_operand(const float* P, int64_t s_row, int64_t s_k, int64_t n_rows, int64_t K, int R, int64_t nkb,
+                      float* out, cudaStream_t st);
 
 // out[n] = sum_m A[m*sam + n*san] * (mask ? act'(mask[m*smm + n*smn]) : 1) * (w ? w[m] : 1)
 int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, int64_t smm,

@@ -893,6 +893,21 @@ extern "C" int ctr_set_scratch(void* ptr, int64_t bytes) {
     return 0;
 }
 
+// helpers for the other tensor-core kernels (cin_tc.cu): the registered scratch and the weight packer
+void* gemm_scratch_ptr(int64_t need_bytes) {
+    const int dev = current_device();
+    return (g_scratch[dev] && g_scratch_bytes[dev] >= need_bytes) ? g_scratch[dev] : nullptr;
+}
+
+// pack P(row,k) (n_rows x K, any strides) into [hi | lo] K-major tiles of R rows x 16 k; out must hold
+// ceil(n_rows/R) * nkb * R * 128 bytes (nkb >= ceil(K/16) k blocks, the extra ones zero)
+int gemm_pack_operand(const float* P, int64_t s_row, int64_t s_k, int64_t n_rows, int64_t K, int R, int64_t nkb, float* out,
+                      cudaStream_t st) {
+    if (nkb < ceil_div64(K, PK_KB)) nkb = ceil_div64(K, PK_KB);
+    PackArgs pa{P, s_row, s_k, nullptr, 0, 0, 0, n_rows, K, R, ceil_div64(n_rows, R), nkb, out};
+    return launch_pack(pa, st);
+}
+
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);

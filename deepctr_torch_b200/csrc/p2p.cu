@@ -36,38 +36,65 @@ struct PushArgs {
     int32_t* err_flag;
 };
 
-// one thread per (field, unique row)
+// One block = one field x a chunk of PUSH_CHUNK unique rows.  The slot claim in the owner's receive
+// list is aggregated per block: positions inside the block come from shared-memory atomics, and ONE
+// remote atomicAdd per (block, owner) reserves the range — a remote atomic that returns a value is a
+// full NVLink round trip, and the first version issued one per row (3.4 M per step: 4.5 ms at G = 2).
+constexpr int PUSH_CHUNK = 1024;
+constexpr int PUSH_MAX_G = 16;
 __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
-    const int64_t total = (int64_t)(a.n_emb + a.n_lin) * a.B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = (int)(i / a.B);
-        const int64_t u = i - (int64_t)f * a.B;
-        const bool is_emb = f < a.n_emb;
-        const int pc = is_emb ? a.emb_plan_col[f] : a.lin_plan_col[f - a.n_emb];
-        if (u >= a.n_uniq[pc]) continue;
-        const int32_t id = a.uniq[(int64_t)pc * a.B + u];
-        const int owner = id % a.G;
-        const int32_t local = id / a.G;
-        const int32_t slot = atomicAdd(a.recv_count[owner] + f, 1);   // remote atomic over NVLink
-        if (slot >= a.cap) {
-            atomicOr(a.err_flag, 2);
-            continue;
-        }
-        a.recv_ids[owner][(int64_t)f * a.cap + slot] = local;
-        if (is_emb) {
-            const float* src = a.emb_rowgrad + f * a.emb_rg_stride + u * a.D;
-            float* dst = a.recv_emb_rows[owner] + ((int64_t)f * a.cap + slot) * a.D;
-            if ((a.D & 3) == 0) {
-                for (int d = 0; d < a.D; d += 4)
-                    *reinterpret_cast<float4*>(dst + d) = *reinterpret_cast<const float4*>(src + d);
-            } else {
-                for (int d = 0; d < a.D; ++d) dst[d] = src[d];
+    __shared__ int s_cnt[PUSH_MAX_G];
+    __shared__ int s_base[PUSH_MAX_G];
+    const int f = blockIdx.y;
+    const bool is_emb = f < a.n_emb;
+    const int pc = is_emb ? a.emb_plan_col[f] : a.lin_plan_col[f - a.n_emb];
+    const int64_t nu = a.n_uniq[pc];
+    for (int64_t u0 = (int64_t)blockIdx.x * PUSH_CHUNK; u0 < nu; u0 += (int64_t)gridDim.x * PUSH_CHUNK) {
+        if (threadIdx.x < PUSH_MAX_G) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int owner[PUSH_CHUNK / 256], pos[PUSH_CHUNK / 256];
+        int32_t local[PUSH_CHUNK / 256];
+#pragma unroll
+        for (int j = 0; j < PUSH_CHUNK / 256; ++j) {
+            const int64_t u = u0 + threadIdx.x + 256 * j;
+            owner[j] = -1;
+            if (u < nu) {
+                const int32_t id = a.uniq[(int64_t)pc * a.B + u];
+                owner[j] = id % a.G;
+                local[j] = id / a.G;
+                pos[j] = atomicAdd(&s_cnt[owner[j]], 1);
             }
-        } else {
-            const int fl = f - a.n_emb;
-            a.recv_lin_rows[owner][(int64_t)fl * a.cap + slot] = a.lin_rowgrad[fl * a.lin_rg_stride + u];
         }
+        __syncthreads();
+        if (threadIdx.x < a.G && s_cnt[threadIdx.x] > 0)
+            s_base[threadIdx.x] = atomicAdd(a.recv_count[threadIdx.x] + f, s_cnt[threadIdx.x]);   // remote, once per owner
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PUSH_CHUNK / 256; ++j) {
+            if (owner[j] < 0) continue;
+            const int64_t u = u0 + threadIdx.x + 256 * j;
+            const int o = owner[j];
+            const int64_t slot = (int64_t)s_base[o] + pos[j];
+            if (slot >= a.cap) {
+                atomicOr(a.err_flag, 2);
+                continue;
+            }
+            a.recv_ids[o][(int64_t)f * a.cap + slot] = local[j];
+            if (is_emb) {
+                const float* src = a.emb_rowgrad + f * a.emb_rg_stride + u * a.D;
+                float* dst = a.recv_emb_rows[o] + ((int64_t)f * a.cap + slot) * a.D;
+                if ((a.D & 3) == 0) {
+                    for (int d = 0; d < a.D; d += 4)
+                        *reinterpret_cast<float4*>(dst + d) = *reinterpret_cast<const float4*>(src + d);
+                } else {
+                    for (int d = 0; d < a.D; ++d) dst[d] = src[d];
+                }
+            } else {
+                const int fl = f - a.n_emb;
+                a.recv_lin_rows[o][(int64_t)fl * a.cap + slot] = a.lin_rowgrad[fl * a.lin_rg_stride + u];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -121,10 +148,13 @@ extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, 
     if (B == 0 || n_emb + n_lin == 0) return 0;
     PushArgs a{B, n_shards, n_uniq, uniq, n_emb, D, emb_rowgrad, emb_rowgrad_stride, emb_plan_col, n_lin,
                lin_rowgrad, lin_rowgrad_stride, lin_plan_col, recv_count, recv_ids, recv_emb_rows, recv_lin_rows, cap, err_flag};
-    int64_t blocks = ceil_div64((int64_t)(n_emb + n_lin) * B, 256);
-    const int64_t limit = (int64_t)ctr_sm_count() * 8;
-    if (blocks > limit) blocks = limit;
-    rowgrad_push_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
+    CTR_ARG(n_shards <= PUSH_MAX_G, "ctr_rowgrad_push: at most %d shards", PUSH_MAX_G);
+    int64_t bx = ceil_div64(B, PUSH_CHUNK);
+    const int64_t limit = ceil_div64((int64_t)ctr_sm_count() * 8, n_emb + n_lin);
+    if (bx > limit) bx = limit;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)(n_emb + n_lin));
+    rowgrad_push_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
     CTR_LAUNCH_OK("rowgrad_push_kernel");
     return 0;
 }

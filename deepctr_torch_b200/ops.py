@@ -70,6 +70,17 @@ def ensure_gemm_scratch(dev, B, K, N):
             _lib.call("ctr_set_scratch", _ptr(buf), buf.numel())
 
 
+def ensure_scratch_bytes(dev, need):
+    """Grow the registered scratch to at least `need` bytes (packed weights of the tensor-core kernels)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf = _scratch_buf.get(idx)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=dev)
+        _scratch_buf[idx] = buf
+        with torch.cuda.device(idx):
+            _lib.call("ctr_set_scratch", _ptr(buf), buf.numel())
+
+
 def act_code(name):
     if isinstance(name, str) and name.lower() in ACT_CODES:
         return ACT_CODES[name.lower()]
@@ -560,6 +571,8 @@ class _CIN(torch.autograd.Function):
             W = W if W.is_contiguous() else W.contiguous()
             b = params[2 * k + 1]
             Y = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+            # packed (hi, lo) copy of W for the TMA-fed forward: ceil(N/128) x 2*ceil(HM/32) tiles of 16 KB
+            ensure_scratch_bytes(dev, ((N + 127) // 128) * 2 * ((Hk * M + 31) // 32) * 16384 + 256)
             _lib.call("ctr_cin_layer_fwd", _ptr(xp), sxp, Hk, _ptr(E), E.stride(0), M, D, _ptr(W),
                       _ptr(b), N, dstart, act, _ptr(Y), _vp(out.data_ptr() + 4 * off), total, B,
                       _stream())
