@@ -83,6 +83,7 @@ __device__ __forceinline__ float act_grad_from_y(int act, float y) {
         case CTR_ACT_RELU: return y > 0.f ? 1.f : 0.f;
         case CTR_ACT_SIGMOID: return y * (1.f - y);
         case CTR_ACT_TANH: return 1.f - y * y;
+        case 100: return y;            // internal: plain multiply by the "mask" operand (GEMM prologue A(m,k) *= aux(m,k))
         default: return 1.f;
     }
 }

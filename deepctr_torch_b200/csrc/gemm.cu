@@ -132,6 +132,9 @@ sgemm_kernel(GemmArgs g, int64_t k_chunk) {
                 case EPI_MUL_ACTGRAD:
                     v *= act_grad_from_y(g.act, __ldg(g.aux + m * g.ldaux + n));
                     break;
+                case EPI_MUL:
+                    v *= __ldg(g.aux + m * g.ldaux + n);
+                    break;
                 case EPI_CROSS: {
                     const float u = v + __ldg(g.bias + n);
                     if (g.out2) g.out2[m * g.ldout2 + n] = u;

@@ -2,11 +2,14 @@
 #pragma once
 #include "common.cuh"
 
+constexpr int CTR_ACT_MULPRO = 100;    // prologue "activation" code: operand *= mask (no derivative involved)
+
 enum GemmEpilogue {
     EPI_STORE = 0,       // C = acc            (or C += acc when accumulate)
     EPI_BIAS_ACT = 1,    // C = act(acc + bias[n])
     EPI_MUL_ACTGRAD = 2, // C (+)= acc * act'(aux[m,n])     (dgrad feeding a previous activation)
     EPI_CROSS = 3,       // U = acc + bias[n]; C = aux[m,n] * U + aux2[m,n]   (CrossNet matrix)
+    EPI_MUL = 4,         // C (+)= acc * aux[m,n]               (bilinear interaction: (v_i W^T) (.) v_j)
 };
 
 struct GemmArgs {

@@ -483,6 +483,9 @@ __device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, float4 b4
         v = act4(g.act, make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w));
     } else if (EPI == EPI_MUL_ACTGRAD) {
         v = actgrad4(g.act, v, ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n)));
+    } else if (EPI == EPI_MUL) {
+        const float4 y = ld4_or_scalar(g.aux + m * g.ldaux + n, nvalid, row_vec_ok(g.aux, g.ldaux, n));
+        v = make_float4(v.x * y.x, v.y * y.y, v.z * y.z, v.w * y.w);
     } else if (EPI == EPI_CROSS) {
         const float4 u = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
         if (g.out2) st4_or_scalar(g.out2 + m * g.ldout2 + n, u, nvalid, row_vec_ok(g.out2, g.ldout2, n));
@@ -969,6 +972,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
     dim3 grid((unsigned)c.gn, (unsigned)c.gm, (unsigned)c.splits);
@@ -976,6 +980,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         case EPI_BIAS_ACT: gemm_pk_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
         case EPI_MUL_ACTGRAD: gemm_pk_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
         case EPI_CROSS: gemm_pk_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_MUL: gemm_pk_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p); break;
         default: gemm_pk_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
     }
     CTR_LAUNCH_OK("gemm_pk_kernel");

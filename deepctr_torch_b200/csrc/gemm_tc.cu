@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
                             case EPI_MUL_ACTGRAD:
                                 v *= act_grad_from_y(g.act, __ldg(g.aux + m * g.ldaux + n));
                                 break;
+                            case EPI_MUL:
+                                v *= __ldg(g.aux + m * g.ldaux + n);
+                                break;
                             case EPI_CROSS: {
                                 const float u = v + __ldg(g.bias + n);
                                 if (g.out2) g.out2[m * g.ldout2 + n] = u;

@@ -793,6 +793,7 @@ class _Bilinear(torch.autograd.Function):
         Wc = W.contiguous()
         P = F * (F - 1) // 2
         out = torch.empty(B, P, D, device=E.device, dtype=torch.float32)
+        ensure_scratch_bytes(E.device, 8 << 20)      # packed weight blocks of the GEMM formulation
         _lib.call("ctr_bilinear_fwd", _ptr(E), E.stride(0), F, D, _ptr(Wc), wsel, _ptr(out), P * D, B,
                   _stream())
         ctx.wsel = wsel

@@ -169,7 +169,8 @@ def _random_params(model, gen, std=0.05):
     ("DeepFM", dict(dnn_hidden_units=[256, 128]), 4096),
     ("xDeepFM", dict(dnn_hidden_units=[64, 64], cin_layer_size=[32, 32]), 1000),
     ("DCN", dict(cross_num=2, dnn_hidden_units=[128, 128]), 4096),
-    ("FiBiNET", dict(bilinear_type="interaction", dnn_hidden_units=[64, 64]), 777),
+    ("FiBiNET", dict(bilinear_type="interaction", dnn_hidden_units=[64, 64]), 1536),   # >= 1024: GEMM formulation
+    ("FiBiNET", dict(bilinear_type="interaction", dnn_hidden_units=[64, 64]), 777),    # per-pair kernels
 ])
 @pytest.mark.parametrize("zipf", [None, 1.05])
 def test_against_oracle_at_medium_size(model, extra, batch, zipf):
