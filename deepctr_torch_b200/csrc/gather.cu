@@ -58,10 +58,9 @@ struct GatherArgs {
 // rows.  A warp works on SPW samples at once: all their ids are fetched first, then all their row
 // loads (SPW x 4 x 128 bit per lane) are issued before the first store, so ~2 * F rows per warp are
 // in flight at the same time.
-template <int LPR, int SPW>
+template <int LPR, int SPW, int STEPS = 4>     // STEPS: row loads in flight per lane and sample
 __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     constexpr int RPW = 32 / LPR;  // rows per warp step
-    constexpr int STEPS = 4;       // row loads in flight per lane and sample
     constexpr int D = LPR * 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // stage slot metadata (table pointers, column, vocab) in shared memory
@@ -679,7 +678,18 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
         switch (lpr) {
             case 1: gather_fwd_vec_kernel<1, 2><<<grid, 256, smem, st>>>(a); break;
             case 2: gather_fwd_vec_kernel<2, 2><<<grid, 256, smem, st>>>(a); break;
-            case 4: gather_fwd_vec_kernel<4, 2><<<grid, 256, smem, st>>>(a); break;
+            case 4: {
+                // CTR_GATHER_VARIANT (diagnostic): fewer loads in flight per lane — peer (NVLink) rows were
+                // 3.7x slower than torch's one-load-per-thread gather with the default 2 samples x 4 steps
+                const char* e = getenv("CTR_GATHER_VARIANT");
+                const int var = e ? atoi(e) : 0;
+                if (var == 1) gather_fwd_vec_kernel<4, 1, 4><<<sample_grid(B, 8, 8), 256, smem, st>>>(a);
+                else if (var == 2) gather_fwd_vec_kernel<4, 1, 2><<<sample_grid(B, 8, 8), 256, smem, st>>>(a);
+                else if (var == 3) gather_fwd_vec_kernel<4, 1, 1><<<sample_grid(B, 8, 8), 256, smem, st>>>(a);
+                else if (var == 4) gather_fwd_vec_kernel<4, 1, 1><<<sample_grid(B, 8, 2), 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<4, 2><<<grid, 256, smem, st>>>(a);
+                break;
+            }
             case 8: gather_fwd_vec_kernel<8, 2><<<grid, 256, smem, st>>>(a); break;
             case 16: gather_fwd_vec_kernel<16, 2><<<grid, 256, smem, st>>>(a); break;
             default: gather_fwd_vec_kernel<32, 2><<<grid, 256, smem, st>>>(a); break;

@@ -44,7 +44,8 @@ def main():
 
     for name, idv in variants.items():
         X = torch.cat([idv.float(), dense], 1).contiguous()
-        for n_lin in (plan.n_lin, 0):
+        for n_lin, var in ((plan.n_lin, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (plan.n_lin, 3)):
+            os.environ["CTR_GATHER_VARIANT"] = str(var)
             dist.barrier()
             for _ in range(3):
                 run(X, n_lin)
@@ -55,7 +56,7 @@ def main():
                 run(X, n_lin)
             e1.record()
             torch.cuda.synchronize()
-            print("rank %d  %-20s n_lin=%2d : %.3f ms per gather" % (rank, name, n_lin, e0.elapsed_time(e1) / 5), flush=True)
+            print("rank %d  %-20s n_lin=%2d variant %d : %.3f ms per gather" % (rank, name, n_lin, var, e0.elapsed_time(e1) / 5), flush=True)
     # the same rows through torch's own gather on the peer-mapped table of field 0 (reference point)
     peer = (rank + 1) % world
     rows = plan.layout.emb_rows[0]
