@@ -31,6 +31,10 @@ SIGNATURES = {
     "ctr_p2p_export": [_P, _P],
     "ctr_p2p_open": [_P, _P],
     "ctr_p2p_close": [_P],
+    "ctr_shard_request": [_P, c_i64, c_i64, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, c_i64, _P, _P],
+    "ctr_shard_serve": [c_int, c_int, c_int, _P, _P, c_i64, _P, _P, _P, _P, _P],
+    "ctr_gather_fwd_exchanged": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P,
+                                 c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
     "ctr_rowgrad_push": [c_i64, c_int, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
                          _P, _P, _P, _P, c_i64, _P, _P],
     "ctr_lin_dense_wgrad": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P],

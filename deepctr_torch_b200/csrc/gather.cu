@@ -49,6 +49,11 @@ struct GatherArgs {
     float* fm;
     int32_t* err_flag;
     int n_shards;   // tables row-sharded: pointer [f*n_shards + id % n_shards], row id / n_shards
+    // exchanged mode (p2p.cu): rows of other shards were delivered into local response buffers;
+    // where[b, plan col] = -1 (row is local) or (owner << 26) | slot
+    const int32_t* where; int n_plan; int me;
+    const int32_t* emb_plan_col; const int32_t* lin_plan_col;
+    const float* const* resp_emb; const float* const* resp_lin;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -68,10 +73,12 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     const int G = a.n_shards;
     int32_t* s_col = reinterpret_cast<int32_t*>(s_tab + a.n_emb * G);
     int32_t* s_voc = s_col + a.n_emb;
+    int32_t* s_pc = s_voc + a.n_emb;            // plan column of each embedding slot (exchanged mode)
     for (int i = threadIdx.x; i < a.n_emb * G; i += blockDim.x) s_tab[i] = a.emb_tables[i];
     for (int i = threadIdx.x; i < a.n_emb; i += blockDim.x) {
         s_col[i] = a.emb_cols[i];
         s_voc[i] = a.emb_vocab[i];
+        s_pc[i] = a.where ? a.emb_plan_col[i] : 0;
     }
     __syncthreads();
 
@@ -111,12 +118,28 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                     const int f = f0 + s * RPW + rslot;
                     const int fc = f < a.n_emb ? f : a.n_emb - 1;
                     const int id = decode_id(xr[t][s], s_voc[fc], a.err_flag);
-                    const float* tab = (G == 1) ? s_tab[fc] : s_tab[fc * G + id % G];
-                    const int row = (G == 1) ? id : id / G;
-                    // peer (NVLink-mapped) rows: plain coherent loads — the non-coherent .nc path the local
-                    // tables use was 25x slower on peer addresses (2.6 ms vs 0.1 ms per step at G = 2)
-                    v[t][s] = (G == 1) ? ld_stream4(tab + (size_t)row * D + sub * 4)
-                                       : *reinterpret_cast<const float4*>(tab + (size_t)row * D + sub * 4);
+                    const float* tab;
+                    int row;
+                    if (G == 1) {
+                        tab = s_tab[fc];
+                        row = id;
+                    } else if (a.where) {
+                        const int64_t bc2 = (bb + t < a.B) ? bb + t : a.B - 1;
+                        const int w = __ldg(a.where + bc2 * a.n_plan + s_pc[fc]);
+                        if (w < 0) {
+                            tab = s_tab[fc * G + a.me];
+                            row = id / G;
+                        } else {                               // delivered by the owner into a LOCAL buffer
+                            tab = a.resp_emb[w >> 26];
+                            row = w & ((1 << 26) - 1);
+                        }
+                    } else {
+                        tab = s_tab[fc * G + id % G];
+                        row = id / G;
+                    }
+                    // direct peer (NVLink-mapped) rows: plain coherent loads; everything local streams past L1
+                    v[t][s] = (G == 1 || a.where) ? ld_stream4(tab + (size_t)row * D + sub * 4)
+                                                  : *reinterpret_cast<const float4*>(tab + (size_t)row * D + sub * 4);
                 }
             }
 #pragma unroll
@@ -159,7 +182,14 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
             float lp = 0.f;
             for (int f = lane; f < a.n_lin; f += 32) {
                 const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
-                lp += (G == 1) ? __ldg(a.lin_tables[f] + id) : a.lin_tables[f * G + id % G][id / G];
+                if (G == 1) {
+                    lp += __ldg(a.lin_tables[f] + id);
+                } else if (a.where) {
+                    const int w = __ldg(a.where + b * a.n_plan + a.lin_plan_col[f]);
+                    lp += (w < 0) ? __ldg(a.lin_tables[f * G + a.me] + id / G) : __ldg(a.resp_lin[w >> 26] + (w & ((1 << 26) - 1)));
+                } else {
+                    lp += a.lin_tables[f * G + id % G][id / G];
+                }
             }
             for (int k = lane; k < a.n_lin_dense; k += 32)
                 lp += __ldg(xrow + a.lin_dense_cols[k]) * __ldg(a.lin_dense_w + k);
@@ -648,14 +678,16 @@ unsigned sample_grid(int64_t B, int warps_per_block, int blocks_per_sm) {
 // =============================================================================================
 // C ABI
 // =============================================================================================
-extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+static int gather_fwd_impl(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
                               const float* const* emb_tables, const int32_t* emb_cols,
                               const int32_t* emb_vocab, int n_lin, const float* const* lin_tables,
                               const int32_t* lin_cols, const int32_t* lin_vocab, int n_dense,
                               const int32_t* dense_cols, int n_lin_dense,
                               const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
                               int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
-                              int n_shards, void* stream) {
+                              int n_shards, void* stream, const int32_t* where, int n_plan, int me,
+                              const int32_t* emb_plan_col, const int32_t* lin_plan_col,
+                              const float* const* resp_emb, const float* const* resp_lin) {
     CTR_ARG(X && B >= 0 && ldx >= 0, "ctr_gather_fwd: X/B/ldx invalid");
     CTR_ARG(n_shards >= 1, "ctr_gather_fwd: n_shards must be >= 1");
     CTR_ARG(n_emb >= 0 && n_lin >= 0 && n_dense >= 0 && n_lin_dense >= 0, "ctr_gather_fwd: negative count");
@@ -667,14 +699,18 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
     if (B == 0) return 0;
     GatherArgs a{X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols,
                  lin_vocab, n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk,
-                 lin, fm, err_flag, n_shards};
+                 lin, fm, err_flag, n_shards, where, n_plan, me, emb_plan_col, lin_plan_col, resp_emb, resp_lin};
     cudaStream_t st = as_stream(stream);
     const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
     const bool vec_ok = lpr > 0 && n_emb * n_shards <= kMaxSmemSlots &&
                         (!blk || ((ld_blk % 4 == 0) && ((reinterpret_cast<uintptr_t>(blk) & 15) == 0)));
     const unsigned grid = sample_grid((B + 1) / 2, 8, 8);
+    if (where && !vec_ok) {
+        ctr_set_error("ctr_gather_fwd_exchanged: needs the vector path (D %% 4 == 0, aligned block)");
+        return -2;
+    }
     if (vec_ok) {
-        const size_t smem = (size_t)n_emb * n_shards * sizeof(void*) + (size_t)n_emb * 8;
+        const size_t smem = (size_t)n_emb * n_shards * sizeof(void*) + (size_t)n_emb * 12;
         switch (lpr) {
             case 1: gather_fwd_vec_kernel<1, 2><<<grid, 256, smem, st>>>(a); break;
             case 2: gather_fwd_vec_kernel<2, 2><<<grid, 256, smem, st>>>(a); break;
@@ -709,6 +745,37 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
         }
     }
     return 0;
+}
+
+extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+                              const float* const* emb_tables, const int32_t* emb_cols,
+                              const int32_t* emb_vocab, int n_lin, const float* const* lin_tables,
+                              const int32_t* lin_cols, const int32_t* lin_vocab, int n_dense,
+                              const int32_t* dense_cols, int n_lin_dense,
+                              const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
+                              int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
+                              int n_shards, void* stream) {
+    return gather_fwd_impl(X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols, lin_vocab,
+                           n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk, lin, fm, err_flag,
+                           n_shards, stream, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ctr_gather_fwd_exchanged(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+                                        const float* const* emb_tables, const int32_t* emb_cols,
+                                        const int32_t* emb_vocab, int n_lin, const float* const* lin_tables,
+                                        const int32_t* lin_cols, const int32_t* lin_vocab, int n_dense,
+                                        const int32_t* dense_cols, int n_lin_dense,
+                                        const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
+                                        int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
+                                        int n_shards, int rank, const int32_t* where, int n_plan,
+                                        const int32_t* emb_plan_col, const int32_t* lin_plan_col,
+                                        const float* const* resp_emb, const float* const* resp_lin, void* stream) {
+    CTR_ARG(where && n_plan > 0 && rank >= 0 && rank < n_shards, "ctr_gather_fwd_exchanged: bad exchange arguments");
+    CTR_ARG((n_emb == 0 || (emb_plan_col && resp_emb)) && (n_lin == 0 || (lin_plan_col && resp_lin)),
+            "ctr_gather_fwd_exchanged: plan columns / response buffers missing");
+    return gather_fwd_impl(X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols, lin_vocab,
+                           n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk, lin, fm, err_flag,
+                           n_shards, stream, where, n_plan, rank, emb_plan_col, lin_plan_col, resp_emb, resp_lin);
 }
 
 extern "C" int ctr_fm_fwd(const float* blk, int64_t ld, int64_t B, int F, int D, float* fm,

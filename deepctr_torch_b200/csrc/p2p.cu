@@ -98,6 +98,129 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Forward exchange of cross-shard rows ("all-to-all" over NVLink peer memory, owner computes).
+// Random 64-byte loads out of a peer's 2.5 GB table arena ran at 570 rows/us (profiles/, run 24:
+// 19x below the NVLink bandwidth, independent of the loads in flight), so rows are not fetched
+// remotely.  Instead:
+//   shard_request_kernel : every (sample, id column) whose row lives on another rank appends
+//                          (column, local row) to that owner's inbox (remote 8-byte stores; the slot
+//                          comes from a LOCAL counter — only this rank writes its slice of the inbox)
+//                          and remembers (owner, slot) in where[b, c]; local ids get where = -1.
+//   [barrier]
+//   shard_serve_kernel   : the owner gathers the requested rows from its LOCAL tables and streams them
+//                          into the requester's response buffer (contiguous remote 128-bit stores).
+//   [barrier]
+//   gather (gather.cu)   : reads local rows from the tables and remote rows from its response buffer.
+// ---------------------------------------------------------------------------------------------
+struct RequestArgs {
+    const float* X; int64_t ldx; int64_t B;
+    int n_cols; const int32_t* cols; const int32_t* vocab;     // distinct id columns (the unique-plan columns)
+    int G, me;
+    int32_t* cnt_to;                 // [G] local counters: requests issued to each owner this step
+    int32_t* const* inbox_req;       // [G] owner o's request list for THIS rank (peer pointer): int2 (col, local row)
+    int32_t* where;                  // [B, n_cols]
+    int64_t cap;
+    int32_t* err_flag;
+};
+
+constexpr int REQ_CHUNK = 1024;
+__global__ void __launch_bounds__(256) shard_request_kernel(RequestArgs a) {
+    __shared__ int s_cnt[PUSH_MAX_G];
+    __shared__ int s_base[PUSH_MAX_G];
+    const int c = blockIdx.y;
+    const int col = a.cols[c], vocab = a.vocab[c];
+    for (int64_t b0 = (int64_t)blockIdx.x * REQ_CHUNK; b0 < a.B; b0 += (int64_t)gridDim.x * REQ_CHUNK) {
+        if (threadIdx.x < PUSH_MAX_G) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int owner[REQ_CHUNK / 256], pos[REQ_CHUNK / 256];
+        int32_t local[REQ_CHUNK / 256];
+#pragma unroll
+        for (int j = 0; j < REQ_CHUNK / 256; ++j) {
+            const int64_t b = b0 + threadIdx.x + 256 * j;
+            owner[j] = -1;
+            if (b < a.B) {
+                int id = __float2int_rz(__ldg(a.X + b * a.ldx + col));
+                if ((unsigned)id >= (unsigned)vocab) {
+                    atomicOr(a.err_flag, 1);
+                    id = 0;
+                }
+                const int o = id % a.G;
+                local[j] = id / a.G;
+                if (o == a.me) {
+                    a.where[b * a.n_cols + c] = -1;
+                } else {
+                    owner[j] = o;
+                    pos[j] = atomicAdd(&s_cnt[o], 1);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < a.G && s_cnt[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(a.cnt_to + threadIdx.x, s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < REQ_CHUNK / 256; ++j) {
+            if (owner[j] < 0) continue;
+            const int64_t b = b0 + threadIdx.x + 256 * j;
+            const int o = owner[j];
+            const int64_t slot = (int64_t)s_base[o] + pos[j];
+            if (slot >= a.cap) {
+                atomicOr(a.err_flag, 2);
+                a.where[b * a.n_cols + c] = -1;
+                continue;
+            }
+            reinterpret_cast<int2*>(a.inbox_req[o])[slot] = make_int2(c, local[j]);     // remote 8-byte store
+            a.where[b * a.n_cols + c] = (o << 26) | (int)slot;
+        }
+        __syncthreads();
+    }
+}
+
+// publish the request counts to the owners' inboxes (after shard_request_kernel): inbox_cnt[o][me] = cnt_to[o]
+__global__ void shard_publish_kernel(const int32_t* cnt_to, int32_t* const* inbox_cnt, int G, int me) {
+    const int o = threadIdx.x;
+    if (o < G && o != me) inbox_cnt[o][me] = cnt_to[o];
+}
+
+struct ServeArgs {
+    int G, me, D;
+    const int32_t* req_cnt;              // [G] requests received from each rank
+    const int32_t* req;                  // [G][cap] int2 (col, local row)
+    int64_t cap;
+    const float* const* emb_of_col;      // [n_cols] LOCAL table of the column (or NULL)
+    const float* const* lin_of_col;      // [n_cols]
+    float* const* resp_emb;              // [G] requester q's response rows for THIS owner (peer pointer) [cap, D]
+    float* const* resp_lin;              // [G] [cap]
+};
+
+// one group of D/4 lanes per request: 128-bit local row load -> 128-bit remote store (consecutive
+// requests are consecutive rows of the response buffer: a warp writes 512 contiguous bytes at D = 16)
+__global__ void __launch_bounds__(256) shard_serve_kernel(ServeArgs a) {
+    const int q = blockIdx.y;
+    if (q == a.me) return;
+    const int n = a.req_cnt[q];
+    const int lpr = a.D >> 2;                                  // lanes per row (D % 4 == 0, D/4 <= 32 checked on the host)
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / lpr;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr;
+    const int sub = threadIdx.x % lpr;
+    const int2* req = reinterpret_cast<const int2*>(a.req) + (int64_t)q * a.cap;
+    float* oemb = a.resp_emb[q];
+    float* olin = a.resp_lin[q];
+    for (int64_t k = gid; k < n; k += groups) {
+        const int2 r = req[k];
+        const float* tab = a.emb_of_col[r.x];
+        if (tab) {
+            const float4 v = ld_stream4(tab + (size_t)r.y * a.D + sub * 4);
+            *reinterpret_cast<float4*>(oemb + k * a.D + sub * 4) = v;
+        }
+        if (sub == 0) {
+            const float* lt = a.lin_of_col[r.x];
+            if (lt) olin[k] = __ldg(lt + r.y);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int ctr_p2p_alloc(int64_t bytes, void** ptr) {
@@ -156,5 +279,46 @@ extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, 
     dim3 grid((unsigned)bx, (unsigned)(n_emb + n_lin));
     rowgrad_push_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
     CTR_LAUNCH_OK("rowgrad_push_kernel");
+    return 0;
+}
+
+extern "C" int ctr_shard_request(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
+                                 const int32_t* vocab, int n_shards, int rank, int32_t* cnt_to,
+                                 int32_t* const* inbox_req, int32_t* const* inbox_cnt, int32_t* where,
+                                 int64_t cap, int32_t* err_flag, void* stream) {
+    CTR_ARG(X && cols && vocab && cnt_to && inbox_req && inbox_cnt && where && err_flag, "ctr_shard_request: null argument");
+    CTR_ARG(n_cols > 0 && B >= 0 && n_shards >= 1 && n_shards <= PUSH_MAX_G && rank >= 0 && rank < n_shards && cap > 0 &&
+                cap < (1 << 26),
+            "ctr_shard_request: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    CTR_CUDA(cudaMemsetAsync(cnt_to, 0, sizeof(int32_t) * n_shards, st));
+    if (B > 0) {
+        RequestArgs a{X, ldx, B, n_cols, cols, vocab, n_shards, rank, cnt_to, inbox_req, where, cap, err_flag};
+        int64_t bx = ceil_div64(B, REQ_CHUNK);
+        const int64_t limit = ceil_div64((int64_t)ctr_sm_count() * 8, n_cols);
+        if (bx > limit) bx = limit;
+        if (bx < 1) bx = 1;
+        dim3 grid((unsigned)bx, (unsigned)n_cols);
+        shard_request_kernel<<<grid, 256, 0, st>>>(a);
+        CTR_LAUNCH_OK("shard_request_kernel");
+    }
+    shard_publish_kernel<<<1, 32, 0, st>>>(cnt_to, inbox_cnt, n_shards, rank);
+    CTR_LAUNCH_OK("shard_publish_kernel");
+    return 0;
+}
+
+extern "C" int ctr_shard_serve(int n_shards, int rank, int D, const int32_t* req_cnt, const int32_t* req, int64_t cap,
+                               const float* const* emb_of_col, const float* const* lin_of_col,
+                               float* const* resp_emb, float* const* resp_lin, void* stream) {
+    CTR_ARG(req_cnt && req && emb_of_col && lin_of_col && resp_emb && resp_lin, "ctr_shard_serve: null argument");
+    CTR_ARG(n_shards >= 1 && n_shards <= PUSH_MAX_G && rank >= 0 && rank < n_shards && cap > 0, "ctr_shard_serve: bad sizes");
+    CTR_ARG(D > 0 && D % 4 == 0 && D / 4 <= 32 && 256 % (D / 4) == 0, "ctr_shard_serve: embedding dim %d unsupported", D);
+    if (n_shards == 1) return 0;
+    ServeArgs a{n_shards, rank, D, req_cnt, req, cap, emb_of_col, lin_of_col, resp_emb, resp_lin};
+    int64_t bx = (int64_t)ctr_sm_count() * 8 / n_shards;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)n_shards);
+    shard_serve_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+    CTR_LAUNCH_OK("shard_serve_kernel");
     return 0;
 }

@@ -178,13 +178,25 @@ class _FusedInput(torch.autograd.Function):
         lin =torch.empty(B, device=dev, dtype=torch.float32)
         fm = torch.empty(B, device=dev, dtype=torch.float32) if want_fm else None
         n_emb = plan.n_emb if (want_blk or want_fm) else 0
-        _lib.call("ctr_gather_fwd", _ptr(X), X.stride(0), B,
-                  n_emb, plan.D, _ptr(emb_ptrs), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
-                  plan.n_lin, _ptr(lin_ptrs), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
-                  plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
-                  plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
-                  _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
-                  plan.n_shards, _stream())
+        if plan.n_shards > 1 and getattr(plan, "exchange", False) and B > 0:
+            # rows of other shards: requests -> owners gather locally -> contiguous delivery (sharded.py)
+            where = plan.exchange_rows(X, B)
+            _lib.call("ctr_gather_fwd_exchanged", _ptr(X), X.stride(0), B,
+                      n_emb, plan.D, _ptr(emb_ptrs), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
+                      plan.n_lin, _ptr(lin_ptrs), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
+                      plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
+                      plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
+                      _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
+                      plan.n_shards, plan.rank, _ptr(where), len(plan.plan_cols_host), _ptr(plan.emb_plan_col),
+                      _ptr(plan.lin_plan_col), _ptr(plan.x_resp_emb_local), _ptr(plan.x_resp_lin_local), _stream())
+        else:
+            _lib.call("ctr_gather_fwd", _ptr(X), X.stride(0), B,
+                      n_emb, plan.D, _ptr(emb_ptrs), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
+                      plan.n_lin, _ptr(lin_ptrs), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
+                      plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
+                      plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
+                      _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
+                      plan.n_shards, _stream())
         ctx.plan_event = None
         if grad_mode in ("rowwise", "sharded") and torch.is_grad_enabled() and B > 0:
             # the duplicate-free plan of the backward depends only on X: build it now on a side stream

@@ -57,7 +57,7 @@ def unshard_rows(shards, vocab):
 class ArenaLayout:
     """Identical on every rank: byte offsets of table shards and receive lists inside the arena."""
 
-    def __init__(self, emb_vocabs, lin_vocabs, dim, world, batch, align=256):
+    def __init__(self, emb_vocabs, lin_vocabs, dim, world, batch, align=256, n_id_cols=None):
         self.world, self.D = world, dim
         self.n_emb, self.n_lin = len(emb_vocabs), len(lin_vocabs)
         self.cap = batch * world                       # worst case: every rank sends `batch` rows
@@ -79,6 +79,14 @@ class ArenaLayout:
             self.recv.append({"count": take(max(nf, 1) * 4), "ids": take(max(nf, 1) * self.cap * 4),
                               "emb": take(max(self.n_emb, 1) * self.cap * dim * 4),
                               "lin": take(max(self.n_lin, 1) * self.cap * 4)})
+        # forward exchange (ctr_shard_request / ctr_shard_serve): request lists and response rows, one slice
+        # per peer.  Capacity per peer: every id of the batch for G <= 2, twice the uniform share beyond
+        # (overflow raises through the error flag rather than corrupting memory)
+        n_cols = n_id_cols if n_id_cols is not None else max(self.n_emb, self.n_lin, 1)
+        full = batch * n_cols
+        self.xcap = full if world <= 2 else min(full, 2 * ((full + world - 1) // world))
+        self.x = {"req_cnt": take(world * 4), "req": take(world * self.xcap * 8),
+                  "resp_emb": take(world * self.xcap * max(dim, 1) * 4), "resp_lin": take(world * self.xcap * 4)}
         self.nbytes = cursor
 
 
@@ -190,6 +198,59 @@ class ShardedPlan(ops.GatherPlan):
             self.recv_ptrs.append({k: torch.tensor([arena.peer_ptr[s] + r[k] for s in range(world)], **i64)
                                    for k in ("count", "ids", "emb", "lin")})
         self.step_parity = 0
+        self._setup_exchange(arena, layout, rank, world)
+
+    def _setup_exchange(self, arena, layout, rank, world):
+        """Pointer tables of the forward row exchange; disabled (direct peer loads) when an id column feeds
+        more than one embedding or linear slot, or with CTR_SHARD_EXCHANGE=0."""
+        import os
+        dev = self.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        n_cols = len(self.plan_cols_host)
+        emb_of, lin_of = [0] * n_cols, [0] * n_cols
+        ok = os.environ.get("CTR_SHARD_EXCHANGE", "1") != "0" and self.D % 4 == 0
+        for f, pc in enumerate(self.emb_plan_col.tolist()):
+            ok = ok and emb_of[pc] == 0
+            emb_of[pc] = arena.peer_ptr[rank] + layout.emb_off[f]
+        for f, pc in enumerate(self.lin_plan_col.tolist()):
+            ok = ok and lin_of[pc] == 0
+            lin_of[pc] = arena.peer_ptr[rank] + layout.lin_off[f]
+        self.exchange = bool(ok)
+        if not self.exchange:
+            return
+        x, cap, D = layout.x, layout.xcap, max(layout.D, 1)
+        me = arena.peer_ptr[rank]
+        self.x_cap = cap
+        self.x_emb_of_col = torch.tensor(emb_of, **i64)
+        self.x_lin_of_col = torch.tensor(lin_of, **i64)
+        self.x_cnt_to = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.x_inbox_req = torch.tensor([arena.peer_ptr[o] + x["req"] + rank * cap * 8 for o in range(world)], **i64)
+        self.x_inbox_cnt = torch.tensor([arena.peer_ptr[o] + x["req_cnt"] for o in range(world)], **i64)
+        self.x_req = me + x["req"]
+        self.x_req_cnt = me + x["req_cnt"]
+        self.x_resp_emb_remote = torch.tensor([arena.peer_ptr[q] + x["resp_emb"] + rank * cap * D * 4 for q in range(world)], **i64)
+        self.x_resp_lin_remote = torch.tensor([arena.peer_ptr[q] + x["resp_lin"] + rank * cap * 4 for q in range(world)], **i64)
+        self.x_resp_emb_local = torch.tensor([me + x["resp_emb"] + o * cap * D * 4 for o in range(world)], **i64)
+        self.x_resp_lin_local = torch.tensor([me + x["resp_lin"] + o * cap * 4 for o in range(world)], **i64)
+        self.x_token = torch.zeros(1, device=dev)
+        self._x_where = {}
+
+    def exchange_rows(self, X, B, group=None):
+        """Requests -> barrier -> owners serve -> barrier; returns where[B, n_cols] for the gather."""
+        import ctypes
+        where = self._x_where.get(B)
+        if where is None:
+            where = torch.empty(B, len(self.plan_cols_host), dtype=torch.int32, device=self.device)
+            self._x_where = {B: where}
+        _lib.call("ctr_shard_request", ops._ptr(X), X.stride(0), B, len(self.plan_cols_host), ops._ptr(self.plan_cols),
+                  ops._ptr(self.plan_vocab), self.world, self.rank, ops._ptr(self.x_cnt_to), ops._ptr(self.x_inbox_req),
+                  ops._ptr(self.x_inbox_cnt), ops._ptr(where), self.x_cap, ops._ptr(self.err_flag), ops._stream())
+        dist.all_reduce(self.x_token, group=group)        # every request list is complete
+        _lib.call("ctr_shard_serve", self.world, self.rank, self.D, ctypes.c_void_p(self.x_req_cnt), ctypes.c_void_p(self.x_req),
+                  self.x_cap, ops._ptr(self.x_emb_of_col), ops._ptr(self.x_lin_of_col), ops._ptr(self.x_resp_emb_remote),
+                  ops._ptr(self.x_resp_lin_remote), ops._stream())
+        dist.all_reduce(self.x_token, group=group)        # every response buffer is complete
+        return where
 
     def table_ptrs(self):
         return self._emb_ptrs, self._lin_ptrs
@@ -288,7 +349,9 @@ def attach_shards(model, logical_cfg, rank, world, batch, group=None):
     emb_vocab = [logical[c.name] for c in sparse]
     lin_vocab = [logical[c.name] for c in lsparse]
     D = sparse[0].embedding_dim if sparse else 1
-    layout = ArenaLayout(emb_vocab, lin_vocab, D, world, batch)
+    fidx = model.feature_index
+    n_id_cols = len(set([fidx[c.name][0] for c in sparse] + [fidx[c.name][0] for c in lsparse]))
+    layout = ArenaLayout(emb_vocab, lin_vocab, D, world, batch, n_id_cols=n_id_cols)
     arena = P2PArena(layout.nbytes, dev, group)
     with torch.no_grad():
         for f, c in enumerate(sparse):

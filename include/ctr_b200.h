@@ -142,6 +142,39 @@ int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32
                      float* const* recv_emb_rows, float* const* recv_lin_rows,
                      int64_t cap, int32_t* err_flag, void* stream);
 
+/* Forward exchange of cross-shard rows (csrc/p2p.cu; "owner computes" all-to-all over peer memory):
+ *   ctr_shard_request : per (sample, distinct id column): ids owned by this rank get where = -1, the others
+ *                       are appended as (column, local row) to the owner's inbox (peer pointers
+ *                       inbox_req[o] = owner o's request list for THIS rank, capacity cap entries of 8
+ *                       bytes) and where[b, c] = (owner << 26) | slot; finally the per-owner counts are
+ *                       published to inbox_cnt[o][rank].  cnt_to: [n_shards] local scratch counters.
+ *   -- all ranks synchronise (e.g. a tiny NCCL all-reduce) --
+ *   ctr_shard_serve   : for every requester q, gathers the req_cnt[q] requested rows from this rank's
+ *                       LOCAL tables (emb_of_col / lin_of_col: table of each id column or NULL) and streams
+ *                       them into resp_emb[q] / resp_lin[q] (peer pointers: q's response buffers for THIS
+ *                       owner, rows in request order).
+ *   -- all ranks synchronise --
+ *   ctr_gather_fwd_exchanged : ctr_gather_fwd whose rows of other shards come from the local response
+ *                       buffers (resp_emb[o], resp_lin[o]: this rank's buffers for owner o) via where;
+ *                       emb_plan_col / lin_plan_col: id-column index of each slot inside where. */
+int ctr_shard_request(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
+                      const int32_t* vocab, int n_shards, int rank, int32_t* cnt_to,
+                      int32_t* const* inbox_req, int32_t* const* inbox_cnt, int32_t* where,
+                      int64_t cap, int32_t* err_flag, void* stream);
+int ctr_shard_serve(int n_shards, int rank, int D, const int32_t* req_cnt, const int32_t* req, int64_t cap,
+                    const float* const* emb_of_col, const float* const* lin_of_col,
+                    float* const* resp_emb, float* const* resp_lin, void* stream);
+int ctr_gather_fwd_exchanged(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
+                             const float* const* emb_tables, const int32_t* emb_cols,
+                             const int32_t* emb_vocab, int n_lin, const float* const* lin_tables,
+                             const int32_t* lin_cols, const int32_t* lin_vocab, int n_dense,
+                             const int32_t* dense_cols, int n_lin_dense,
+                             const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
+                             int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
+                             int n_shards, int rank, const int32_t* where, int n_plan,
+                             const int32_t* emb_plan_col, const int32_t* lin_plan_col,
+                             const float* const* resp_emb, const float* const* resp_lin, void* stream);
+
 /* gradient of Linear's dense weight: dw[k] = sum_b g[b] * X[b, cols[k]]   (basemodel.py:88-90) */
 int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n, const int32_t* cols,
                         const float* g, float* dw, void* stream);
