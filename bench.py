@@ -300,13 +300,26 @@ def run_gpu_arm(args):
             model.sharded.clear_received(model.sharded.finish_step())
         return float(loss.item())          # device -> host read of the step's result
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     gstep = None
-    if use_graph:
+    if use_graph and world > 1:
+        # the sharded step (row exchange, push, NCCL all-reduce) as two alternating graphs; every rank
+        # must agree on whether the capture worked, otherwise the collectives would not match
+        ok = torch.ones(1, device=dev)
+        try:
+            gstep = model.make_graphed_step(B)
+        except Exception as ex:                      # noqa: BLE001
+            if rank == 0:
+                print("bench.py: sharded graph capture failed (%s); running eagerly" % str(ex)[:200], file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            use_graph, gstep = False, None
+    elif use_graph:
         # the whole fwd+loss+bwd step captured once as a CUDA graph and replayed (public API:
         # model.make_graphed_step); removes the ~30 per-launch host overheads from the step
         gstep = model.make_graphed_step(B)
-
+    if use_graph:
         def step_resident(i):      # noqa: F811
             X, y = dev_batches[i % N_ROTATE]
             return gstep(X, y)
@@ -365,6 +378,8 @@ def run_gpu_arm(args):
         if world > 1:
             model.sharded.clear_received(model.sharded.finish_step())
 
+    if gstep is not None and world > 1 and (gstep.replays & 1):
+        gstep(*dev_batches[0])          # leave the receive-list parity where the eager steps expect it
     _lib.enable_timing(True)
     for i in range(args.steps):
         step_eager(i)

@@ -60,3 +60,61 @@ class GraphedStep:
         self.graph.replay()
         self.replays += 1
         return self.loss
+
+
+
+class ShardedGraphedStep:
+    """The row-sharded multi-GPU step (forward with the row exchange, loss, backward with the row-gradient
+    push, dense-gradient all-reduce, receive-list bookkeeping) as TWO alternating CUDA graphs — one per
+    step parity, because the receive lists are double-buffered by parity.  NCCL collectives are captured
+    like any other kernel; all ranks must construct and call this object in lock-step."""
+
+    def __init__(self, model, batch_size, loss_fn=None, warmup=4):
+        if getattr(model, "sharded", None) is None:
+            raise RuntimeError("ShardedGraphedStep needs a model prepared by sharded.attach_shards")
+        self.model = model
+        dev = torch.device(model.device)
+        n_cols = max(e for _, e in model.feature_index.values())
+        self.X = torch.zeros(batch_size, n_cols, device=dev, dtype=torch.float32)
+        self.y = torch.zeros(batch_size, device=dev, dtype=torch.float32)
+        self.loss_fn = loss_fn or F.binary_cross_entropy
+        model.train()
+        if warmup % 2:
+            warmup += 1                                  # leave the parity where it started
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.check_ids()
+        from . import _lib
+        self.graphs, self.losses = [], []
+        self.first_parity = model._plan.step_parity
+        l0 = _lib.launch_count()
+        for _ in range(2):                               # parity p, then parity p ^ 1
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._body()
+            self.graphs.append(g)
+            self.losses.append(loss)
+        self.launches_per_replay = (_lib.launch_count() - l0) // 2
+        self.replays = 0
+
+    def _body(self):
+        m = self.model
+        m.zero_grad(set_to_none=True)
+        y_pred = m(self.X)
+        loss = self.loss_fn(y_pred.squeeze(1), self.y, reduction="sum")
+        loss.backward()
+        m.sharded.clear_received(m.sharded.finish_step())
+        return loss
+
+    def __call__(self, X, y):
+        self.X.copy_(X, non_blocking=True)
+        self.y.copy_(y.reshape(-1), non_blocking=True)
+        i = self.replays & 1
+        self.graphs[i].replay()
+        self.replays += 1
+        return self.losses[i]

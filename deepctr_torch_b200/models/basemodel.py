@@ -441,7 +441,9 @@ class BaseModel(nn.Module):
 
     def make_graphed_step(self, batch_size, loss_fn=None, with_reg=False):
         """One forward+loss+backward captured as a CUDA graph (see deepctr_torch_b200.graph)."""
-        from ..graph import GraphedStep
+        from ..graph import GraphedStep, ShardedGraphedStep
+        if getattr(self, "sharded", None) is not None:
+            return ShardedGraphedStep(self, batch_size, loss_fn=loss_fn)
         return GraphedStep(self, batch_size, loss_fn=loss_fn, with_reg=with_reg)
 
     def _in_multi_worker_mode(self):
