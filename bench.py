@@ -239,6 +239,22 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _finish_multi_gpu():
+    """Leave without tearing the NCCL communicator down: destroy_process_group() hangs when CUDA graphs
+    that captured collectives are still alive (observed on 2 GPUs, run 26).  All ranks meet once more,
+    flush, and exit."""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+    except Exception:                     # noqa: BLE001
+        pass
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from deepctr_torch_b200 import _lib
@@ -388,7 +404,7 @@ def run_gpu_arm(args):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _finish_multi_gpu()
         return
 
     total_B = B * world
@@ -460,7 +476,7 @@ def run_gpu_arm(args):
                                           "%d threads; os.cpu_count()=%d)" % (cb, torch.get_num_threads(), os.cpu_count())}
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _finish_multi_gpu()
 
 
 def main():
