@@ -163,7 +163,7 @@ def entry_flops_per_sample(cfg):
     for h in kw.get("dnn_hidden_units", []):
         dnn += 2 * prev * h
         prev = h
-    out = {"ctr_dnn_layer_fwd": float(dnn), "ctr_dnn_layer_bwd": 2.0 * dnn}
+    out = {"ctr_dnn_layer_fwd": float(dnn), "ctr_dnn_layer_bwd": 2.0 * dnn, "ctr_dnn_layer_bwd_chain": 2.0 * dnn}
     if cfg["model"] == "xDeepFM":
         cin, H = 0, F
         sizes = kw["cin_layer_size"]

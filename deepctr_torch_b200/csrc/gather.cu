@@ -63,7 +63,9 @@ struct GatherArgs {
 // rows.  A warp works on SPW samples at once: all their ids are fetched first, then all their row
 // loads (SPW x 4 x 128 bit per lane) are issued before the first store, so ~2 * F rows per warp are
 // in flight at the same time.
-template <int LPR, int SPW, int STEPS = 4>     // STEPS: row loads in flight per lane and sample
+// STEPS: row loads in flight per lane and sample; XCH: exchanged mode compiled in (kept out of the
+// single-GPU instantiation: its extra registers cost the local gather 25 % — run 23)
+template <int LPR, int SPW, int STEPS = 4, bool XCH = false>
 __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     constexpr int RPW = 32 / LPR;  // rows per warp step
     constexpr int D = LPR * 4;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
     for (int i = threadIdx.x; i < a.n_emb; i += blockDim.x) {
         s_col[i] = a.emb_cols[i];
         s_voc[i] = a.emb_vocab[i];
-        s_pc[i] = a.where ? a.emb_plan_col[i] : 0;
+        s_pc[i] = (XCH && a.where) ? a.emb_plan_col[i] : 0;
     }
     __syncthreads();
 
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                     if (G == 1) {
                         tab = s_tab[fc];
                         row = id;
-                    } else if (a.where) {
+                    } else if (XCH && a.where) {
                         const int64_t bc2 = (bb + t < a.B) ? bb + t : a.B - 1;
                         const int w = __ldg(a.where + bc2 * a.n_plan + s_pc[fc]);
                         if (w < 0) {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                         row = id / G;
                     }
                     // direct peer (NVLink-mapped) rows: plain coherent loads; everything local streams past L1
-                    v[t][s] = (G == 1 || a.where) ? ld_stream4(tab + (size_t)row * D + sub * 4)
+                    v[t][s] = (G == 1 || (XCH && a.where)) ? ld_stream4(tab + (size_t)row * D + sub * 4)
                                                   : *reinterpret_cast<const float4*>(tab + (size_t)row * D + sub * 4);
                 }
             }
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                 const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
                 if (G == 1) {
                     lp += __ldg(a.lin_tables[f] + id);
-                } else if (a.where) {
+                } else if (XCH && a.where) {
                     const int w = __ldg(a.where + b * a.n_plan + a.lin_plan_col[f]);
                     lp += (w < 0) ? __ldg(a.lin_tables[f * G + a.me] + id / G) : __ldg(a.resp_lin[w >> 26] + (w & ((1 << 26) - 1)));
                 } else {
@@ -712,8 +714,14 @@ static int gather_fwd_impl(const float* X, int64_t ldx, int64_t B, int n_emb, in
     if (vec_ok) {
         const size_t smem = (size_t)n_emb * n_shards * sizeof(void*) + (size_t)n_emb * 12;
         switch (lpr) {
-            case 1: gather_fwd_vec_kernel<1, 2><<<grid, 256, smem, st>>>(a); break;
-            case 2: gather_fwd_vec_kernel<2, 2><<<grid, 256, smem, st>>>(a); break;
+            case 1:
+                if (where) gather_fwd_vec_kernel<1, 2, 4, true><<<grid, 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<1, 2><<<grid, 256, smem, st>>>(a);
+                break;
+            case 2:
+                if (where) gather_fwd_vec_kernel<2, 2, 4, true><<<grid, 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<2, 2><<<grid, 256, smem, st>>>(a);
+                break;
             case 4: {
                 // CTR_GATHER_VARIANT (diagnostic): fewer loads in flight per lane — peer (NVLink) rows were
                 // 3.7x slower than torch's one-load-per-thread gather with the default 2 samples x 4 steps
@@ -723,12 +731,22 @@ static int gather_fwd_impl(const float* X, int64_t ldx, int64_t B, int n_emb, in
                 else if (var == 2) gather_fwd_vec_kernel<4, 1, 2><<<sample_grid(B, 8, 8), 256, smem, st>>>(a);
                 else if (var == 3) gather_fwd_vec_kernel<4, 1, 1><<<sample_grid(B, 8, 8), 256, smem, st>>>(a);
                 else if (var == 4) gather_fwd_vec_kernel<4, 1, 1><<<sample_grid(B, 8, 2), 256, smem, st>>>(a);
+                else if (where) gather_fwd_vec_kernel<4, 2, 4, true><<<grid, 256, smem, st>>>(a);
                 else gather_fwd_vec_kernel<4, 2><<<grid, 256, smem, st>>>(a);
                 break;
             }
-            case 8: gather_fwd_vec_kernel<8, 2><<<grid, 256, smem, st>>>(a); break;
-            case 16: gather_fwd_vec_kernel<16, 2><<<grid, 256, smem, st>>>(a); break;
-            default: gather_fwd_vec_kernel<32, 2><<<grid, 256, smem, st>>>(a); break;
+            case 8:
+                if (where) gather_fwd_vec_kernel<8, 2, 4, true><<<grid, 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<8, 2><<<grid, 256, smem, st>>>(a);
+                break;
+            case 16:
+                if (where) gather_fwd_vec_kernel<16, 2, 4, true><<<grid, 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<16, 2><<<grid, 256, smem, st>>>(a);
+                break;
+            default:
+                if (where) gather_fwd_vec_kernel<32, 2, 4, true><<<grid, 256, smem, st>>>(a);
+                else gather_fwd_vec_kernel<32, 2><<<grid, 256, smem, st>>>(a);
+                break;
         }
         CTR_LAUNCH_OK("gather_fwd_vec_kernel");
     } else {

@@ -766,7 +766,7 @@ int stream_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, i
 // and fetched by TMA.  CTR_PK_STREAM=0 forces the packed path for everything (A/B profiling).
 constexpr int64_t kStreamThresholdBytes = 4 << 20;
 
-PkConfig pk_config(const GemmArgs& g, bool allow_split) {
+PkConfig pk_config(const GemmArgs& g, bool allow_split, bool force_mt1 = false) {
     PkConfig c{};
     const int64_t M = g.M, N = g.N, K = g.K;
     const int64_t ntiles = ceil_div64(N, 256);
@@ -777,7 +777,7 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split) {
     const int64_t sms = ctr_sm_count();
     // two accumulators per CTA when there is enough work to fill the machine anyway
     c.MT = (ceil_div64(M, 2 * PK_AR) * c.gn >= sms || (allow_split && M > PK_AR)) ? 2 : 1;
-    if (M <= PK_AR) c.MT = 1;
+    if (M <= PK_AR || force_mt1) c.MT = 1;
     c.gm = ceil_div64(M, (int64_t)PK_AR * c.MT);
     c.splits = 1;
     if (allow_split) {
@@ -811,7 +811,7 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split) {
     // shared-memory plan: [A ring | B ring | raw cp.async slots | barriers]
     const int64_t a_stage = (int64_t)c.MT * PK_AR * 128, b_stage = (int64_t)c.BN * 128;
     const int64_t raw_per_depth = (int64_t)c.raw_a_bytes + c.raw_b_bytes;
-    const int64_t budget = 220 * 1024 - 512;
+    const int64_t budget = 232448 - 1024;                  // the 227 KB opt-in maximum minus barriers / slack
     const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;       // epilogue staging overlays the rings
     c.ok = false;
     if (raw_per_depth == 0) {
@@ -842,8 +842,10 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split) {
         c.off_raw = (uint32_t)rings;
         c.off_bar = (uint32_t)(rings + c.depth * raw_per_depth);
         c.smem = c.off_bar + (uint32_t)((2 * c.SA + 2 * c.SB + 1) * sizeof(uint64_t) + 16);
-        if (c.smem > 225 * 1024) c.ok = false;
+        if (c.smem > 232448) c.ok = false;
     }
+    // nothing fits with two accumulators (e.g. both operands streamed, one of them masked): one accumulator
+    if (!c.ok && c.MT == 2 && !force_mt1) return pk_config(g, allow_split, true);
     return c;
 }
 
@@ -967,7 +969,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const size_t smem = c.smem;
     static bool configured = false;
     if (!configured) {
-        const int max_smem = 225 * 1024;
+        const int max_smem = 232448;
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CTR_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

@@ -105,3 +105,34 @@ def test_dnn_layer_fwd_bwd(engine, act):
     assert rel_err(x.grad.cpu(), xd.grad.cpu()) <= 5e-6
     assert rel_err(W.grad.cpu(), Wd.grad.cpu()) <= 5e-6
     assert rel_err(b.grad.cpu(), bd.grad.cpu()) <= 5e-6
+
+
+@pytest.mark.parametrize("hidden", [(256, 256), (256, 128)])
+def test_dnn_tower_large_batch_streaming(hidden):
+    """The fused tower at a batch large enough that every activation operand is converted inside the
+    GEMM (streamed, masked on the top layer, both operands streamed in the weight gradients)."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    B, K = 40000, 429
+    x = torch.randn(B, 432, device=DEV, generator=g)[:, :K].requires_grad_(True)
+    Ws, bs, dims = [], [], [K] + list(hidden)
+    for i in range(len(hidden)):
+        Ws.append((torch.randn(dims[i + 1], dims[i], device=DEV, generator=g) * 0.05).requires_grad_(True))
+        bs.append((torch.randn(dims[i + 1], device=DEV, generator=g) * 0.05).requires_grad_(True))
+    y = ops.dnn_tower(x, "relu", Ws, bs)
+    w = torch.randn(B, hidden[-1], device=DEV, generator=g)
+    (y * w).sum().backward()
+    xd = x.detach().double().requires_grad_(True)
+    Wd = [W.detach().double().requires_grad_(True) for W in Ws]
+    bd = [b.detach().double().requires_grad_(True) for b in bs]
+    h = xd
+    for W, b in zip(Wd, bd):
+        h = torch.relu(h @ W.t() + b)
+    (h * w.double()).sum().backward()
+    assert rel_err(y.detach().cpu(), h.detach().cpu()) <= 1e-5
+    # gradients: a ReLU unit within ~1e-6 of zero may flip between two correctly rounded implementations
+    # (DESIGN.md, precision policy); one flip in 10^7 units moves the max-normalised error by < 1e-3
+    assert rel_err(x.grad.cpu(), xd.grad.cpu()) <= 1e-3
+    for W, Wr in zip(Ws, Wd):
+        assert rel_err(W.grad.cpu(), Wr.grad.cpu()) <= 1e-3
+    for b, br in zip(bs, bd):
+        assert rel_err(b.grad.cpu(), br.grad.cpu()) <= 1e-3
