@@ -118,7 +118,10 @@ def test_dnn_tower_large_batch_streaming(hidden):
     for i in range(len(hidden)):
         Ws.append((torch.randn(dims[i + 1], dims[i], device=DEV, generator=g) * 0.05).requires_grad_(True))
         bs.append((torch.randn(dims[i + 1], device=DEV, generator=g) * 0.05).requires_grad_(True))
-    y = ops.dnn_tower(x, "relu", Ws, bs)
+    # tanh on purpose: same code paths as ReLU (act'(Y) prologue on the top layer, act'(X) epilogues below),
+    # but smooth — at 10^7 units a handful of ReLU masks flip between two correctly rounded
+    # implementations and each flip moves one sample's gradient row by ~10 % of the maximum (run 27)
+    y = ops.dnn_tower(x, "tanh", Ws, bs)
     w = torch.randn(B, hidden[-1], device=DEV, generator=g)
     (y * w).sum().backward()
     xd = x.detach().double().requires_grad_(True)
@@ -126,13 +129,11 @@ def test_dnn_tower_large_batch_streaming(hidden):
     bd = [b.detach().double().requires_grad_(True) for b in bs]
     h = xd
     for W, b in zip(Wd, bd):
-        h = torch.relu(h @ W.t() + b)
+        h = torch.tanh(h @ W.t() + b)
     (h * w.double()).sum().backward()
     assert rel_err(y.detach().cpu(), h.detach().cpu()) <= 1e-5
-    # gradients: a ReLU unit within ~1e-6 of zero may flip between two correctly rounded implementations
-    # (precision policy); one flip in 10^7 units moves the max-normalised error by < 1e-3
-    assert rel_err(x.grad.cpu(), xd.grad.cpu()) <= 1e-3
+    assert rel_err(x.grad.cpu(), xd.grad.cpu()) <= 2e-5
     for W, Wr in zip(Ws, Wd):
-        assert rel_err(W.grad.cpu(), Wr.grad.cpu()) <= 1e-3
+        assert rel_err(W.grad.cpu(), Wr.grad.cpu()) <= 5e-5      # K = 40 000 truncating accumulations
     for b, br in zip(bs, bd):
-        assert rel_err(b.grad.cpu(), br.grad.cpu()) <= 1e-3
+        assert rel_err(b.grad.cpu(), br.grad.cpu()) <= 5e-5
