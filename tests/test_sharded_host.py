@@ -89,3 +89,34 @@ def test_localize_cfg_handles_columns_shared_between_linear_and_dnn():
             if c_full["type"] == "sparse":
                 assert c_loc["vocab"] == sharded.max_local_rows(c_full["vocab"], world)
         assert cfg["dnn_columns"][0]["vocab"] == 1003           # the logical cfg is untouched
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_arena_layout_regions_are_disjoint_and_aligned(world):
+    """Tables, the two receive lists and the forward-exchange buffers of the peer arena must not overlap
+    (every rank derives peer addresses from these offsets alone) and must keep 16-byte alignment."""
+    F, D, B = 26, 16, 65536
+    vocabs = [1538462] * F
+    L = sharded.ArenaLayout(vocabs, vocabs, D, world, B, n_id_cols=F)
+    regions = []
+    for f in range(F):
+        regions.append((L.emb_off[f], L.emb_rows[f] * D * 4))
+        regions.append((L.lin_off[f], L.lin_rows[f] * 4))
+    nf = 2 * F
+    for par in range(2):
+        r = L.recv[par]
+        regions += [(r["count"], nf * 4), (r["ids"], nf * L.cap * 4), (r["emb"], F * L.cap * D * 4), (r["lin"], F * L.cap * 4)]
+    x = L.x
+    regions += [(x["req_cnt"], world * 4), (x["req"], world * L.xcap * 8), (x["resp_emb"], world * L.xcap * D * 4),
+                (x["resp_lin"], world * L.xcap * 4)]
+    regions.sort()
+    for (o0, n0), (o1, _) in zip(regions, regions[1:]):
+        assert o0 % 16 == 0 and o0 + n0 <= o1, (o0, n0, o1)
+    assert regions[-1][0] + regions[-1][1] <= L.nbytes
+    # capacity: a peer can always hold twice the uniform share of one rank's ids (all of them for 2 ranks)
+    full = B * F
+    assert L.xcap >= min(full, 2 * ((full + world - 1) // world))
+    assert L.xcap < (1 << 26) and L.cap < (1 << 26)          # (owner << 26) | slot encodings
+    # rows per shard cover the vocabulary
+    for v, rows in zip(vocabs, L.emb_rows):
+        assert rows * world >= v
