@@ -24,6 +24,11 @@ int launch_cin_tc_bwd(const float* Xp, int64_t sxp, int H, const float* X0, int6
                       const float* W, int N, const float* dZ, float* dW, float* dXp, int64_t sdxp,
                       float* dX0, int64_t sdx0, int64_t B, int same, cudaStream_t st);
 
+// second-generation forward (cin_v2.cu): experimental, only with CTR_CIN_V2=1
+int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, const float* W,
+                      const float* bias, int N, int direct_start, int act, float* Y, float* out, int64_t ld_out, int64_t B,
+                      cudaStream_t st);
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
@@ -462,6 +467,9 @@ extern "C" int ctr_cin_layer_fwd(const float* Xp, int64_t sxp, int H, const floa
     {   // tensor-core path (cin_tc.cu) unless CTR_GEMM=simt or the shape is unsupported
         const char* e = getenv("CTR_GEMM");
         if (!(e && e[0] == 's')) {
+            const int rc2 = launch_cin_v2_fwd(Xp, sxp, H, X0, sx0, M, D, W, bias, N, direct_start, act, Y, out, ld_out, B, st);
+            if (rc2 == 1) return 0;
+            if (rc2 != 0) return rc2;
             const int rc = launch_cin_tc_fwd(Xp, sxp, H, X0, sx0, M, D, W, bias, N, direct_start, act, Y, out,
                                              ld_out, B, st);
             if (rc == 1) return 0;

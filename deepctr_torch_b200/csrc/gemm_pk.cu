@@ -791,8 +791,11 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split, bool force_mt1 = false) 
     }
     c.kb_per_split = ceil_div64(c.nkb, c.splits);
     c.splits = ceil_div64(c.nkb, c.kb_per_split);
+    // the epilogue reads whole 32-column chunks: the last chunk of the last accumulator must stay inside the
+    // TMEM allocation (matters for BN < 32 with two accumulators)
+    const int tm_need = (c.MT - 1) * c.BN + 32 * ((c.BN + 31) / 32);
     c.tmem_cols = 32;
-    while (c.tmem_cols < c.MT * c.BN) c.tmem_cols <<= 1;
+    while (c.tmem_cols < c.MT * c.BN || c.tmem_cols < tm_need) c.tmem_cols <<= 1;
 
     const char* e = getenv("CTR_PK_STREAM");
     const bool stream_ok = !(e && e[0] == '0');

@@ -1,0 +1,42 @@
+"""Parity of the experimental second-generation CIN forward (csrc/cin_v2.cu, CTR_CIN_V2=1) against the fp64
+oracle.  The kernel was written after the round-1 GPU budget was spent and has not run on hardware yet, so the
+test only runs on request: CTR_TEST_CIN_V2=1 python -m pytest tests/test_gpu_cin_v2.py -m gpu"""
+import os
+
+import pytest
+import torch
+
+from deepctr_torch_b200 import ops
+from helpers import rel_err
+from oracle import ctr_oracle as O
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CTR_TEST_CIN_V2") != "1", reason="experimental kernel: set CTR_TEST_CIN_V2=1")]
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("B,M,D,sizes,split", [(300, 26, 16, (32, 16), True), (1000, 26, 16, (128, 128), True),
+                                               (77, 7, 8, (6, 4, 3), False), (4096, 26, 16, (200,), True)])
+def test_cin_v2_forward_matches_fp64(B, M, D, sizes, split):
+    g = torch.Generator(device=DEV).manual_seed(B + M)
+    E = torch.randn(B, M, D, device=DEV, generator=g) * 0.5
+    params, P, H = [], {}, M
+    for k, n in enumerate(sizes):
+        W = torch.randn(n, H * M, 1, device=DEV, generator=g) * 0.1
+        b = torch.randn(n, device=DEV, generator=g) * 0.1
+        params += [W, b]
+        P["conv1ds.%d.weight" % k], P["conv1ds.%d.bias" % k] = W, b
+        H = n // 2 if (split and k != len(sizes) - 1) else n
+    old = os.environ.get("CTR_CIN_V2")
+    os.environ["CTR_CIN_V2"] = "1"
+    try:
+        out = ops.cin(E, sizes, split, "relu", params)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("CTR_CIN_V2", None)
+        else:
+            os.environ["CTR_CIN_V2"] = old
+    P64 = {k: v.double().cpu() for k, v in P.items()}
+    ref = O.cin(P64, "", E.double().cpu(), sizes, split, "relu")
+    assert rel_err(out.cpu(), ref) <= 1e-5
