@@ -334,7 +334,7 @@ int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
     const int engine = gemm_engine(g);
     if (engine == 2) {
         const int rc = launch_gemm_pk(g, st);
-        if (rc != -3) return rc;          // -3: operand layout the packed/streaming engine does not take
+        if (rc != -3) return rc;          // -3: no plan for this shape in the streaming engine (gemm_pk.cu)
         return launch_gemm_tc(g, st);
     }
     if (engine == 1) return launch_gemm_tc(g, st);

@@ -919,10 +919,7 @@ int gemm_pack_operand(const float* P, int64_t s_row, int64_t s_k, int64_t n_rows
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);
-    if (!c.ok) {
-        ctr_set_error("launch_gemm_pk: tile does not fit shared memory");
-        return -1;
-    }
+    if (!c.ok) return -3;     // no shared-memory plan for this shape: the caller uses the first-generation engine
     const int64_t need = c.a_bytes + c.b_bytes;
     const int dev = current_device();
     void* scratch = g_scratch[dev];
