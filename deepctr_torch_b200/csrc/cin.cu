@@ -22,12 +22,14 @@ int launch_cin_tc_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int6
 
 int launch_cin_tc_bwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D,
                       const float* W, int N, const float* dZ, float* dW, float* dXp, int64_t sdxp,
-                      float* dX0, int64_t sdx0, int64_t B, int same, cudaStream_t st);
+                      float* dX0, int64_t sdx0, int64_t B, int same, cudaStream_t st, int skip_dw);
 
 // second-generation forward (cin_v2.cu): experimental, only with CTR_CIN_V2=1
 int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, const float* W,
                       const float* bias, int N, int direct_start, int act, float* Y, float* out, int64_t ld_out, int64_t B,
                       cudaStream_t st);
+int launch_cin_v2_dw(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, int N, const float* dZ,
+                     float* dW, int64_t B, cudaStream_t st);
 
 namespace {
 
@@ -521,16 +523,21 @@ extern "C" int ctr_cin_layer_bwd(const float* Xp, int64_t sxp, int H, const floa
         cin_dbias_kernel<<<(unsigned)blocks, 256, 0, st>>>(dZ, N, D, B, bpb, dbias);
         CTR_LAUNCH_OK("cin_dbias_kernel");
     }
+    bool dw_done = false;
     {   // tensor-core dW + dX (cin_tc.cu) unless CTR_GEMM=simt or the shape is unsupported
         const char* e = getenv("CTR_GEMM");
         const char* e2 = getenv("CTR_CIN_TC_BWD");
         if (!(e && e[0] == 's') && !(e2 && e2[0] == '0')) {
-            const int rc = launch_cin_tc_bwd(Xp, sxp, H, X0, sx0, M, D, W, N, dZ, dW, dXp, sdxp, dX0, sdx0, B, same, st);
+            const int rcw = launch_cin_v2_dw(Xp, sxp, H, X0, sx0, M, D, N, dZ, dW, B, st);     // experimental, off by default
+            if (rcw != 0 && rcw != 1) return rcw;
+            dw_done = (rcw == 1);
+            const int rc = launch_cin_tc_bwd(Xp, sxp, H, X0, sx0, M, D, W, N, dZ, dW, dXp, sdxp, dX0, sdx0, B, same, st,
+                                             rcw == 1);
             if (rc == 1) return 0;
             if (rc != 0) return rc;
         }
     }
-    {
+    if (!dw_done) {
         const int64_t tiles = ceil_div64(HM, BN) * ceil_div64(N, BM);
         int64_t splits = ceil_div64(2LL * sms, tiles);
         if (splits > B) splits = B;

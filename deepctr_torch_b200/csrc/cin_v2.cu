@@ -253,6 +253,182 @@ __global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_fwd_kernel(CinV2Fwd a) {
     }
 }
 
+
+// =============================================================================================
+// dW[n, hm] = sum_{(b,d)} dZ[b,n,d] * Xp[b,h,d] * X0[b,m,d]     (EXPERIMENTAL, CTR_CIN_V2=1, D == 16)
+//
+// GEMM with M = channels (128 per CTA), N' = 256 (h,m) columns, K = (b,d): one 16-k stage = one sample.
+//   A(n, (b,d)) = dZ[b, n, d]            : the sample's [N][16] block IS a K-contiguous tile
+//   B(hm, (b,d)) = Xp[b,h,d] * X0[b,m,d] : generated; (h, m) of a thread's two rows are kernel constants
+// 16 generator warps, loads of sample b+1 in registers while sample b is split and stored, fp32
+// reductions (red.global.add.v4 through a transposing staging tile) because K is split across CTAs.
+// =============================================================================================
+struct CinV2Dw {
+    const float* Xp; int64_t sxp; int H;
+    const float* X0; int64_t sx0; int M;
+    int N;
+    const float* dZ; float* dW;
+    int64_t B; int64_t b_per_cta;
+    int S; uint32_t off_bar;
+};
+
+constexpr int V2_STG_PITCH = 36;
+
+__global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_dw_kernel(CinV2Dw a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int M = a.M, N = a.N, S = a.S;
+    const int HM = a.H * M;
+    const uint32_t a_tile = 128u * 128u, b_tile = 256u * 128u, stage_bytes = a_tile + b_tile;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + a.off_bar);
+    uint64_t* empty_bar = full_bar + S;
+    uint64_t* accum_bar = empty_bar + S;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int hm0 = blockIdx.x * 256, n0 = blockIdx.y * 128;
+    const int64_t b_beg = (int64_t)blockIdx.z * a.b_per_cta;
+    const int64_t b_end = (b_beg + a.b_per_cta < a.B) ? b_beg + a.b_per_cta : a.B;
+    const int nst = (int)(b_end - b_beg);                       // stages = samples of this CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], V2_GEN_WARPS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) tmem_alloc_warp(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wid == 1) {
+        const uint32_t idesc = tf32_idesc(256);
+        const uint32_t a_lbo = 128u * 16u, b_lbo = 256u * 16u;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nst; ++i) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t base = smem_u32(smem_raw + (size_t)s * stage_bytes);
+                const uint32_t a_hi = base, a_lo = base + a_tile / 2, b_hi = base + a_tile, b_lo = b_hi + b_tile / 2;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t dah = make_smem_desc(a_hi + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
+                    const uint64_t dal = make_smem_desc(a_lo + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
+                    const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    umma_tf32(tmem_base, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (i == nst - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+    } else if (wid >= 2) {
+        const int ct = tid - 64;
+        // A piece of this thread: channel row ra, chunk ca;  B pieces: rows rb (q = 0, 1), chunk cb
+        const int ra = ct & 127, ca = ct >> 7;
+        const bool a_ok = n0 + ra < N;
+        const int64_t a_off = (int64_t)(a_ok ? n0 + ra : 0) * 16 + 4 * ca;
+        const int a_toff = (ca * 128 + ra) * 4;
+        int64_t xp_off[2], x0_off[2];
+        int b_toff[2];
+        bool b_ok[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = ct + V2_GEN_WARPS * 32 * q;
+            const int rb = idx & 255, cb = idx >> 8;
+            const int hm = hm0 + rb;
+            b_ok[q] = hm < HM;
+            const int h = b_ok[q] ? hm / M : 0, m = b_ok[q] ? hm - h * M : 0;
+            xp_off[q] = (int64_t)h * 16 + 4 * cb;
+            x0_off[q] = (int64_t)m * 16 + 4 * cb;
+            b_toff[q] = (cb * 256 + rb) * 4;
+        }
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 av, pv[2], xv[2];
+        auto load = [&](int64_t b) {
+            const bool in = b < b_end;
+            const int64_t bc = in ? b : b_beg;
+            av = (in && a_ok) ? __ldg(reinterpret_cast<const float4*>(a.dZ + bc * N * 16 + a_off)) : z4;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                pv[q] = (in && b_ok[q]) ? __ldg(reinterpret_cast<const float4*>(a.Xp + bc * a.sxp + xp_off[q])) : z4;
+                xv[q] = (in && b_ok[q]) ? __ldg(reinterpret_cast<const float4*>(a.X0 + bc * a.sx0 + x0_off[q])) : z4;
+            }
+        };
+        load(b_beg);
+        int s = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < nst; ++i) {
+            const float4 a_cur = av;
+            const float4 p0 = make_float4(pv[0].x * xv[0].x, pv[0].y * xv[0].y, pv[0].z * xv[0].z, pv[0].w * xv[0].w);
+            const float4 p1 = make_float4(pv[1].x * xv[1].x, pv[1].y * xv[1].y, pv[1].z * xv[1].z, pv[1].w * xv[1].w);
+            load(b_beg + i + 1);                                  // next sample's loads fly during the stores below
+            mbar_wait(&empty_bar[s], ph);
+            float* st = reinterpret_cast<float*>(smem_raw + (size_t)s * stage_bytes);
+            v2_split_store(st, a_toff, 128 * 16, a_cur);
+            v2_split_store(st + a_tile / 4, b_toff[0], 256 * 16, p0);
+            v2_split_store(st + a_tile / 4, b_toff[1], 256 * 16, p1);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        // epilogue: accumulate the 128 x 256 tile into dW (K is split across CTAs)
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int ew = wid - 2, quad = wid & 3, cg = ew >> 2;
+        float* stg = reinterpret_cast<float*>(smem_raw) + (size_t)ew * (32 * V2_STG_PITCH);
+        const bool vec = (HM % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.dW) & 15) == 0);
+        for (int ci = cg; ci < 8; ci += V2_GEN_WARPS / 4) {
+            const int c0 = ci * 32;
+            if (hm0 + c0 >= HM) break;                            // warp-uniform
+            uint32_t raw[32];
+            v2_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * V2_STG_PITCH + 4 * j) =
+                    make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+            __syncwarp();
+            const int colq = lane & 7;
+            const int hm = hm0 + c0 + 4 * colq;
+#pragma unroll 1
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = 4 * i2 + (lane >> 3);
+                const int n = n0 + quad * 32 + r;
+                const float4 v = *reinterpret_cast<const float4*>(stg + r * V2_STG_PITCH + 4 * colq);
+                if (n < N && hm < HM) {
+                    float* dst = a.dW + (size_t)n * HM + hm;
+                    if (vec && hm + 3 < HM) {
+                        red_add4(dst, v);
+                    } else {
+                        atomicAdd(dst, v.x);
+                        if (hm + 1 < HM) atomicAdd(dst + 1, v.y);
+                        if (hm + 2 < HM) atomicAdd(dst + 2, v.z);
+                        if (hm + 3 < HM) atomicAdd(dst + 3, v.w);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (wid == 1) {
+        tc_fence_after();
+        tmem_dealloc_warp(tmem_base, 256);
+    }
+}
+
 }  // namespace
 
 // returns 1 if the kernel was launched, 0 if the shape / environment is not supported (caller falls back
@@ -310,6 +486,47 @@ int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int6
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
         ctr_set_error("launch of cin_v2_fwd_kernel failed: %s", cudaGetErrorString(le));
+        return (int)le + 1000;
+    }
+    return 1;
+}
+
+// dW of one CIN layer (dW must have been zeroed).  Returns 1 if launched, 0 if not supported / not enabled.
+int launch_cin_v2_dw(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, int N, const float* dZ,
+                     float* dW, int64_t B, cudaStream_t st) {
+    const char* e = getenv("CTR_CIN_V2");
+    if (!(e && e[0] == '1')) return 0;
+    if (D != 16 || B < 1) return 0;
+    if ((sxp % 4) != 0 || (sx0 % 4) != 0 || (reinterpret_cast<uintptr_t>(Xp) & 15) || (reinterpret_cast<uintptr_t>(X0) & 15) ||
+        (reinterpret_cast<uintptr_t>(dZ) & 15))
+        return 0;
+    const int HM = H * M;
+    CinV2Dw a{Xp, sxp, H, X0, sx0, M, N, dZ, dW, B, 0, 4, 0};
+    const int64_t tiles = ceil_div64(HM, 256) * ceil_div64(N, 128);
+    int64_t splits = ceil_div64((int64_t)ctr_sm_count(), tiles);
+    if (splits > B) splits = B;
+    if (splits < 1) splits = 1;
+    a.b_per_cta = ceil_div64(B, splits);
+    splits = ceil_div64(B, a.b_per_cta);
+    if (splits > 65535) return 0;
+    const size_t stage_bytes = 128 * 128 + 256 * 128;
+    a.off_bar = (uint32_t)(a.S * stage_bytes);
+    const size_t smem = a.off_bar + (2 * a.S + 1) * sizeof(uint64_t) + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(cin_v2_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (ce != cudaSuccess) {
+            ctr_set_error("cin_v2_dw: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
+            return (int)ce + 1000;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div64(HM, 256), (unsigned)ceil_div64(N, 128), (unsigned)splits);
+    cin_v2_dw_kernel<<<grid, V2_THREADS, smem, st>>>(a);
+    ctr_count_launch();
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        ctr_set_error("launch of cin_v2_dw_kernel failed: %s", cudaGetErrorString(le));
         return (int)le + 1000;
     }
     return 1;
