@@ -441,7 +441,8 @@ def run_gpu_arm(args):
     ld = (blk_w + 3) // 4 * 4
     gather_bytes = 4 * (39 + 26 * D + 26 + blk_w + 2)                 # X row + rows + linear w + blk + lin/fm
     scatter_bytes = 4 * (2 * ld + 26 * 2 + 26 * D + 26 + 2)             # d_blk + blk + inv/cnt + row grads out
-    hbm_entries = {"ctr_gather_fwd": gather_bytes, "ctr_scatter_bwd_rowwise": scatter_bytes}
+    hbm_entries = {"ctr_gather_fwd": gather_bytes, "ctr_gather_fwd_exchanged": gather_bytes,
+                   "ctr_scatter_bwd_rowwise": scatter_bytes}
     roofs = {}
     for name, bps in hbm_entries.items():
         if name in per_entry and per_entry[name]["ms_per_step"] > 0:
