@@ -14,16 +14,19 @@ from ._build import LIB_PATH
 c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 c_int, c_ptr = ctypes.c_int, ctypes.c_void_p
 
+ABI_VERSION = 2
+
 # name -> argtypes (restype is int for everything except the three listed below)
 _P = c_ptr
 SIGNATURES = {
     "ctr_gather_fwd": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P,
-                       c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, _P],
+                       c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, c_int, _P],
     "ctr_fm_fwd": [_P, c_i64, c_i64, c_int, c_int, _P, _P],
     "ctr_fm_bwd": [_P, c_i64, c_i64, c_int, c_int, _P, _P, c_i64, _P],
     "ctr_scatter_bwd_dense": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P,
-                              _P, c_i64, _P, c_i64, _P, _P, _P],
-    "ctr_unique_plan": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P, c_i64, _P, _P, _P, _P, _P, _P],
+                              _P, c_i64, _P, c_i64, _P, _P, c_int, _P],
+    "ctr_write_ptrs": [_P, c_int, _P, _P],
+    "ctr_unique_plan": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P, c_i64, _P, _P, _P, _P, _P, c_int, _P, _P],
     "ctr_scatter_bwd_rowwise": [c_i64, c_int, _P, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
                                 _P, c_i64, _P, c_i64, _P, _P, _P],
     "ctr_p2p_alloc": [c_i64, _P],
@@ -31,10 +34,10 @@ SIGNATURES = {
     "ctr_p2p_export": [_P, _P],
     "ctr_p2p_open": [_P, _P],
     "ctr_p2p_close": [_P],
-    "ctr_shard_request": [_P, c_i64, c_i64, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, c_i64, _P, _P],
+    "ctr_shard_request": [_P, c_i64, c_i64, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, c_i64, _P, c_int, _P],
     "ctr_shard_serve": [c_int, c_int, c_int, _P, _P, c_i64, _P, _P, _P, _P, _P],
     "ctr_gather_fwd_exchanged": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P,
-                                 c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
+                                 c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P],
     "ctr_rowgrad_push": [c_i64, c_int, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
                          _P, _P, _P, _P, c_i64, _P, _P],
     "ctr_lin_dense_wgrad": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P],
@@ -71,9 +74,20 @@ SIGNATURES = {
     "ctr_debug_set_buffer": [_P],
     "ctr_set_scratch": [_P, c_i64],
     "ctr_varlen_pool_fwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,
-                            c_i64, _P, _P],
+                            c_i64, _P, c_int, _P],
     "ctr_varlen_pool_bwd": [_P, c_i64, c_i64, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P,
-                            c_i64, _P, _P],
+                            c_i64, _P, c_int, _P],
+    "ctr_bipool_fwd": [_P, c_i64, c_int, c_int, _P, c_i64, c_i64, _P],
+    "ctr_bipool_bwd": [_P, c_i64, c_int, c_int, _P, c_i64, _P, c_i64, c_i64, _P],
+    "ctr_refine_fwd": [_P, _P, c_i64, _P, c_int, c_int, c_int, _P, _P, c_i64, _P, c_i64, _P],
+    "ctr_refine_bwd": [_P, _P, c_i64, _P, c_int, c_int, c_int, _P, c_i64, _P, _P, _P, c_i64, _P, c_i64, _P],
+    "ctr_afm_fwd": [_P, c_i64, c_int, c_int, c_int, _P, _P, _P, _P, c_i64, _P],
+    "ctr_afm_bwd": [_P, c_i64, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_i64, _P, _P, _P, c_i64, _P],
+    "ctr_fieldattn_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_f32, _P, c_i64, _P],
+    "ctr_fieldattn_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_f32, _P, _P, _P, _P, c_i64, _P],
+    "ctr_rowopt_tick": [_P, _P],
+    "ctr_rowopt_step": [c_int, c_i64, _P, _P, c_int, c_int, _P, c_i64, _P, _P, _P, _P, _P, c_f32, _P],
+    "ctr_rowgrad_combine": [c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, c_i64, _P, c_i64, _P],
 }
 SPECIAL = {
     "ctr_version": ([], c_int),
@@ -117,8 +131,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = restype
-        if lib.ctr_version() != 1:
-            raise CtrLibraryError("libctr_b200.so ABI version %d, expected 1" % lib.ctr_version())
+        if lib.ctr_version() != ABI_VERSION:
+            raise CtrLibraryError("libctr_b200.so ABI version %d, expected %d" % (lib.ctr_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

@@ -30,7 +30,7 @@ static std::atomic<long long> g_launches{0};
 void ctr_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int64_t ctr_launch_count(void) { return (int64_t)g_launches.load(); }
 
-extern "C" int ctr_version(void) { return 1; }
+extern "C" int ctr_version(void) { return 2; }
 extern "C" const char* ctr_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,10 +15,12 @@ namespace {
 
 constexpr int kMaxSmemSlots = 256;  // slot metadata staged in shared memory up to this many fields
 
-__device__ __forceinline__ int decode_id(float xv, int vocab, int32_t* err_flag) {
-    // fp32 -> integer by truncation, exactly like `.long()` (reference basemodel.py:369); ids live in
-    // [0, vocab) with vocab < 2^31, out-of-range / negative / huge values trip the unsigned compare
-    int id = __float2int_rz(xv);
+__device__ __forceinline__ int decode_id(float xv, int vocab, int32_t* err_flag, int id_mode) {
+    // id_mode 0 (reference): fp32 -> integer by truncation, exactly like `.long()` (reference
+    // basemodel.py:369), exact only below 2^24.  id_mode 1 (CTR_IDS_I32BITS): the 4-byte cell holds the
+    // int32 id itself (bit pattern), no 2^24 limit.  ids live in [0, vocab) with vocab < 2^31:
+    // out-of-range / negative / huge values trip the unsigned compare
+    int id = id_mode ? __float_as_int(xv) : __float2int_rz(xv);
     if ((unsigned)id >= (unsigned)vocab) {
         if (err_flag) atomicOr(err_flag, 1);
         id = 0;
@@ -54,6 +56,7 @@ struct GatherArgs {
     const int32_t* where; int n_plan; int me;
     const int32_t* emb_plan_col; const int32_t* lin_plan_col;
     const float* const* resp_emb; const float* const* resp_lin;
+    int id_mode;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
                 for (int s = 0; s < STEPS; ++s) {
                     const int f = f0 + s * RPW + rslot;
                     const int fc = f < a.n_emb ? f : a.n_emb - 1;
-                    const int id = decode_id(xr[t][s], s_voc[fc], a.err_flag);
+                    const int id = decode_id(xr[t][s], s_voc[fc], a.err_flag, a.id_mode);
                     const float* tab;
                     int row;
                     if (G == 1) {
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(256) gather_fwd_vec_kernel(GatherArgs a) {
             // linear term: sparse weights + dense dot; dense copy (and zero padding) into the block
             float lp = 0.f;
             for (int f = lane; f < a.n_lin; f += 32) {
-                const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+                const int id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag, a.id_mode);
                 if (G == 1) {
                     lp += __ldg(a.lin_tables[f] + id);
                 } else if (XCH && a.where) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
             const int total = a.n_emb * D;
             for (int i = lane; i < total; i += 32) {
                 const int f = i / D, d = i - f * D;
-                const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], a.err_flag);
+                const int64_t id = decode_id(__ldg(xrow + a.emb_cols[f]), a.emb_vocab[f], a.err_flag, a.id_mode);
                 const float* src = a.emb_tables[f * G + (int)(id % G)] + (id / G) * D + d;
                 a.blk[b * a.ld_blk + i] = (G == 1) ? __ldg(src) : *src;      // peer rows: plain loads
             }
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256) gather_fwd_generic_kernel(GatherArgs a) {
         }
         float lp = 0.f;
         for (int f = lane; f < a.n_lin; f += 32) {
-            const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag);
+            const int64_t id = decode_id(__ldg(xrow + a.lin_cols[f]), a.lin_vocab[f], a.err_flag, a.id_mode);
             const float* lsrc = a.lin_tables[f * G + (int)(id % G)] + id / G;
             lp += (G == 1) ? __ldg(lsrc) : *lsrc;
         }
@@ -316,6 +319,7 @@ struct ScatterArgs {
     int n_plan;
     const int32_t* inv;
     const int32_t* cnt;
+    int id_mode;
 };
 
 // A warp works on SPW samples at once.  r[b,f,:] = d_blk + g_fm (S - E) is added to its destination
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(128) scatter_bwd_vec_kernel(ScatterArgs a) {
                     const int fc = f < a.n_emb ? f : a.n_emb - 1;
                     r[t][s] = a.d_blk ? ld_stream4(a.d_blk + bc[t] * a.ld_dblk + (int64_t)fc * D + sub * 4) : zero4;
                     if (ROWWISE) u[t][s] = __ldg(a.inv + bc[t] * a.n_plan + a.emb_cols[fc]);
-                    else u[t][s] = decode_id(__ldg(a.X + bc[t] * a.ldx + a.emb_cols[fc]), a.emb_vocab[fc], nullptr);
+                    else u[t][s] = decode_id(__ldg(a.X + bc[t] * a.ldx + a.emb_cols[fc]), a.emb_vocab[fc], nullptr, a.id_mode);
                 }
             if (ROWWISE) {
 #pragma unroll
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(128) scatter_bwd_vec_kernel(ScatterArgs a) {
                         if (cc == 1) *dst = gl;
                         else atomicAdd(dst, gl);
                     } else {
-                        const int id = decode_id(__ldg(a.X + bc[t] * a.ldx + a.lin_cols[f]), a.lin_vocab[f], nullptr);
+                        const int id = decode_id(__ldg(a.X + bc[t] * a.ldx + a.lin_cols[f]), a.lin_vocab[f], nullptr, a.id_mode);
                         atomicAdd(a.lin_out[f] + id, gl);
                     }
                 }
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a)
                 const int u = a.inv[b * a.n_plan + pc];
                 atomicAdd(a.emb_rg + f * a.emb_rg_stride + (int64_t)u * D + d, r);
             } else {
-                const int64_t id = decode_id(xrow[a.emb_cols[f]], a.emb_vocab[f], nullptr);
+                const int64_t id = decode_id(xrow[a.emb_cols[f]], a.emb_vocab[f], nullptr, a.id_mode);
                 atomicAdd(a.emb_out[f] + id * D + d, r);
             }
         }
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(256) scatter_bwd_generic_kernel(ScatterArgs a)
                     const int u = a.inv[b * a.n_plan + a.lin_cols[f]];
                     atomicAdd(a.lin_rg + f * a.lin_rg_stride + u, gl);
                 } else {
-                    const int64_t id = decode_id(xrow[a.lin_cols[f]], a.lin_vocab[f], nullptr);
+                    const int64_t id = decode_id(xrow[a.lin_cols[f]], a.lin_vocab[f], nullptr, a.id_mode);
                     atomicAdd(a.lin_out[f] + id, gl);
                 }
             }
@@ -544,7 +548,8 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
                                                           const int32_t* __restrict__ vocab,
                                                           int32_t* keys, int32_t* vals, int64_t H,
                                                           int32_t* n_uniq, int32_t* uniq,
-                                                          int32_t* inv, int32_t* err_flag) {
+                                                          int32_t* inv, int32_t* err_flag, int id_mode,
+                                                          const int32_t* __restrict__ col_count) {
     const int64_t total = B * n_cols;
     const uint32_t mask = (uint32_t)(H - 1);
     const int lane = threadIdx.x & 31;
@@ -564,11 +569,13 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
             const int64_t ic = valid[t] ? i : 0;
             c[t] = (int)(ic / B);
             b[t] = ic - (int64_t)c[t] * B;
-            xv[t] = __ldg(X + b[t] * ldx + cols[c[t]]);
+            // ragged columns (receive lists of the sharded backward): only the first col_count[c] entries exist
+            if (col_count && b[t] >= __ldg(col_count + c[t])) valid[t] = false;
+            xv[t] = __ldg(X + (valid[t] ? b[t] : 0) * ldx + cols[c[t]]);
         }
 #pragma unroll
         for (int t = 0; t < PLAN_ILP; ++t) {                 // all first probes (CAS) in flight
-            key[t] = (int32_t)decode_id(xv[t], vocab[c[t]], valid[t] ? err_flag : nullptr);
+            key[t] = (int32_t)decode_id(xv[t], vocab[c[t]], valid[t] ? err_flag : nullptr, id_mode);
             slot[t] = mix32((uint32_t)key[t]) & mask;
             old[t] = valid[t] ? atomicCAS(keys + (int64_t)c[t] * H + slot[t], -1, key[t]) : key[t];
         }
@@ -611,11 +618,13 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) plan_finalize_kernel(int64_t B, int n_cols,
                                                             const int32_t* __restrict__ vals,
-                                                            int64_t H, int32_t* inv, int32_t* cnt) {
+                                                            int64_t H, int32_t* inv, int32_t* cnt,
+                                                            const int32_t* __restrict__ col_count) {
     const int64_t total = B * n_cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % n_cols);
+        if (col_count && i / n_cols >= __ldg(col_count + c)) continue;
         const int32_t u = __ldcg(vals + (int64_t)c * H + inv[i]);
         inv[i] = u;
         atomicAdd(cnt + (int64_t)c * B + u, 1);
@@ -687,7 +696,7 @@ static int gather_fwd_impl(const float* X, int64_t ldx, int64_t B, int n_emb, in
                               const int32_t* dense_cols, int n_lin_dense,
                               const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
                               int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
-                              int n_shards, void* stream, const int32_t* where, int n_plan, int me,
+                              int n_shards, int id_mode, void* stream, const int32_t* where, int n_plan, int me,
                               const int32_t* emb_plan_col, const int32_t* lin_plan_col,
                               const float* const* resp_emb, const float* const* resp_lin) {
     CTR_ARG(X && B >= 0 && ldx >= 0, "ctr_gather_fwd: X/B/ldx invalid");
@@ -701,7 +710,7 @@ static int gather_fwd_impl(const float* X, int64_t ldx, int64_t B, int n_emb, in
     if (B == 0) return 0;
     GatherArgs a{X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols,
                  lin_vocab, n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk,
-                 lin, fm, err_flag, n_shards, where, n_plan, me, emb_plan_col, lin_plan_col, resp_emb, resp_lin};
+                 lin, fm, err_flag, n_shards, where, n_plan, me, emb_plan_col, lin_plan_col, resp_emb, resp_lin, id_mode};
     cudaStream_t st = as_stream(stream);
     const int lpr = (n_emb > 0) ? lpr_for_dim(D) : 1;
     const bool vec_ok = lpr > 0 && n_emb * n_shards <= kMaxSmemSlots &&
@@ -772,10 +781,10 @@ extern "C" int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B, int n_emb,
                               const int32_t* dense_cols, int n_lin_dense,
                               const int32_t* lin_dense_cols, const float* lin_dense_w, float* blk,
                               int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
-                              int n_shards, void* stream) {
+                              int n_shards, int id_mode, void* stream) {
     return gather_fwd_impl(X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols, lin_vocab,
                            n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk, lin, fm, err_flag,
-                           n_shards, stream, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr);
+                           n_shards, id_mode, stream, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int ctr_gather_fwd_exchanged(const float* X, int64_t ldx, int64_t B, int n_emb, int D,
@@ -787,13 +796,14 @@ extern "C" int ctr_gather_fwd_exchanged(const float* X, int64_t ldx, int64_t B, 
                                         int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
                                         int n_shards, int rank, const int32_t* where, int n_plan,
                                         const int32_t* emb_plan_col, const int32_t* lin_plan_col,
-                                        const float* const* resp_emb, const float* const* resp_lin, void* stream) {
+                                        const float* const* resp_emb, const float* const* resp_lin, int id_mode,
+                                        void* stream) {
     CTR_ARG(where && n_plan > 0 && rank >= 0 && rank < n_shards, "ctr_gather_fwd_exchanged: bad exchange arguments");
     CTR_ARG((n_emb == 0 || (emb_plan_col && resp_emb)) && (n_lin == 0 || (lin_plan_col && resp_lin)),
             "ctr_gather_fwd_exchanged: plan columns / response buffers missing");
     return gather_fwd_impl(X, ldx, B, n_emb, D, emb_tables, emb_cols, emb_vocab, n_lin, lin_tables, lin_cols, lin_vocab,
                            n_dense, dense_cols, n_lin_dense, lin_dense_cols, lin_dense_w, blk, ld_blk, lin, fm, err_flag,
-                           n_shards, stream, where, n_plan, rank, emb_plan_col, lin_plan_col, resp_emb, resp_lin);
+                           n_shards, id_mode, stream, where, n_plan, rank, emb_plan_col, lin_plan_col, resp_emb, resp_lin);
 }
 
 extern "C" int ctr_fm_fwd(const float* blk, int64_t ld, int64_t B, int F, int D, float* fm,
@@ -861,7 +871,7 @@ extern "C" int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B, int
                                      const int32_t* lin_cols, const int32_t* lin_vocab,
                                      const float* blk, int64_t ld_blk, const float* d_blk,
                                      int64_t ld_dblk, const float* g_fm, const float* g_lin,
-                                     void* stream) {
+                                     int id_mode, void* stream) {
     CTR_ARG(X && B >= 0, "ctr_scatter_bwd_dense: X/B invalid");
     CTR_ARG(n_emb == 0 || (D > 0 && emb_grads && emb_cols && emb_vocab), "ctr_scatter_bwd_dense: embedding arrays missing");
     CTR_ARG(n_lin == 0 || !g_lin || (lin_grads && lin_cols && lin_vocab), "ctr_scatter_bwd_dense: linear arrays missing");
@@ -872,6 +882,7 @@ extern "C" int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B, int
     a.emb_out = emb_grads; a.emb_cols = emb_cols; a.emb_vocab = emb_vocab;
     a.n_lin = g_lin ? n_lin : 0; a.lin_out = lin_grads; a.lin_cols = lin_cols; a.lin_vocab = lin_vocab;
     a.blk = blk; a.ld_blk = ld_blk; a.d_blk = d_blk; a.ld_dblk = ld_dblk; a.g_fm = g_fm; a.g_lin = g_lin;
+    a.id_mode = id_mode;
     if (!d_blk && !g_fm) a.n_emb = 0;
     const int r = launch_scatter(a, false, as_stream(stream));
     return r < 0 ? r : (r > 2 ? r : 0);
@@ -886,7 +897,8 @@ extern "C" int64_t ctr_unique_plan_hash_slots(int64_t B) {
 extern "C" int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_cols,
                                const int32_t* cols, const int32_t* vocab, int32_t* hash_keys,
                                int32_t* hash_vals, int64_t H, int32_t* n_uniq, int32_t* uniq,
-                               int32_t* inv, int32_t* cnt, int32_t* err_flag, void* stream) {
+                               int32_t* inv, int32_t* cnt, int32_t* err_flag, int id_mode,
+                               const int32_t* col_count, void* stream) {
     CTR_ARG(X && cols && vocab && hash_keys && hash_vals && n_uniq && uniq && inv && cnt,
             "ctr_unique_plan: null argument");
     CTR_ARG(n_cols > 0 && B >= 0, "ctr_unique_plan: bad sizes");
@@ -901,9 +913,10 @@ extern "C" int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_col
     const int64_t cap = (int64_t)ctr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     plan_insert_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, B, n_cols, cols, vocab, hash_keys,
-                                                         hash_vals, H, n_uniq, uniq, inv, err_flag);
+                                                         hash_vals, H, n_uniq, uniq, inv, err_flag, id_mode,
+                                                         col_count);
     CTR_LAUNCH_OK("plan_insert_kernel");
-    plan_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, n_cols, hash_vals, H, inv, cnt);
+    plan_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, n_cols, hash_vals, H, inv, cnt, col_count);
     CTR_LAUNCH_OK("plan_finalize_kernel");
     return 0;
 }

@@ -141,6 +141,7 @@ struct RequestArgs {
     int32_t* where;                  // [B, n_cols]
     int64_t cap;
     int32_t* err_flag;
+    int id_mode;
 };
 
 constexpr int REQ_CHUNK = 1024;
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(256) shard_request_kernel(RequestArgs a) {
             const int64_t b = b0 + threadIdx.x + 256 * j;
             owner[j] = -1;
             if (b < a.B) {
-                int id = __float2int_rz(__ldg(a.X + b * a.ldx + col));
+                const float xv = __ldg(a.X + b * a.ldx + col);
+                int id = a.id_mode ? __float_as_int(xv) : __float2int_rz(xv);
                 if ((unsigned)id >= (unsigned)vocab) {
                     atomicOr(a.err_flag, 1);
                     id = 0;
@@ -304,7 +306,7 @@ extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, 
 extern "C" int ctr_shard_request(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
                                  const int32_t* vocab, int n_shards, int rank, int32_t* cnt_to,
                                  int32_t* const* inbox_req, int32_t* const* inbox_cnt, int32_t* where,
-                                 int64_t cap, int32_t* err_flag, void* stream) {
+                                 int64_t cap, int32_t* err_flag, int id_mode, void* stream) {
     CTR_ARG(X && cols && vocab && cnt_to && inbox_req && inbox_cnt && where && err_flag, "ctr_shard_request: null argument");
     CTR_ARG(n_cols > 0 && B >= 0 && n_shards >= 1 && n_shards <= PUSH_MAX_G && rank >= 0 && rank < n_shards && cap > 0 &&
                 cap < (1 << 26),
@@ -312,7 +314,7 @@ extern "C" int ctr_shard_request(const float* X, int64_t ldx, int64_t B, int n_c
     cudaStream_t st = as_stream(stream);
     CTR_CUDA(cudaMemsetAsync(cnt_to, 0, sizeof(int32_t) * n_shards, st));
     if (B > 0) {
-        RequestArgs a{X, ldx, B, n_cols, cols, vocab, n_shards, rank, cnt_to, inbox_req, where, cap, err_flag};
+        RequestArgs a{X, ldx, B, n_cols, cols, vocab, n_shards, rank, cnt_to, inbox_req, where, cap, err_flag, id_mode};
         int64_t bx = ceil_div64(B, REQ_CHUNK);
         const int64_t limit = ceil_div64((int64_t)ctr_sm_count() * 8, n_cols);
         if (bx > limit) bx = limit;

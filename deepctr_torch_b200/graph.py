@@ -35,6 +35,9 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         model.check_ids()
         model.zero_grad(set_to_none=True)
+        plan = model._plan
+        if plan is not None:
+            plan.pending.clear()
         self.graph = torch.cuda.CUDAGraph()
         from . import _lib
         l0 = _lib.launch_count()
@@ -43,6 +46,9 @@ class GraphedStep:
         # kernels of libctr_b200.so recorded as graph nodes: each replay launches exactly these
         self.launches_per_replay = _lib.launch_count() - l0
         self.replays = 0
+        # row gradients parked for the fused optimizer (plan.keep_rowgrads): the captured buffers are
+        # rewritten by every replay, so every replay re-publishes them
+        self._parked = list(plan.pending) if plan is not None else []
 
     def _body(self):
         y_pred = self.model(self.X)
@@ -59,6 +65,8 @@ class GraphedStep:
         self.y.copy_(y.reshape(-1), non_blocking=True)
         self.graph.replay()
         self.replays += 1
+        if self._parked:
+            self.model._plan.pending[:] = self._parked
         return self.loss
 
     # ---- input pipeline: the next batch travels host -> device while the current step computes ----
@@ -104,6 +112,8 @@ class GraphedStep:
         self._free[k].record(cur)
         self.graph.replay()
         self.replays += 1
+        if self._parked:
+            self.model._plan.pending[:] = self._parked
         return self.loss
 
 
@@ -153,7 +163,9 @@ class ShardedGraphedStep:
         y_pred = m(self.X)
         loss = self.loss_fn(y_pred.squeeze(1), self.y, reduction="sum")
         loss.backward()
-        m.sharded.clear_received(m.sharded.finish_step())
+        done = m.sharded.finish_step()
+        m.sharded.combine_received(done)       # owner-side dedup-sum: the same (uniq, rowgrad) contract as 1 GPU
+        m.sharded.clear_received(done)
         return loss
 
     def __call__(self, X, y):

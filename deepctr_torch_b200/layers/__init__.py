@@ -1,5 +1,6 @@
 from .core import DNN, PredictionLayer
-from .interaction import (FM, CIN, CrossNet, CrossNetMix, SENETLayer, BilinearInteraction)
+from .interaction import (FM, CIN, CrossNet, CrossNetMix, SENETLayer, BilinearInteraction,
+                          BiInteractionPooling, AFMLayer, InteractingLayer)
 
 __all__ = ["DNN", "PredictionLayer", "FM", "CIN", "CrossNet", "CrossNetMix", "SENETLayer",
-           "BilinearInteraction"]
+           "BilinearInteraction", "BiInteractionPooling", "AFMLayer", "InteractingLayer"]

@@ -171,3 +171,82 @@ class CrossNetMix(nn.Module):
                 uvs.append(ops.dnn_layer(v, self.U_list[i, e], None, "linear"))        # v U^T       [B,in]
             xl = ops.cross_mix_combine(x0, xl, torch.stack(uvs, dim=0), gate, self.bias[i])
         return xl
+
+
+class BiInteractionPooling(nn.Module):
+    """``0.5 ((sum_f e)^2 - sum_f e^2)`` keeping the embedding axis, ``[B,F,D] -> [B,1,D]``
+    (reference interaction.py:37-61); one kernel."""
+
+    def forward(self, inputs):
+        if inputs.dim() != 3:
+            raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % inputs.dim())
+        return ops.bi_interaction_pooling(inputs)
+
+
+class AFMLayer(nn.Module):
+    """Attentional FM (reference interaction.py:250-331): parameters ``attention_W [D,A]``,
+    ``attention_b [A]``, ``projection_h [A,1]``, ``projection_p [D,1]`` (xavier-normal / zeros like the
+    reference).  Accepts the reference's list of ``[B,1,D]`` tensors or an assembled ``[B,F,D]`` block;
+    pair products, attention net, softmax over the pairs and the weighted sum are one kernel."""
+
+    def __init__(self, in_features, attention_factor=4, l2_reg_w=0, dropout_rate=0, seed=1024, device="cpu"):
+        super().__init__()
+        self.attention_factor = attention_factor
+        self.l2_reg_w = l2_reg_w
+        self.dropout_rate = dropout_rate
+        self.seed = seed
+        self.attention_W = nn.Parameter(torch.Tensor(in_features, attention_factor))
+        self.attention_b = nn.Parameter(torch.Tensor(attention_factor))
+        self.projection_h = nn.Parameter(torch.Tensor(attention_factor, 1))
+        self.projection_p = nn.Parameter(torch.Tensor(in_features, 1))
+        for tensor in [self.attention_W, self.projection_h, self.projection_p]:
+            nn.init.xavier_normal_(tensor)
+        nn.init.zeros_(self.attention_b)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.to(device)
+
+    def forward(self, inputs):
+        E = torch.cat(list(inputs), dim=1) if isinstance(inputs, (list, tuple)) else inputs
+        att = ops.afm_attention(E, self.attention_W, self.attention_b, self.projection_h)     # [B,D]
+        if self.dropout_rate > 0:
+            att = self.dropout(att)
+        return ops.rowdot(att, self.projection_p).unsqueeze(1)
+
+
+class InteractingLayer(nn.Module):
+    """AutoInt's multi-head self-attention over the fields with residual + relu (reference
+    interaction.py:334-394): ``W_Query / W_key / W_Value / W_Res [D,D]``, ``N(0, 0.05)``.  The four
+    projections are GEMM kernel calls on the ``[B*F, D]`` view, the attention core is one kernel."""
+
+    def __init__(self, embedding_size, head_num=2, use_res=True, scaling=False, seed=1024, device="cpu"):
+        super().__init__()
+        if head_num <= 0:
+            raise ValueError("head_num must be a int > 0")
+        if embedding_size % head_num != 0:
+            raise ValueError("embedding_size is not an integer multiple of head_num!")
+        self.att_embedding_size = embedding_size // head_num
+        self.head_num = head_num
+        self.use_res = use_res
+        self.scaling = scaling
+        self.seed = seed
+        self.W_Query = nn.Parameter(torch.Tensor(embedding_size, embedding_size))
+        self.W_key = nn.Parameter(torch.Tensor(embedding_size, embedding_size))
+        self.W_Value = nn.Parameter(torch.Tensor(embedding_size, embedding_size))
+        if self.use_res:
+            self.W_Res = nn.Parameter(torch.Tensor(embedding_size, embedding_size))
+        for tensor in self.parameters():
+            nn.init.normal_(tensor, mean=0.0, std=0.05)
+        self.to(device)
+
+    def forward(self, inputs):
+        if len(inputs.shape) != 3:
+            raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
+        B, F, D = inputs.shape
+        x = inputs.reshape(B * F, D)
+        q = ops.dnn_layer(x, self.W_Query, None, "linear", w_kn=True).view(B, F, D)
+        k = ops.dnn_layer(x, self.W_key, None, "linear", w_kn=True).view(B, F, D)
+        v = ops.dnn_layer(x, self.W_Value, None, "linear", w_kn=True).view(B, F, D)
+        r = ops.dnn_layer(x, self.W_Res, None, "linear", w_kn=True).view(B, F, D) if self.use_res \
+            else torch.zeros_like(q)
+        scale = 1.0 / self.att_embedding_size ** 0.5 if self.scaling else 1.0
+        return ops.field_attention(q, k, v, r, self.head_num, scale)

@@ -37,29 +37,9 @@ from ..inputs import (DenseFeat, SparseFeat, VarLenSparseFeat, build_input_featu
 from ..layers import PredictionLayer
 
 
-def slice_arrays(arrays, start=None, stop=None):
-    """Keras-style slicing of an array or list of arrays (reference layers/utils.py:19-70)."""
-    if arrays is None:
-        return [None]
-    if isinstance(arrays, np.ndarray):
-        arrays = [arrays]
-    if isinstance(start, list) and stop is not None:
-        raise ValueError("The stop argument has to be None if the value of start is a list.")
-    if isinstance(arrays, list):
-        if hasattr(start, "__len__"):
-            if hasattr(start, "shape"):
-                start = start.tolist()
-            return [None if x is None else x[start] for x in arrays]
-        if len(arrays) == 1:
-            return arrays[0][start:stop]
-        return [None if x is None else x[start:stop] for x in arrays]
-    if hasattr(start, "__len__"):
-        if hasattr(start, "shape"):
-            start = start.tolist()
-        return arrays[start]
-    if hasattr(start, "__getitem__"):
-        return arrays[start:stop]
-    return [None]
+def _take(arrays, lo, hi):
+    """Rows [lo, hi) of every array of a feature list (what `validation_split` needs)."""
+    return [np.asarray(a)[lo:hi] for a in arrays]
 
 
 def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu"):
@@ -97,10 +77,16 @@ class Linear(nn.Module):
 
 
 class BaseModel(nn.Module):
+    # how the id cells of X are encoded: "float32" = the reference's fp32-encoded ids (exact below 2^24,
+    # models/basemodel.py:242,369); "int32" = the 4-byte cell holds the int32 id itself:
+    # `fit/predict/evaluate` pack the matrix accordingly, `forward` expects what `pack_inputs` returns.
+    id_dtype = "float32"
+
     def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5,
                  init_std=0.0001, seed=1024, task="binary", device="cpu", gpus=None, table_grad="dense"):
         super().__init__()
         torch.manual_seed(seed)
+        self.l2_reg_linear, self.l2_reg_embedding = l2_reg_linear, l2_reg_embedding
         if table_grad not in ("dense", "rowwise"):
             raise ValueError("table_grad must be 'dense' or 'rowwise'")
         self.table_grad = table_grad
@@ -152,7 +138,8 @@ class BaseModel(nn.Module):
                       c.vocabulary_size) for c in lsparse]
         dense_cols = [k for c in dense for k in range(fi[c.name][0], fi[c.name][1])]
         lin_dense_cols = [k for c in ldense for k in range(fi[c.name][0], fi[c.name][1])]
-        self._plan = ops.GatherPlan(emb_slots, lin_slots, dense_cols, lin_dense_cols, dim, device)
+        self._plan = ops.GatherPlan(emb_slots, lin_slots, dense_cols, lin_dense_cols, dim, device,
+                                    id_mode=1 if self.id_dtype == "int32" else 0)
         self._plan.varlen = varlen
         self._plan.lin_varlen = lvarlen
         self._plan.n_sparse = len(sparse)
@@ -190,7 +177,7 @@ class BaseModel(nn.Module):
                 s, e = self.feature_index[c.name]
                 lcol = self.feature_index[c.length_name][0] if c.length_name is not None else None
                 pooled.append(ops.varlen_pool(X, self.embedding_dict[c.embedding_name].weight, s, e - s,
-                                              lcol, c.combiner, plan.err_flag))
+                                              lcol, c.combiner, plan.err_flag, plan.id_mode))
             Dv = pooled[0].shape[1]
             if F0 and Dv != D:
                 raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
@@ -204,8 +191,33 @@ class BaseModel(nn.Module):
             s, e = self.feature_index[c.name]
             lcol = self.feature_index[c.length_name][0] if c.length_name is not None else None
             lin = lin + ops.varlen_pool(X, self.linear_model.embedding_dict[c.embedding_name].weight, s, e - s,
-                                        lcol, c.combiner, plan.err_flag).squeeze(1)
+                                        lcol, c.combiner, plan.err_flag, plan.id_mode).squeeze(1)
         return E, dnn_input, lin, fm, (blk if not varlen else None)
+
+    def linear_field_terms(self, X):
+        """``(L [B, n_lin] | None, dense_term [B] | None)``: the per-field linear weights ``w_f[id_f]`` of every
+        sample (IFM / DIFM multiply them by an input-aware factor before summing — the
+        ``sparse_feat_refine_weight`` branch of reference basemodel.py:82-84) and the dense part of the linear
+        logit.  One launch of the fused gather with the dim-1 tables in the embedding slots."""
+        if self.table_grad != "dense":
+            raise NotImplementedError("per-field linear terms (IFM / DIFM) need table_grad='dense'")
+        main = self._gather_plan(X.device)
+        if main.lin_varlen:
+            raise NotImplementedError("per-field linear terms with VarLenSparseFeat linear columns")
+        lp = getattr(self, "_lin_plan", None)
+        if lp is None or lp.device != X.device or lp.id_mode != main.id_mode:
+            fi = self.feature_index
+            lsparse, ldense, _ = split_columns(self.linear_feature_columns)
+            slots = [(self.linear_model.embedding_dict[c.embedding_name].weight, fi[c.name][0], c.vocabulary_size)
+                     for c in lsparse]
+            lin_dense_cols = [k for c in ldense for k in range(fi[c.name][0], fi[c.name][1])]
+            lp = ops.GatherPlan(slots, [], [], lin_dense_cols, 1, X.device, id_mode=main.id_mode)
+            lp.err_flag = main.err_flag
+            self._lin_plan = lp
+        ldw = self.linear_model.weight if lp.n_lin_dense > 0 else None
+        blk, lin, _ = ops.fused_input(X, lp, ldw, want_blk=lp.n_emb > 0, want_fm=False, grad_mode="dense")
+        L = blk[:, :lp.n_emb] if lp.n_emb > 0 else None
+        return L, (lin if ldw is not None else None)
 
     def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):
         """API-compatible view of the fused lookup (reference basemodel.py:354-380): a list of
@@ -244,13 +256,31 @@ class BaseModel(nn.Module):
                     total = total + torch.sum(l1 * torch.abs(p))
             if l2 > 0:
                 if params and params[0].is_cuda:
-                    pen = ops.l2_penalty(params, l2)
+                    # tables whose gradient is consumed row-wise by the fused optimizer contribute their VALUE
+                    # here; their L2 gradient is applied to the touched rows inside ctr_rowopt_step
+                    lazy = self._lazy_l2_ids()
+                    pen = ops.l2_penalty(params, l2, no_grad_ids=lazy)
                     if pen is not None:
                         total = total + pen
                 else:
                     for p in params:
                         total = total + torch.sum(l2 * torch.square(p))
         return total
+
+    def _lazy_l2_ids(self):
+        plan = self._plan
+        if plan is None or not (plan.keep_rowgrads or getattr(self, "sharded", None) is not None):
+            return ()
+        return set(id(p) for p in plan.emb_params + plan.lin_params)
+
+    def use_int_ids(self, on=True):
+        """Switch the id encoding of X (see `id_dtype`); rebuilds the launch metadata lazily."""
+        self.id_dtype = "int32" if on else "float32"
+        if self._plan is not None and getattr(self, "sharded", None) is None:
+            self._plan = None
+        elif self._plan is not None:
+            self._plan.id_mode = 1 if on else 0
+        return self
 
     def add_auxiliary_loss(self, aux_loss, alpha):
         self.aux_loss = aux_loss * alpha
@@ -266,12 +296,16 @@ class BaseModel(nn.Module):
 
     def _get_optim(self, optimizer):
         if isinstance(optimizer, str):
+            if self.table_grad in ("rowwise", "sharded") and torch.device(self.device).type == "cuda":
+                # tables: fused row-wise kernels on the row-gradient stream; everything else: the torch
+                # optimizer of the same family with the reference's defaults (deepctr_torch_b200/optim.py)
+                from ..optim import KINDS, RowwiseOptimizer
+                if optimizer not in KINDS:
+                    raise NotImplementedError
+                return RowwiseOptimizer(self, optimizer)
             if optimizer == "sgd":
                 return torch.optim.SGD(self.parameters(), lr=0.01)
             if optimizer == "adam":
-                if self.table_grad == "rowwise":
-                    raise NotImplementedError("torch.optim.Adam does not accept the sparse row gradients of "
-                                              "table_grad='rowwise'; use 'sgd' or 'adagrad'")
                 return torch.optim.Adam(self.parameters())
             if optimizer == "adagrad":
                 return torch.optim.Adagrad(self.parameters())
@@ -317,51 +351,155 @@ class BaseModel(nn.Module):
                 self.metrics_names.append(metric)
         return metrics_
 
-    def _to_matrix(self, x):
-        """dict / list of arrays -> ONE [N, C] array in feature_index order (reference :155-156,191-198)."""
+    # ------------------------------------------------------------------------------------------
+    # input pipeline (reference basemodel.py:191-198, 242-243: ONE [N, C] matrix per call)
+    # ------------------------------------------------------------------------------------------
+    def _id_feature_names(self):
+        names = set()
+        for c in list(self.linear_feature_columns or []) + list(self.dnn_feature_columns or []):
+            if isinstance(c, (SparseFeat, VarLenSparseFeat)):
+                names.add(c.name)
+                if isinstance(c, VarLenSparseFeat) and c.length_name is not None:
+                    names.add(c.length_name)
+        return names
+
+    def pack_inputs(self, x):
+        """dict / list of per-feature arrays -> ONE float32 ``[N, C]`` matrix in ``feature_index`` order.
+
+        ``id_dtype == "float32"``: what the reference builds (ids converted to fp32, exact below 2^24).
+        ``id_dtype == "int32"``: id cells carry the int32 id itself (bit pattern) — the matrix stays one
+        float32-typed buffer so a batch is still one contiguous H2D copy."""
         if isinstance(x, dict):
             x = [x[feature] for feature in self.feature_index]
-        x = [np.asarray(a) for a in x]
-        for i in range(len(x)):
-            if len(x[i].shape) == 1:
-                x[i] = np.expand_dims(x[i], axis=1)
-        return np.concatenate(x, axis=-1)
+        arrs = []
+        for a in x:
+            a = np.asarray(a)
+            arrs.append(a[:, None] if a.ndim == 1 else a)
+        n = arrs[0].shape[0] if arrs else 0
+        width = sum(a.shape[1] for a in arrs)
+        out = np.empty((n, width), dtype=np.float32)
+        as_int = self.id_dtype == "int32"
+        bits = out.view(np.int32)
+        id_names = self._id_feature_names() if as_int else ()
+        cursor = 0
+        names = list(self.feature_index.keys())
+        for k, a in enumerate(arrs):
+            w = a.shape[1]
+            if as_int and k < len(names) and names[k] in id_names:
+                ai = a.astype(np.int64)
+                if ai.size and (ai.min() < -2 ** 31 or ai.max() >= 2 ** 31):
+                    raise IndexError("index out of range in self (id does not fit int32)")
+                bits[:, cursor:cursor + w] = ai
+            else:
+                out[:, cursor:cursor + w] = a
+            cursor += w
+        return out
+
+    def _batches(self, X_all, y_all, batch_size, shuffle):
+        """Yield device batches (X [b, C], y) with the NEXT batch's host->device copy already in flight.
+
+        Small data sets (<= a quarter of the free HBM) are made device-resident once and batches are
+        device-side row gathers; larger ones stream through two pinned staging buffers on a copy stream
+        (the reference copies synchronously per batch, basemodel.py:242-243).  The index order is produced
+        by the same ``DataLoader(shuffle=...)`` machinery as the reference, so the RNG consumption and
+        the batch composition are identical."""
+        dev = torch.device(self.device)
+        n = X_all.shape[0]
+        order = DataLoader(Data.TensorDataset(torch.arange(n)), shuffle=shuffle, batch_size=batch_size)
+        shard = getattr(self, "sharded", None)
+
+        def my_part(idx):
+            if shard is None:
+                return idx
+            chunk = (idx.numel() + shard.plan.world - 1) // shard.plan.world
+            return idx[shard.plan.rank * chunk:(shard.plan.rank + 1) * chunk]
+
+        free, _total = torch.cuda.mem_get_info(dev)
+        resident = X_all.numel() * 4 + (y_all.numel() * 4 if y_all is not None else 0) <= free // 4
+        if resident:
+            Xd = X_all.to(dev, non_blocking=True)
+            yd = y_all.to(dev, non_blocking=True) if y_all is not None else None
+            for (idx,) in order:
+                idx = my_part(idx)
+                if not shuffle and idx.numel() > 0:
+                    lo, hi = int(idx[0]), int(idx[-1]) + 1
+                    yield Xd[lo:hi], (yd[lo:hi] if yd is not None else None)
+                else:
+                    idx_d = idx.to(dev, non_blocking=True)
+                    yield Xd.index_select(0, idx_d), (yd.index_select(0, idx_d) if yd is not None else None)
+            return
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        C = X_all.shape[1]
+        ywidth = tuple(y_all.shape[1:]) if y_all is not None else ()
+        stage = [(torch.empty(batch_size, C).pin_memory(), torch.empty((batch_size,) + ywidth).pin_memory())
+                 for _ in range(2)]
+        devbuf = [(torch.empty(batch_size, C, device=dev), torch.empty((batch_size,) + ywidth, device=dev))
+                  for _ in range(2)]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in consumed:
+            e.record(cur)
+
+        def enqueue(k, idx):
+            m = idx.numel()
+            copied[k].synchronize()              # the previous H2D out of this staging buffer has finished
+            torch.index_select(X_all, 0, idx, out=stage[k][0][:m])
+            if y_all is not None:
+                torch.index_select(y_all, 0, idx, out=stage[k][1][:m])
+            copy_stream.wait_event(consumed[k])  # the step that read devbuf[k] has finished
+            with torch.cuda.stream(copy_stream):
+                devbuf[k][0][:m].copy_(stage[k][0][:m], non_blocking=True)
+                if y_all is not None:
+                    devbuf[k][1][:m].copy_(stage[k][1][:m], non_blocking=True)
+                copied[k].record(copy_stream)
+            return m
+
+        it = iter(order)
+        k = 0
+        nxt = next(it, None)
+        m_next = enqueue(k, my_part(nxt[0])) if nxt is not None else 0
+        while nxt is not None:
+            m, kk = m_next, k
+            nxt = next(it, None)
+            if nxt is not None:
+                k ^= 1
+                m_next = enqueue(k, my_part(nxt[0]))
+            cur.wait_event(copied[kk])
+            yield devbuf[kk][0][:m], (devbuf[kk][1][:m] if y_all is not None else None)
+            consumed[kk].record(cur)
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, initial_epoch=0, validation_split=0.,
             validation_data=None, shuffle=True, callbacks=None):
+        """Keras-style training loop with the reference's arguments, log keys and History
+        (reference basemodel.py:137-309).  Differences, all on the input/bookkeeping side:
+        batches are prefetched, the epoch loss is accumulated on the device and read once per epoch, the
+        per-batch training metrics are computed at the end of the epoch from predictions kept on the
+        device, and out-of-range ids are reported once per epoch."""
         if isinstance(x, dict):
             x = [x[feature] for feature in self.feature_index]
-        do_validation = False
+        val_x, val_y = [], []
         if validation_data:
-            do_validation = True
-            if len(validation_data) == 2:
-                val_x, val_y = validation_data
-            elif len(validation_data) == 3:
-                val_x, val_y, _ = validation_data
-            else:
+            if len(validation_data) not in (2, 3):
                 raise ValueError("When passing a `validation_data` argument, it must contain either 2 items "
                                  "(x_val, y_val), or 3 items (x_val, y_val, val_sample_weights). "
                                  "However we received `validation_data=%s`" % (validation_data,))
-            if isinstance(val_x, dict):
-                val_x = [val_x[feature] for feature in self.feature_index]
+            val_x, val_y = validation_data[0], validation_data[1]
         elif validation_split and 0. < validation_split < 1.:
-            do_validation = True
-            n0 = x[0].shape[0] if hasattr(x[0], "shape") else len(x[0])
-            split_at = int(n0 * (1. - validation_split))
-            x, val_x = slice_arrays(x, 0, split_at), slice_arrays(x, split_at)
-            y, val_y = slice_arrays(y, 0, split_at), slice_arrays(y, split_at)
-        else:
-            val_x, val_y = [], []
-        X_all = torch.from_numpy(self._to_matrix(x))
-        y_all = torch.from_numpy(np.asarray(y))
-        train_tensor_data = Data.TensorDataset(X_all, y_all)
-        if batch_size is None:
-            batch_size = 256
+            n0 = len(x[0])
+            cut = int(n0 * (1. - validation_split))
+            x, val_x = _take(x, 0, cut), _take(x, cut, n0)
+            y, val_y = np.asarray(y)[:cut], np.asarray(y)[cut:]
+        do_validation = len(val_y) > 0
+        X_all = torch.from_numpy(self.pack_inputs(x))
+        y_all = torch.from_numpy(np.asarray(y)).float()
+        batch_size = 256 if batch_size is None else batch_size
+        sample_num = X_all.shape[0]
+        steps_per_epoch = (sample_num - 1) // batch_size + 1
         model = self.train()
         loss_func, optim = self.loss_func, self.optim
-        train_loader = DataLoader(dataset=train_tensor_data, shuffle=shuffle, batch_size=batch_size)
-        sample_num = len(train_tensor_data)
-        steps_per_epoch = (sample_num - 1) // batch_size + 1
+        shard = getattr(self, "sharded", None)
+        dev = torch.device(self.device)
 
         callbacks = CallbackList((callbacks or []) + [self.history])
         callbacks.set_model(self)
@@ -369,19 +507,16 @@ class BaseModel(nn.Module):
         self.stop_training = False
         if verbose:
             print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(
-                len(train_tensor_data), len(val_y), steps_per_epoch))
+                sample_num, len(val_y), steps_per_epoch))
         for epoch in range(initial_epoch, epochs):
             callbacks.on_epoch_begin(epoch)
-            epoch_logs = {}
             start_time = time.time()
-            total_loss_epoch = 0.0
-            train_result = {}
-            it = enumerate(train_loader)
-            bar = tqdm(it, disable=verbose != 1) if tqdm is not None else it
+            loss_acc = torch.zeros((), device=dev)
+            kept = []
+            batches = self._batches(X_all, y_all, batch_size, shuffle)
+            bar = tqdm(batches, total=steps_per_epoch, disable=verbose != 1) if tqdm is not None else batches
             try:
-                for _, (x_train, y_train) in bar:
-                    xb = x_train.to(self.device).float()
-                    yb = y_train.to(self.device).float()
+                for xb, yb in bar:
                     y_pred = model(xb).squeeze()
                     optim.zero_grad()
                     if isinstance(loss_func, list):
@@ -389,34 +524,46 @@ class BaseModel(nn.Module):
                                    for i in range(self.num_tasks))
                     else:
                         loss = loss_func(y_pred, yb.squeeze(), reduction="sum")
-                    total_loss = loss + self.get_regularization_loss() + self.aux_loss
-                    total_loss_epoch += total_loss.item()      # host sync, as in the reference (:259)
-                    self.check_ids()
-                    total_loss.backward()
+                    if shard is None:
+                        total_loss = loss + self.get_regularization_loss() + self.aux_loss
+                        total_loss.backward()
+                    else:
+                        # data term first; its dense gradients are summed over the ranks, then the
+                        # (replicated) regulariser adds its gradient once
+                        loss.backward()
+                        shard.finish_step()
+                        reg = self.get_regularization_loss() + self.aux_loss
+                        if reg.requires_grad:
+                            reg.sum().backward()
+                        total_loss = loss + reg
+                    loss_acc += total_loss.detach().sum()
                     optim.step()
-                    if verbose > 0:
-                        for name, metric_fun in self.metrics.items():
-                            train_result.setdefault(name, []).append(metric_fun(
-                                yb.cpu().data.numpy(), y_pred.cpu().data.numpy().astype("float64")))
+                    if verbose > 0 and self.metrics:
+                        kept.append((yb.detach(), y_pred.detach()))
             finally:
                 if tqdm is not None:
                     bar.close()
-            epoch_logs["loss"] = total_loss_epoch / sample_num
-            for name, result in train_result.items():
-                epoch_logs[name] = np.sum(result) / steps_per_epoch
+            if shard is not None:
+                torch.distributed.all_reduce(loss_acc, group=shard.group)
+            self.check_ids()
+            epoch_logs = {"loss": float(loss_acc.item()) / sample_num}      # the only host sync of the epoch
+            if kept:
+                host = [(t.cpu().numpy(), p.cpu().numpy().astype("float64")) for t, p in kept]
+                for name, metric_fun in self.metrics.items():
+                    epoch_logs[name] = np.sum([metric_fun(t, p) for t, p in host]) / steps_per_epoch
             if do_validation:
                 for name, result in self.evaluate(val_x, val_y, batch_size).items():
                     epoch_logs["val_" + name] = result
             if verbose > 0:
-                epoch_time = int(time.time() - start_time)
-                print("Epoch {0}/{1}".format(epoch + 1, epochs))
-                eval_str = "{0}s - loss: {1: .4f}".format(epoch_time, epoch_logs["loss"])
+                msg = "{0}s - loss: {1: .4f}".format(int(time.time() - start_time), epoch_logs["loss"])
                 for name in self.metrics:
-                    eval_str += " - " + name + ": {0: .4f}".format(epoch_logs[name])
+                    if name in epoch_logs:
+                        msg += " - " + name + ": {0: .4f}".format(epoch_logs[name])
                 if do_validation:
                     for name in self.metrics:
-                        eval_str += " - val_" + name + ": {0: .4f}".format(epoch_logs["val_" + name])
-                print(eval_str)
+                        msg += " - val_" + name + ": {0: .4f}".format(epoch_logs["val_" + name])
+                print("Epoch {0}/{1}".format(epoch + 1, epochs))
+                print(msg)
             callbacks.on_epoch_end(epoch, epoch_logs)
             if self.stop_training:
                 break
@@ -428,16 +575,22 @@ class BaseModel(nn.Module):
         return {name: metric_fun(y, pred_ans) for name, metric_fun in self.metrics.items()}
 
     def predict(self, x, batch_size=256):
+        """float64 ``[N, 1]`` predictions (reference basemodel.py:325-352); results stay on the device until
+        the last batch, one device->host copy at the end."""
         model = self.eval()
-        tensor_data = Data.TensorDataset(torch.from_numpy(self._to_matrix(x)))
-        test_loader = DataLoader(dataset=tensor_data, shuffle=False, batch_size=batch_size)
-        pred_ans = []
+        X_all = torch.from_numpy(self.pack_inputs(x))
+        shard, self_sharded = getattr(self, "sharded", None), None
+        if shard is not None:
+            raise NotImplementedError("predict() on a row-sharded model: gather the tables with "
+                                      "sharded.gather_full_state_dict and predict on one GPU")
+        outs = []
         with torch.no_grad():
-            for _, x_test in enumerate(test_loader):
-                xb = x_test[0].to(self.device).float()
-                pred_ans.append(model(xb).cpu().data.numpy())
-                self.check_ids()
-        return np.concatenate(pred_ans).astype("float64")
+            for xb, _ in self._batches(X_all, None, batch_size, False):
+                outs.append(model(xb))
+        self.check_ids()
+        if not outs:
+            return np.zeros((0, 1), dtype="float64")
+        return torch.cat(outs).cpu().numpy().astype("float64")
 
     def make_graphed_step(self, batch_size, loss_fn=None, with_reg=False):
         """One forward+loss+backward captured as a CUDA graph (see deepctr_torch_b200.graph)."""
@@ -452,6 +605,7 @@ class BaseModel(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_plan"] = None      # device-side launch metadata is rebuilt lazily after unpickling
+        state["_lin_plan"] = None
         return state
 
     @property

@@ -7,6 +7,7 @@ stock-torch fallback: a non-CUDA tensor raises ``RuntimeError``.
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import torch
 
@@ -23,6 +24,31 @@ def _ptr(t):
 
 def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_device(args):
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        if isinstance(a, (list, tuple)):
+            d = _first_cuda_device(a)
+            if d is not None:
+                return d
+    return None
+
+
+def _on_device(fn):
+    """Run an autograd forward/backward with the CUDA device of its tensor arguments current: the C ABI
+    launches on cudaGetDevice()'s device and `_stream()` is that device's current stream, so a model built
+    on cuda:1 (the reference API accepts any device string) must not launch on device 0."""
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        dev = _first_cuda_device(args)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapped
 
 
 def _require_cuda(t, what):
@@ -50,6 +76,7 @@ def _round4(n):
 # ----------------------------------------------------------------------------------------------
 _scratch_buf = {}
 _scratch_need = {}
+_scratch_retired = []      # outgrown buffers stay alive: a captured CUDA graph may still address them
 
 
 def ensure_gemm_scratch(dev, B, K, N):
@@ -64,6 +91,8 @@ def ensure_gemm_scratch(dev, B, K, N):
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     buf = _scratch_buf.get(idx)
     if buf is None or buf.numel() < need:
+        if buf is not None:
+            _scratch_retired.append(buf)
         buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=dev)
         _scratch_buf[idx] = buf
         with torch.cuda.device(idx):
@@ -75,6 +104,8 @@ def ensure_scratch_bytes(dev, need):
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     buf = _scratch_buf.get(idx)
     if buf is None or buf.numel() < need:
+        if buf is not None:
+            _scratch_retired.append(buf)
         buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=dev)
         _scratch_buf[idx] = buf
         with torch.cuda.device(idx):
@@ -91,14 +122,32 @@ def act_code(name):
 # ----------------------------------------------------------------------------------------------
 # fused input: gather + linear + FM + dnn_input assembly
 # ----------------------------------------------------------------------------------------------
+class _WsLease:
+    """One unique-plan workspace checked out of a GatherPlan's pool.  It returns to the pool when the last
+    holder (the autograd node of the forward that built the plan, or the optimizer that still has to consume
+    the row gradients) lets go of it — never while a backward may still read it."""
+    __slots__ = ("plan", "ws")
+
+    def __init__(self, plan, ws):
+        self.plan, self.ws = plan, ws
+
+    def __del__(self):
+        try:
+            self.plan._ws_free.setdefault(self.ws["B"], []).append(self.ws)
+        except Exception:       # interpreter shutdown
+            pass
+
+
 class GatherPlan:
     """Device-side slot metadata for one model (built once, refreshed if storages move).
 
     emb / lin: lists of (parameter, X column, vocab, plan column) per field; dense_cols: X columns
-    copied behind the embedding block; lin_dense_cols: X columns of Linear's dense weight."""
+    copied behind the embedding block; lin_dense_cols: X columns of Linear's dense weight.
+    id_mode: how the id cells of X are encoded (include/ctr_b200.h: CTR_IDS_F32 / CTR_IDS_I32BITS)."""
 
-    def __init__(self, emb_slots, lin_slots, dense_cols, lin_dense_cols, dim, device):
+    def __init__(self, emb_slots, lin_slots, dense_cols, lin_dense_cols, dim, device, id_mode=0):
         self.device = torch.device(device)
+        self.id_mode = int(id_mode)
         self.emb_params = [s[0] for s in emb_slots]
         self.lin_params = [s[0] for s in lin_slots]
         self.n_emb, self.n_lin = len(emb_slots), len(lin_slots)
@@ -124,13 +173,19 @@ class GatherPlan:
             vocab_of[s[1]] = max(vocab_of.get(s[1], 0), s[2])
         self.plan_cols = torch.tensor(plan_cols, **i32)
         self.plan_vocab = torch.tensor([vocab_of[c] for c in plan_cols], **i32)
-        self.emb_plan_col = torch.tensor([plan_cols.index(s[1]) for s in emb_slots], **i32)
-        self.lin_plan_col = torch.tensor([plan_cols.index(s[1]) for s in lin_slots], **i32)
+        self.emb_plan_col_host = [plan_cols.index(s[1]) for s in emb_slots]
+        self.lin_plan_col_host = [plan_cols.index(s[1]) for s in lin_slots]
+        self.emb_plan_col = torch.tensor(self.emb_plan_col_host, **i32)
+        self.lin_plan_col = torch.tensor(self.lin_plan_col_host, **i32)
         self.err_flag = torch.zeros(1, **i32)
         self.n_shards = 1
         self._ptr_key = None
         self._emb_ptrs = self._lin_ptrs = None
-        self._ws = {}
+        self._ws_free = {}
+        # set by optim.RowwiseOptimizer: the backward parks (lease, rg_emb, rg_lin, n_emb) in `pending`
+        # for the fused optimizer kernels instead of handing sparse COO gradients to autograd
+        self.keep_rowgrads = False
+        self.pending = []
 
     def table_ptrs(self):
         key = tuple(p.data_ptr() for p in self.emb_params) + tuple(p.data_ptr() for p in self.lin_params)
@@ -141,33 +196,54 @@ class GatherPlan:
             self._ptr_key = key
         return self._emb_ptrs, self._lin_ptrs
 
-    def workspace(self, B):
-        """Buffers of the row-wise backward for batch size B (cached)."""
-        ws = self._ws.get(B)
-        if ws is None:
-            n = len(self.plan_cols_host)
-            H = int(_lib.load().ctr_unique_plan_hash_slots(B))
-            i32 = dict(dtype=torch.int32, device=self.device)
-            ws = {"H": H, "keys": torch.empty(n * H, **i32), "vals": torch.empty(n * H, **i32),
-                  "n_uniq": torch.empty(n, **i32), "uniq": torch.empty(n, B, **i32),
-                  "inv": torch.empty(B, n, **i32), "cnt": torch.empty(n, B, **i32)}
-            self._ws = {B: ws}
-        return ws
+    def alloc_workspace(self, B, n_cols=None):
+        n = len(self.plan_cols_host) if n_cols is None else n_cols
+        H = int(_lib.load().ctr_unique_plan_hash_slots(B))
+        i32 = dict(dtype=torch.int32, device=self.device)
+        return {"B": B, "H": H, "keys": torch.empty(n * H, **i32), "vals": torch.empty(n * H, **i32),
+                "n_uniq": torch.empty(n, **i32), "uniq": torch.empty(n, B, **i32),
+                "inv": torch.empty(B, n, **i32), "cnt": torch.empty(n, B, **i32)}
+
+    def lease_workspace(self, B):
+        """Buffers of one row-wise backward for batch size B, owned by the caller until the lease dies
+        (two grad-enabled forwards before a backward therefore never share a plan)."""
+        free = self._ws_free.get(B)
+        ws = free.pop() if free else self.alloc_workspace(B)
+        return _WsLease(self, ws)
 
     def side_stream(self):
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def build_unique_plan(self, X, B, ws):
+        _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, len(self.plan_cols_host),
+                  _ptr(self.plan_cols), _ptr(self.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]),
+                  ws["H"], _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                  _ptr(self.err_flag), self.id_mode, None, _stream())
+
     def check_ids(self):
         """Raise IndexError (like nn.Embedding on CPU) if any id was out of range.  Synchronises."""
-        if int(self.err_flag.item()) != 0:
+        flag = int(self.err_flag.item())
+        if flag != 0:
             self.err_flag.zero_()
-            raise IndexError("index out of range in self (sparse feature id outside [0, vocabulary_size))")
+            if flag & 1:
+                raise IndexError("index out of range in self (sparse feature id outside [0, vocabulary_size))")
+            raise RuntimeError("deepctr_torch_b200: an exchange / receive list of the row-sharded tables overflowed "
+                               "(err_flag=%d); raise the batch capacity passed to sharded.attach_shards" % flag)
+
+
+def _dev_ptr_table(ptrs, dev):
+    """Device array of pointers written by a kernel from by-value arguments (capturable in a CUDA graph)."""
+    out = torch.empty(max(len(ptrs), 1), dtype=torch.int64, device=dev)
+    arr = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
+    _lib.call("ctr_write_ptrs", arr, len(ptrs), _ptr(out), _stream())
+    return out
 
 
 class _FusedInput(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, X, plan, lin_dense_w, want_blk, want_fm, grad_mode, *tables):
         _require_cuda(X, "X")
         X = _rowmajor(X)
@@ -175,7 +251,7 @@ class _FusedInput(torch.autograd.Function):
         dev = X.device
         emb_ptrs, lin_ptrs = plan.table_ptrs()
         blk = torch.empty(B, plan.ld, device=dev, dtype=torch.float32) if want_blk else None
-        lin =torch.empty(B, device=dev, dtype=torch.float32)
+        lin = torch.empty(B, device=dev, dtype=torch.float32)
         fm = torch.empty(B, device=dev, dtype=torch.float32) if want_fm else None
         n_emb = plan.n_emb if (want_blk or want_fm) else 0
         if plan.n_shards > 1 and getattr(plan, "exchange", False) and B > 0:
@@ -188,7 +264,8 @@ class _FusedInput(torch.autograd.Function):
                       plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
                       _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
                       plan.n_shards, plan.rank, _ptr(where), len(plan.plan_cols_host), _ptr(plan.emb_plan_col),
-                      _ptr(plan.lin_plan_col), _ptr(plan.x_resp_emb_local), _ptr(plan.x_resp_lin_local), _stream())
+                      _ptr(plan.lin_plan_col), _ptr(plan.x_resp_emb_local), _ptr(plan.x_resp_lin_local),
+                      plan.id_mode, _stream())
         else:
             _lib.call("ctr_gather_fwd", _ptr(X), X.stride(0), B,
                       n_emb, plan.D, _ptr(emb_ptrs), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
@@ -196,20 +273,20 @@ class _FusedInput(torch.autograd.Function):
                       plan.n_dense if want_blk else 0, _ptr(plan.dense_cols),
                       plan.n_lin_dense if lin_dense_w is not None else 0, _ptr(plan.lin_dense_cols),
                       _ptr(lin_dense_w), _ptr(blk), plan.ld, _ptr(lin), _ptr(fm), _ptr(plan.err_flag),
-                      plan.n_shards, _stream())
+                      plan.n_shards, plan.id_mode, _stream())
         ctx.plan_event = None
+        ctx.lease = None
         if grad_mode in ("rowwise", "sharded") and torch.is_grad_enabled() and B > 0:
             # the duplicate-free plan of the backward depends only on X: build it now on a side stream
-            # so that it overlaps the forward tower instead of sitting on the backward's critical path
-            ws = plan.workspace(B)
+            # so that it overlaps the forward tower instead of sitting on the backward's critical path.
+            # The workspace belongs to THIS autograd node (a second forward must not overwrite it).
+            ctx.lease = plan.lease_workspace(B)
             side = plan.side_stream()
             cur = torch.cuda.current_stream(dev)
             side.wait_stream(cur)
+            X.record_stream(side)
             with torch.cuda.stream(side):
-                _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, len(plan.plan_cols_host),
-                          _ptr(plan.plan_cols), _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]),
-                          ws["H"], _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
-                          _ptr(plan.err_flag), _stream())
+                plan.build_unique_plan(X, B, ctx.lease.ws)
                 ctx.plan_event = torch.cuda.Event()
                 ctx.plan_event.record(side)
         ctx.plan, ctx.grad_mode = plan, grad_mode
@@ -225,6 +302,7 @@ class _FusedInput(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_blk, d_lin, d_fm):
         plan = ctx.plan
         X, blk = ctx.saved_tensors
@@ -246,67 +324,62 @@ class _FusedInput(torch.autograd.Function):
         d_fm = d_fm.contiguous() if d_fm is not None else None
         emb_live = plan.n_emb > 0 and (d_blk is not None or d_fm is not None)
         n_emb = plan.n_emb if emb_live else 0
-        i64 = dict(dtype=torch.int64, device=dev)
-        grads_emb, grads_lin = [], []
-        if ctx.grad_mode == "dense":
-            grads_emb = [torch.zeros_like(p) for p in plan.emb_params] if emb_live else [None] * plan.n_emb
-            grads_lin = [torch.zeros_like(p) for p in plan.lin_params]
-            eg = torch.tensor([g.data_ptr() for g in grads_emb], **i64) if emb_live else None
-            lg = torch.tensor([g.data_ptr() for g in grads_lin], **i64)
-            _lib.call("ctr_scatter_bwd_dense", _ptr(X), X.stride(0), B,
-                      n_emb, plan.D, _ptr(eg), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
-                      plan.n_lin, _ptr(lg), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
-                      _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
-                      _ptr(d_fm), _ptr(d_lin), _stream())
-        else:  # row-wise: (unique ids, summed row grads) per table, returned as sparse COO
-            ws = plan.workspace(B)
-            n_plan = len(plan.plan_cols_host)
-            if ctx.plan_event is not None:
-                torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
-            else:
-                _lib.call("ctr_unique_plan", _ptr(X), X.stride(0), B, n_plan, _ptr(plan.plan_cols),
-                          _ptr(plan.plan_vocab), _ptr(ws["keys"]), _ptr(ws["vals"]), ws["H"],
-                          _ptr(ws["n_uniq"]), _ptr(ws["uniq"]), _ptr(ws["inv"]), _ptr(ws["cnt"]),
-                          _ptr(plan.err_flag), _stream())
-            rg_emb = torch.empty(max(n_emb, 1), B, max(plan.D, 1), device=dev, dtype=torch.float32)
-            rg_lin = torch.empty(max(plan.n_lin, 1), B, device=dev, dtype=torch.float32)
-            _lib.call("ctr_scatter_bwd_rowwise", B, n_plan, _ptr(ws["inv"]), _ptr(ws["cnt"]),
-                      _ptr(ws["n_uniq"]), n_emb, plan.D, _ptr(rg_emb), B * max(plan.D, 1),
-                      _ptr(plan.emb_plan_col), plan.n_lin, _ptr(rg_lin), B, _ptr(plan.lin_plan_col),
-                      _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
-                      _ptr(d_fm), _ptr(d_lin), _stream())
-            if ctx.grad_mode == "sharded":
-                # deliver every unique (row, gradient) to the rank that owns the row (csrc/p2p.cu);
-                # table gradients then live in the owners' receive lists, not in autograd
-                from . import sharded
-                sharded.push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb)
-                grads_emb = [None] * plan.n_emb
-                grads_lin = [None] * plan.n_lin
-                d_ldw = None
-                if ctx.has_ldw:
-                    d_ldw = torch.empty(plan.n_lin_dense, 1, device=dev, dtype=torch.float32)
-                    _lib.call("ctr_lin_dense_wgrad", _ptr(X), X.stride(0), B, plan.n_lin_dense,
-                              _ptr(plan.lin_dense_cols), _ptr(d_lin), _ptr(d_ldw), _stream())
-                return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
-            uniq = ws["uniq"].to(torch.int64)
-            emb_pc = plan.emb_plan_col.tolist() if not hasattr(plan, "_emb_pc") else plan._emb_pc
-            lin_pc = plan.lin_plan_col.tolist() if not hasattr(plan, "_lin_pc") else plan._lin_pc
-            plan._emb_pc, plan._lin_pc = emb_pc, lin_pc
-            for f, p in enumerate(plan.emb_params):
-                if not emb_live:
-                    grads_emb.append(None)
-                    continue
-                grads_emb.append(torch.sparse_coo_tensor(uniq[emb_pc[f]].unsqueeze(0), rg_emb[f],
-                                                         size=p.shape, check_invariants=False))
-            for f, p in enumerate(plan.lin_params):
-                grads_lin.append(torch.sparse_coo_tensor(uniq[lin_pc[f]].unsqueeze(0),
-                                                         rg_lin[f].unsqueeze(1), size=p.shape,
-                                                         check_invariants=False))
+        grads_emb, grads_lin = [None] * plan.n_emb, [None] * plan.n_lin
         d_ldw = None
         if ctx.has_ldw:
             d_ldw = torch.empty(plan.n_lin_dense, 1, device=dev, dtype=torch.float32)
             _lib.call("ctr_lin_dense_wgrad", _ptr(X), X.stride(0), B, plan.n_lin_dense,
                       _ptr(plan.lin_dense_cols), _ptr(d_lin), _ptr(d_ldw), _stream())
+        if B == 0:
+            if ctx.grad_mode == "dense":
+                grads_emb = [torch.zeros_like(p) for p in plan.emb_params]
+                grads_lin = [torch.zeros_like(p) for p in plan.lin_params]
+            return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
+        if ctx.grad_mode == "dense":
+            grads_emb = [torch.zeros_like(p) for p in plan.emb_params] if emb_live else [None] * plan.n_emb
+            grads_lin = [torch.zeros_like(p) for p in plan.lin_params]
+            eg = _dev_ptr_table([g.data_ptr() for g in grads_emb], dev) if emb_live else None
+            lg = _dev_ptr_table([g.data_ptr() for g in grads_lin], dev)
+            _lib.call("ctr_scatter_bwd_dense", _ptr(X), X.stride(0), B,
+                      n_emb, plan.D, _ptr(eg), _ptr(plan.emb_cols), _ptr(plan.emb_vocab),
+                      plan.n_lin, _ptr(lg), _ptr(plan.lin_cols), _ptr(plan.lin_vocab),
+                      _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
+                      _ptr(d_fm), _ptr(d_lin), plan.id_mode, _stream())
+            return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
+        # row-wise: (unique ids, summed row grads) per table
+        lease = ctx.lease
+        n_plan = len(plan.plan_cols_host)
+        if lease is not None:
+            torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+        else:                       # the forward ran without grad mode bookkeeping: build the plan here
+            lease = plan.lease_workspace(B)
+            plan.build_unique_plan(X, B, lease.ws)
+        ws = lease.ws
+        rg_emb = torch.empty(max(n_emb, 1), B, max(plan.D, 1), device=dev, dtype=torch.float32)
+        rg_lin = torch.empty(max(plan.n_lin, 1), B, device=dev, dtype=torch.float32)
+        _lib.call("ctr_scatter_bwd_rowwise", B, n_plan, _ptr(ws["inv"]), _ptr(ws["cnt"]),
+                  _ptr(ws["n_uniq"]), n_emb, plan.D, _ptr(rg_emb), B * max(plan.D, 1),
+                  _ptr(plan.emb_plan_col), plan.n_lin, _ptr(rg_lin), B, _ptr(plan.lin_plan_col),
+                  _ptr(blk), plan.ld, _ptr(d_blk), d_blk.stride(0) if d_blk is not None else 0,
+                  _ptr(d_fm), _ptr(d_lin), _stream())
+        if ctx.grad_mode == "sharded":
+            # deliver every unique (row, gradient) to the rank that owns the row (csrc/p2p.cu);
+            # table gradients then live in the owners' receive lists, not in autograd
+            from . import sharded
+            sharded.push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb)
+        elif plan.keep_rowgrads:
+            # consumed in place by the fused row-wise optimizer (optim.RowwiseOptimizer.step)
+            plan.pending.append((lease, rg_emb, rg_lin, n_emb))
+        else:                       # hand autograd padded sparse COO gradients (any torch optimizer that takes them)
+            uniq = ws["uniq"].to(torch.int64)
+            for f, p in enumerate(plan.emb_params):
+                if emb_live:
+                    grads_emb[f] = torch.sparse_coo_tensor(uniq[plan.emb_plan_col_host[f]].unsqueeze(0), rg_emb[f],
+                                                           size=p.shape, check_invariants=False)
+            for f, p in enumerate(plan.lin_params):
+                grads_lin[f] = torch.sparse_coo_tensor(uniq[plan.lin_plan_col_host[f]].unsqueeze(0),
+                                                       rg_lin[f].unsqueeze(1), size=p.shape,
+                                                       check_invariants=False)
         # a table shared by several fields appears several times in `tables`; autograd sums them
         return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
 
@@ -323,6 +396,7 @@ def fused_input(X, plan, lin_dense_w, want_blk=True, want_fm=False, grad_mode="d
 # ----------------------------------------------------------------------------------------------
 class _FM(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, E):
         _require_cuda(E, "FM input")
         B, F, D = E.shape
@@ -335,6 +409,7 @@ class _FM(torch.autograd.Function):
         return out.unsqueeze(1)
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         (E2,) = ctx.saved_tensors
         B, F, D = ctx.shape
@@ -353,6 +428,7 @@ def fm(E):
 # ----------------------------------------------------------------------------------------------
 class _DnnLayer(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, W, bias, act, w_kn):
         """w_kn: W is stored [K, N] (CrossNetMix factors) instead of nn.Linear's [N, K]."""
         _require_cuda(x, "DNN input")
@@ -382,6 +458,7 @@ class _DnnLayer(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x, Wc, y = ctx.saved_tensors
         B, K = x.shape
@@ -418,6 +495,7 @@ class _DnnTower(torch.autograd.Function):
     activation mask, and no dY (.) act'(Y) product is ever re-derived from two tensors."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, act, *params):
         _require_cuda(x, "DNN input")
         x = _rowmajor(x)
@@ -448,6 +526,7 @@ class _DnnTower(torch.autograd.Function):
         return cur
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         L = ctx.L
         saved = ctx.saved_tensors
@@ -488,6 +567,7 @@ def dnn_tower(x, act, weights, biases):
 
 class _RowDot(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, H, w):
         _require_cuda(H, "row-dot input")
         H = _rowmajor(H)
@@ -500,6 +580,7 @@ class _RowDot(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         H, wv = ctx.saved_tensors
         B, N = H.shape
@@ -519,6 +600,7 @@ def rowdot(H, w):
 
 class _Predict(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, bias, binary, *terms):
         terms = [t.reshape(-1).contiguous() for t in terms]
         _require_cuda(terms[0], "logit term")
@@ -532,6 +614,7 @@ class _Predict(torch.autograd.Function):
         return y.unsqueeze(1)
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
         B = y.shape[0]
@@ -555,6 +638,7 @@ def predict(terms, bias, binary=True):
 # ----------------------------------------------------------------------------------------------
 class _CIN(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, E, act, split_half, layer_size, *params):
         """E [B,M,D] (any batch stride); params = (W0, b0, W1, b1, ...) with W [N, H*M, 1]."""
         _require_cuda(E, "CIN input")
@@ -595,6 +679,7 @@ class _CIN(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         B, M, D, total = ctx.dims
         plan = ctx.plan
@@ -636,6 +721,7 @@ def cin(E, layer_size, split_half, act, params):
 # ----------------------------------------------------------------------------------------------
 class _CrossVector(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, kernels, bias):
         _require_cuda(x, "CrossNet input")
         x = _rowmajor(x)
@@ -652,6 +738,7 @@ class _CrossVector(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         x, kv, bv, s = ctx.saved_tensors
         B, n = x.shape
@@ -668,6 +755,7 @@ class _CrossVector(torch.autograd.Function):
 
 class _CrossMatrix(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, kernels, bias):
         _require_cuda(x, "CrossNet input")
         x = _rowmajor(x)
@@ -690,6 +778,7 @@ class _CrossMatrix(torch.autograd.Function):
         return xs[-1] if L > 0 else x.clone()
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         L = ctx.L
         saved = ctx.saved_tensors
@@ -726,6 +815,7 @@ class _CrossMixCombine(torch.autograd.Function):
     """x_{l+1} = sum_e softmax(gate)_e * x0 (.) (uv_e + bias) + x_l  (one layer)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x0, xl, uv, gate, bias):
         E, B, n = uv.shape
         x0, xl = _rowmajor(x0), _rowmajor(xl)
@@ -739,6 +829,7 @@ class _CrossMixCombine(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         x0, uv, gate, bv = ctx.saved_tensors
         E, B, n = uv.shape
@@ -761,6 +852,7 @@ def cross_mix_combine(x0, xl, uv, gate, bias):
 # ----------------------------------------------------------------------------------------------
 class _SENET(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, E, W1, W2):
         _require_cuda(E, "SENET input")
         B, F, D = E.shape
@@ -775,6 +867,7 @@ class _SENET(torch.autograd.Function):
         return V
 
     @staticmethod
+    @_on_device
     def backward(ctx, dV):
         E, W1c, W2c = ctx.saved_tensors
         B, F, D = E.shape
@@ -796,6 +889,7 @@ BILINEAR_SEL = {"all": 0, "each": 1, "interaction": 2}
 
 class _Bilinear(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, E, W, wsel):
         """E [B,F,D]; W [n_w, D, D] stacked weights; returns [B, P, D]."""
         _require_cuda(E, "bilinear input")
@@ -813,6 +907,7 @@ class _Bilinear(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         E, Wc = ctx.saved_tensors
         B, F, D = E.shape
@@ -837,40 +932,43 @@ POOL_MODES = {"sum": 0, "mean": 1, "max": 2}
 
 class _VarlenPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, X, table, col, T, len_col, mode, err_flag):
+    @_on_device
+    def forward(ctx, X, table, col, T, len_col, mode, err_flag, id_mode):
         _require_cuda(X, "X")
         X = _rowmajor(X)
         B = X.shape[0]
         V, D = table.shape
         out = torch.empty(B, D, device=X.device, dtype=torch.float32)
         _lib.call("ctr_varlen_pool_fwd", _ptr(X), X.stride(0), B, col, T, len_col, _ptr(table), V, D,
-                  mode, _ptr(out), D, _ptr(err_flag), _stream())
-        ctx.args = (col, T, len_col, mode)
+                  mode, _ptr(out), D, _ptr(err_flag), id_mode, _stream())
+        ctx.args = (col, T, len_col, mode, id_mode)
         ctx.save_for_backward(X, table)
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         X, table = ctx.saved_tensors
-        col, T, len_col, mode = ctx.args
+        col, T, len_col, mode, id_mode = ctx.args
         V, D = table.shape
         dout = dout.contiguous()
         dtable = torch.zeros_like(table)
         _lib.call("ctr_varlen_pool_bwd", _ptr(X), X.stride(0), X.shape[0], col, T, len_col, _ptr(table),
-                  V, D, mode, _ptr(dout), D, _ptr(dtable), _stream())
-        return None, dtable, None, None, None, None, None
+                  V, D, mode, _ptr(dout), D, _ptr(dtable), id_mode, _stream())
+        return None, dtable, None, None, None, None, None, None
 
 
-def varlen_pool(X, table, col, maxlen, len_col, combiner, err_flag):
+def varlen_pool(X, table, col, maxlen, len_col, combiner, err_flag, id_mode=0):
     if combiner not in POOL_MODES:
         raise ValueError("parameter mode should in [sum, mean, max]")
     return _VarlenPool.apply(X, table, int(col), int(maxlen), -1 if len_col is None else int(len_col),
-                             POOL_MODES[combiner], err_flag)
+                             POOL_MODES[combiner], err_flag, int(id_mode))
 
 
 class _SumSq(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scale, *weights):
+    @_on_device
+    def forward(ctx, scale, no_grad_ids, *weights):
         dev = weights[0].device
         out = torch.zeros(1, device=dev, dtype=torch.float32)
         for w in weights:
@@ -878,18 +976,175 @@ class _SumSq(torch.autograd.Function):
             wc = w if w.is_contiguous() else w.contiguous()
             _lib.call("ctr_sumsq_acc", _ptr(wc), wc.numel(), float(scale), _ptr(out), _stream())
         ctx.scale = float(scale)
+        ctx.skip = [id(w) in no_grad_ids for w in weights]
         ctx.save_for_backward(*weights)
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         # d/dw (scale * sum w^2) = 2*scale*w — elementwise scaling of parameters already resident
-        return (None,) + tuple(w * (2.0 * ctx.scale * g) for w in ctx.saved_tensors)
+        return (None, None) + tuple(None if skip else w * (2.0 * ctx.scale * g)
+                                    for w, skip in zip(ctx.saved_tensors, ctx.skip))
 
 
-def l2_penalty(weights, scale):
-    """scale * sum_w sum(w^2) via the streaming sum-of-squares kernel (basemodel.py:412-428)."""
+def l2_penalty(weights, scale, no_grad_ids=()):
+    """scale * sum_w sum(w^2) via the streaming sum-of-squares kernel (basemodel.py:412-428).
+    Parameters whose id() is in no_grad_ids contribute their value but receive no gradient here (the
+    fused row-wise optimizer applies their L2 term to the rows it touches)."""
     weights = [w for w in weights if w.numel() > 0]
     if not weights or scale == 0:
         return None
-    return _SumSq.apply(scale, *weights)
+    return _SumSq.apply(scale, no_grad_ids, *weights)
+
+
+# ----------------------------------------------------------------------------------------------
+# adjacent models (SURVEY §8 f4): bi-interaction pooling, input-aware refinement, AFM attention
+# ----------------------------------------------------------------------------------------------
+def _block3(E):
+    B, F, D = E.shape
+    if E.stride(2) != 1 or E.stride(1) != D:
+        E = E.contiguous()
+    return E
+
+
+class _BiPool(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, E):
+        _require_cuda(E, "BiInteractionPooling input")
+        E = _block3(E)
+        B, F, D = E.shape
+        out = torch.empty(B, D, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_bipool_fwd", _ptr(E), E.stride(0), F, D, _ptr(out), D, B, _stream())
+        ctx.save_for_backward(E)
+        return out.unsqueeze(1)
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        (E,) = ctx.saved_tensors
+        B, F, D = E.shape
+        g = g.reshape(B, D).contiguous()
+        dE = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_bipool_bwd", _ptr(E), E.stride(0), F, D, _ptr(g), D, _ptr(dE), F * D, B, _stream())
+        return dE
+
+
+def bi_interaction_pooling(E):
+    """[B,F,D] -> [B,1,D] (reference layers/interaction.py:54-61)."""
+    return _BiPool.apply(E)
+
+
+class _Refine(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, P, E, L, softmax):
+        _require_cuda(P, "refine factor")
+        E = _block3(E)
+        B, F, D = E.shape
+        P = P.contiguous()
+        Lc = L.contiguous() if L is not None else None
+        m = torch.empty(B, F, device=E.device, dtype=torch.float32)
+        Er = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        lin = torch.empty(B, device=E.device, dtype=torch.float32) if Lc is not None else None
+        _lib.call("ctr_refine_fwd", _ptr(P), _ptr(E), E.stride(0), _ptr(Lc), F, D, 1 if softmax else 0, _ptr(m),
+                  _ptr(Er), F * D, _ptr(lin), B, _stream())
+        ctx.softmax, ctx.has_L = softmax, Lc is not None
+        ctx.save_for_backward(m, E, Lc if Lc is not None else m.new_empty(0))
+        if lin is None:
+            lin = m.new_empty(0)
+            ctx.mark_non_differentiable(lin)
+        return Er, lin
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dEr, dlin):
+        m, E, L = ctx.saved_tensors
+        B, F, D = E.shape
+        L = L if ctx.has_L else None
+        dEr = dEr.contiguous() if dEr is not None else None
+        dlin = dlin.contiguous() if (dlin is not None and ctx.has_L) else None
+        dP = torch.empty(B, F, device=E.device, dtype=torch.float32)
+        dE = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        dL = torch.empty(B, F, device=E.device, dtype=torch.float32) if L is not None else None
+        _lib.call("ctr_refine_bwd", _ptr(m), _ptr(E), E.stride(0), _ptr(L if dlin is not None else None), F, D,
+                  1 if ctx.softmax else 0, _ptr(dEr), F * D, _ptr(dlin), _ptr(dP), _ptr(dE), F * D,
+                  _ptr(dL if dlin is not None else None), B, _stream())
+        if dL is not None and dlin is None:
+            dL.zero_()
+        return dP, dE, dL, None
+
+
+def refine(P, E, L=None, softmax=True):
+    """(Er [B,F,D], lin [B] | None): input-aware re-weighting of IFM (softmax=True: m = F*softmax(P)) and
+    DIFM (softmax=False: m = P); L [B,F] = the sample's per-field linear weights."""
+    Er, lin = _Refine.apply(P, E, L, bool(softmax))
+    return Er, (lin if L is not None else None)
+
+
+class _AFM(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, E, W, b, h):
+        _require_cuda(E, "AFM input")
+        E = _block3(E)
+        B, F, D = E.shape
+        Wc, bc, hc = W.contiguous(), b.contiguous(), h.reshape(-1).contiguous()
+        A = Wc.shape[1]
+        out = torch.empty(B, D, device=E.device, dtype=torch.float32)
+        _lib.call("ctr_afm_fwd", _ptr(E), E.stride(0), F, D, A, _ptr(Wc), _ptr(bc), _ptr(hc), _ptr(out), B, _stream())
+        ctx.save_for_backward(E, Wc, bc, hc)
+        ctx.shapes = (W.shape, b.shape, h.shape)
+        return out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        E, Wc, bc, hc = ctx.saved_tensors
+        B, F, D = E.shape
+        A = Wc.shape[1]
+        g = g.contiguous()
+        dE = torch.empty(B, F, D, device=E.device, dtype=torch.float32)
+        dW, db, dh = (torch.empty_like(t) for t in (Wc, bc, hc))
+        _lib.call("ctr_afm_bwd", _ptr(E), E.stride(0), F, D, A, _ptr(Wc), _ptr(bc), _ptr(hc), _ptr(g),
+                  _ptr(dE), F * D, _ptr(dW), _ptr(db), _ptr(dh), B, _stream())
+        s = ctx.shapes
+        return dE, dW.view(s[0]), db.view(s[1]), dh.view(s[2])
+
+
+def afm_attention(E, attention_W, attention_b, projection_h):
+    """[B,F,D] -> attention output [B,D] (reference layers/interaction.py:307-326; the caller applies the
+    dropout and the projection p)."""
+    return _AFM.apply(E, attention_W, attention_b, projection_h)
+
+
+class _FieldAttn(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, Q, K, V, R, heads, scale):
+        _require_cuda(Q, "attention input")
+        Q, K, V, R = (t.contiguous() for t in (Q, K, V, R))
+        B, F, D = Q.shape
+        Y = torch.empty_like(Q)
+        _lib.call("ctr_fieldattn_fwd", _ptr(Q), _ptr(K), _ptr(V), _ptr(R), F, D, heads, ctypes.c_float(scale), _ptr(Y), B,
+                  _stream())
+        ctx.heads, ctx.scale = heads, scale
+        ctx.save_for_backward(Q, K, V, Y)
+        return Y
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dY):
+        Q, K, V, Y = ctx.saved_tensors
+        B, F, D = Q.shape
+        dY = dY.contiguous()
+        dQ, dK, dV, dR = (torch.empty_like(Q) for _ in range(4))
+        _lib.call("ctr_fieldattn_bwd", _ptr(Q), _ptr(K), _ptr(V), _ptr(Y), _ptr(dY), F, D, ctx.heads,
+                  ctypes.c_float(ctx.scale), _ptr(dQ), _ptr(dK), _ptr(dV), _ptr(dR), B, _stream())
+        return dQ, dK, dV, dR, None, None
+
+
+def field_attention(Q, K, V, R, heads, scale):
+    """relu(multi-head softmax(QK^T * scale) V + R) over the field axis, all [B,F,D]."""
+    return _FieldAttn.apply(Q, K, V, R, int(heads), float(scale))

@@ -80,11 +80,10 @@ class ArenaLayout:
                               "emb": take(max(self.n_emb, 1) * self.cap * dim * 4),
                               "lin": take(max(self.n_lin, 1) * self.cap * 4)})
         # forward exchange (ctr_shard_request / ctr_shard_serve): request lists and response rows, one slice
-        # per peer.  Capacity per peer: every id of the batch for G <= 2, twice the uniform share beyond
-        # (overflow raises through the error flag rather than corrupting memory)
+        # per peer, sized for the worst case (every id of the batch owned by one peer): about 1 GB per rank at
+        # BASELINE config #5, nothing on a 180 GB part, and a skewed id distribution can never overflow
         n_cols = n_id_cols if n_id_cols is not None else max(self.n_emb, self.n_lin, 1)
-        full = batch * n_cols
-        self.xcap = full if world <= 2 else min(full, 2 * ((full + world - 1) // world))
+        self.xcap = batch * n_cols
         self.x = {"req_cnt": take(world * 4), "req": take(world * self.xcap * 8),
                   "resp_emb": take(world * self.xcap * max(dim, 1) * 4), "resp_lin": take(world * self.xcap * 4)}
         self.nbytes = cursor
@@ -244,7 +243,8 @@ class ShardedPlan(ops.GatherPlan):
             self._x_where = {B: where}
         _lib.call("ctr_shard_request", ops._ptr(X), X.stride(0), B, len(self.plan_cols_host), ops._ptr(self.plan_cols),
                   ops._ptr(self.plan_vocab), self.world, self.rank, ops._ptr(self.x_cnt_to), ops._ptr(self.x_inbox_req),
-                  ops._ptr(self.x_inbox_cnt), ops._ptr(where), self.x_cap, ops._ptr(self.err_flag), ops._stream())
+                  ops._ptr(self.x_inbox_cnt), ops._ptr(where), self.x_cap, ops._ptr(self.err_flag), self.id_mode,
+                  ops._stream())
         dist.all_reduce(self.x_token, group=group)        # every request list is complete
         _lib.call("ctr_shard_serve", self.world, self.rank, self.D, ctypes.c_void_p(self.x_req_cnt), ctypes.c_void_p(self.x_req),
                   self.x_cap, ops._ptr(self.x_emb_of_col), ops._ptr(self.x_lin_of_col), ops._ptr(self.x_resp_emb_remote),
@@ -277,17 +277,21 @@ def push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb):
 
 
 class ShardedRuntime:
-    """Attached to a model as ``model.sharded``: dense-gradient all-reduce and step bookkeeping."""
+    """Attached to a model as ``model.sharded``: dense-gradient all-reduce, owner-side combine of the
+    received row gradients and step bookkeeping."""
 
     def __init__(self, model, plan, group=None):
         self.model, self.plan, self.group = model, plan, group
         table_ids = set(id(p) for p in plan.emb_params + plan.lin_params)
         self.dense_params = [p for p in model.parameters() if id(p) not in table_ids]
+        self.last_done = None          # parity of the receive lists completed by the last finish_step()
+        self._cws = None
 
     def finish_step(self):
         """All-reduce the replicated parameters' gradients (this also orders every rank's
-        ``ctr_rowgrad_push`` before any owner reads its receive list), then flip the parity and
-        clear the list that peers will fill two steps from now."""
+        ``ctr_rowgrad_push`` before any owner reads its receive list), then flip the parity.  The
+        completed lists stay readable (``received_row_grads`` / ``combine_received``) until
+        ``clear_received`` — the fused optimizer consumes them in ``optim.step()``."""
         grads = [p.grad for p in self.dense_params if p.grad is not None]
         if grads:
             flat = torch.cat([g.reshape(-1) for g in grads])
@@ -301,6 +305,7 @@ class ShardedRuntime:
             dist.barrier(group=self.group)
         done = self.plan.step_parity
         self.plan.step_parity ^= 1
+        self.last_done = done
         return done
 
     def received_row_grads(self, parity):
@@ -309,6 +314,59 @@ class ShardedRuntime:
 
     def clear_received(self, parity):
         self.plan.recv_views(parity)[0].zero_()
+
+    def _combine_workspace(self):
+        if self._cws is None:
+            plan, L = self.plan, self.plan.layout
+            nf = L.n_emb + L.n_lin
+            dev = plan.device
+            ws = plan.alloc_workspace(L.cap, n_cols=max(nf, 1))
+            i32 = dict(dtype=torch.int32, device=dev)
+            ws["cols"] = torch.arange(max(nf, 1), **i32) * L.cap           # field f's ids start at f * cap
+            ws["vocab"] = torch.tensor((L.emb_rows + L.lin_rows) or [1], **i32)
+            ws["emb_pc"] = torch.arange(max(L.n_emb, 1), **i32)
+            ws["lin_pc"] = torch.arange(max(L.n_lin, 1), **i32) + L.n_emb
+            ws["comb_emb"] = torch.empty(max(L.n_emb, 1), L.cap, max(L.D, 1), device=dev)
+            ws["comb_lin"] = torch.empty(max(L.n_lin, 1), L.cap, device=dev)
+            self._cws = ws
+        return self._cws
+
+    def combine_received(self, parity):
+        """Owner side of the backward: up to G senders deliver a gradient for the same
+        local row; build a duplicate-free plan over each field's receive list and sum the duplicates.
+        Returns the workspace: ``n_uniq [nf]``, ``uniq [nf, cap]`` (local rows), ``comb_emb [n_emb, cap, D]``,
+        ``comb_lin [n_lin, cap]`` — the same (uniq, rowgrad) contract as the single-GPU backward."""
+        plan, L = self.plan, self.plan.layout
+        ws = self._combine_workspace()
+        counts, ids, emb, lin = plan.recv_views(parity)
+        nf = L.n_emb + L.n_lin
+        if nf == 0:
+            return ws
+        _lib.call("ctr_unique_plan", ops._ptr(ids.view(torch.float32)), 1, L.cap, nf, ops._ptr(ws["cols"]),
+                  ops._ptr(ws["vocab"]), ops._ptr(ws["keys"]), ops._ptr(ws["vals"]), ws["H"], ops._ptr(ws["n_uniq"]),
+                  ops._ptr(ws["uniq"]), ops._ptr(ws["inv"]), ops._ptr(ws["cnt"]), ops._ptr(plan.err_flag), 1,
+                  ops._ptr(counts), ops._stream())
+        if L.n_emb:
+            _lib.call("ctr_rowgrad_combine", L.cap, L.n_emb, L.D, ops._ptr(counts), ops._ptr(ws["n_uniq"]),
+                      ops._ptr(ws["inv"]), nf, ops._ptr(ws["emb_pc"]), ops._ptr(emb), L.cap * L.D,
+                      ops._ptr(ws["comb_emb"]), L.cap * L.D, ops._stream())
+        if L.n_lin:
+            _lib.call("ctr_rowgrad_combine", L.cap, L.n_lin, 1, ops._ptr(counts[L.n_emb:]), ops._ptr(ws["n_uniq"]),
+                      ops._ptr(ws["inv"]), nf, ops._ptr(ws["lin_pc"]), ops._ptr(lin), L.cap,
+                      ops._ptr(ws["comb_lin"]), L.cap, ops._stream())
+        return ws
+
+    def apply_received(self, optimizer):
+        """Called by ``RowwiseOptimizer.step``: combine the lists of the last finished step, update the
+        local shards with the fused optimizer kernels, release the lists."""
+        if self.last_done is None:
+            return
+        L = self.plan.layout
+        ws = self.combine_received(self.last_done)
+        optimizer.apply_rows(L.cap, ws["n_uniq"], ws["uniq"], ws["comb_emb"], ws["comb_lin"], L.n_emb,
+                             emb_plan_col=ws["emb_pc"], lin_plan_col=ws["lin_pc"])
+        self.clear_received(self.last_done)
+        self.last_done = None
 
 
 def localize_cfg(cfg, world):
@@ -369,7 +427,8 @@ def attach_shards(model, logical_cfg, rank, world, batch, group=None):
     emb_slots = [(model.embedding_dict[c.embedding_name].weight, fi[c.name][0], logical[c.name]) for c in sparse]
     lin_slots = [(model.linear_model.embedding_dict[c.embedding_name].weight, fi[c.name][0], logical[c.name])
                  for c in lsparse]
-    plan = ShardedPlan(emb_slots, lin_slots, base.dense_cols.tolist(), base.lin_dense_cols.tolist(), D, dev)
+    plan = ShardedPlan(emb_slots, lin_slots, base.dense_cols.tolist(), base.lin_dense_cols.tolist(), D, dev,
+                       id_mode=base.id_mode)
     plan.varlen, plan.lin_varlen, plan.n_sparse = [], [], len(sparse)
     plan.setup_shards(arena, layout, rank, world, emb_vocab, lin_vocab)
     model._plan = plan

@@ -12,9 +12,13 @@
  *  - the library never allocates, frees or synchronises; launches are asynchronous on `stream`.
  *  - return value: 0 = OK, <0 = argument error, >0 = cudaError_t.  `ctr_last_error()` returns a
  *    thread-local message for the last non-zero return on this thread.
- *  - ids travel as fp32 inside X (reference models/basemodel.py:242,369) and are decoded by
- *    truncation exactly like `.long()`.  Out-of-range ids set bit 0 of `*err_flag` (the reference
- *    raises IndexError on CPU); the row is then read from id 0 so no memory is touched out of bounds.
+ *  - ids travel inside X, one 4-byte cell per id.  `id_mode` says how a cell is read:
+ *      CTR_IDS_F32     (0) fp32-encoded integers (reference models/basemodel.py:242,369), decoded by
+ *                          truncation exactly like `.long()` — exact only below 2^24;
+ *      CTR_IDS_I32BITS (1) the cell holds the int32 id itself (bit pattern of an int32 stored in the
+ *                          fp32 matrix) — any id below 2^31, no float round trip.
+ *    Out-of-range ids set bit 0 of `*err_flag` (the reference raises IndexError on CPU); the row is
+ *    then read from id 0 so no memory is touched out of bounds.
  *  - "pointer arrays" (`const float* const*`) are DEVICE arrays of device pointers.
  */
 #ifndef CTR_B200_H_
@@ -27,13 +31,14 @@ extern "C" {
 #endif
 
 /* ---- library ---------------------------------------------------------------------------- */
-int         ctr_version(void);            /* ABI version, currently 1 */
+int         ctr_version(void);            /* ABI version, currently 2 */
 const char* ctr_last_error(void);
 int         ctr_debug_set_buffer(void* dev_u64_buffer);   /* optional: per-stage clock64 timeline of the tensor-core GEMM (>= 256 u64), NULL = off */
 int64_t     ctr_launch_count(void);       /* kernels launched by this library so far (process-wide) */
 
 /* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
-enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3 };
+enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3, CTR_ACT_PRELU = 4 };
+enum { CTR_IDS_F32 = 0, CTR_IDS_I32BITS = 1 };
 
 /* ---- a4+a5+a6+a7: fused multi-slot gather + linear term + FM + dnn_input assembly --------
  * replaces: BaseModel.input_from_feature_columns  models/basemodel.py:354-380
@@ -57,7 +62,7 @@ int ctr_gather_fwd(const float* X, int64_t ldx, int64_t B,
                    int n_dense, const int32_t* dense_cols,
                    int n_lin_dense, const int32_t* lin_dense_cols, const float* lin_dense_w,
                    float* blk, int64_t ld_blk, float* lin, float* fm,
-                   int32_t* err_flag, int n_shards, void* stream);
+                   int32_t* err_flag, int n_shards, int id_mode, void* stream);
 
 /* FM on an already assembled block (used when pooled VarLen fields were added to it).
  * replaces FM.forward layers/interaction.py:26-34.  E = blk viewed as [B, F, D], row stride ld. */
@@ -83,7 +88,11 @@ int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B,
                           const int32_t* lin_vocab,
                           const float* blk, int64_t ld_blk,
                           const float* d_blk, int64_t ld_dblk,
-                          const float* g_fm, const float* g_lin, void* stream);
+                          const float* g_fm, const float* g_lin, int id_mode, void* stream);
+
+/* device pointer table for the calls above, written by a kernel from by-value arguments (so it can be
+ * recorded into a CUDA graph; a host->device copy of a Python list cannot): dev_out[i] = ptrs[i], n <= 4096 */
+int ctr_write_ptrs(const void* const* host_ptrs, int n, void** dev_out, void* stream);
 
 /* (2) row-wise mode (B200-native): per id column a duplicate-free list of touched rows.
  *   ctr_unique_plan  : for each of n_cols id columns builds, with an open-addressing hash table
@@ -93,7 +102,9 @@ int ctr_scatter_bwd_dense(const float* X, int64_t ldx, int64_t B,
  *                        cnt [c*B + u]   = multiplicity of that id in the batch
  *                      hash_keys/hash_vals: int32 [n_cols*H] scratch, n_uniq: int32 [n_cols];
  *                      all three are (re)initialised inside.  Entries u >= n_uniq[c] get
- *                      uniq = 0, cnt = 0.
+ *                      uniq = 0, cnt = 0.  col_count (may be NULL): int32 [n_cols], only the first
+ *                      col_count[c] entries of column c exist (ragged receive lists, see
+ *                      ctr_rowgrad_combine).
  *   ctr_scatter_bwd_rowwise: field f writes the [B, D] buffer at emb_rowgrad + f*emb_rowgrad_stride
  *                      (linear field f the [B] buffer at lin_rowgrad + f*lin_rowgrad_stride);
  *                      row u of field f receives the summed gradient of uniq id u of the plan
@@ -104,7 +115,7 @@ int64_t ctr_unique_plan_hash_slots(int64_t B);
 int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
                     const int32_t* vocab, int32_t* hash_keys, int32_t* hash_vals, int64_t H,
                     int32_t* n_uniq, int32_t* uniq, int32_t* inv, int32_t* cnt,
-                    int32_t* err_flag, void* stream);
+                    int32_t* err_flag, int id_mode, const int32_t* col_count, void* stream);
 int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv, const int32_t* cnt,
                             const int32_t* n_uniq,
                             int n_emb, int D, float* emb_rowgrad, int64_t emb_rowgrad_stride,
@@ -160,7 +171,7 @@ int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32
 int ctr_shard_request(const float* X, int64_t ldx, int64_t B, int n_cols, const int32_t* cols,
                       const int32_t* vocab, int n_shards, int rank, int32_t* cnt_to,
                       int32_t* const* inbox_req, int32_t* const* inbox_cnt, int32_t* where,
-                      int64_t cap, int32_t* err_flag, void* stream);
+                      int64_t cap, int32_t* err_flag, int id_mode, void* stream);
 int ctr_shard_serve(int n_shards, int rank, int D, const int32_t* req_cnt, const int32_t* req, int64_t cap,
                     const float* const* emb_of_col, const float* const* lin_of_col,
                     float* const* resp_emb, float* const* resp_lin, void* stream);
@@ -173,7 +184,8 @@ int ctr_gather_fwd_exchanged(const float* X, int64_t ldx, int64_t B, int n_emb, 
                              int64_t ld_blk, float* lin, float* fm, int32_t* err_flag,
                              int n_shards, int rank, const int32_t* where, int n_plan,
                              const int32_t* emb_plan_col, const int32_t* lin_plan_col,
-                             const float* const* resp_emb, const float* const* resp_lin, void* stream);
+                             const float* const* resp_emb, const float* const* resp_lin, int id_mode,
+                             void* stream);
 
 /* gradient of Linear's dense weight: dw[k] = sum_b g[b] * X[b, cols[k]]   (basemodel.py:88-90) */
 int ctr_lin_dense_wgrad(const float* X, int64_t ldx, int64_t B, int n, const int32_t* cols,
@@ -339,10 +351,76 @@ int ctr_sumsq_acc(const float* w, int64_t n, float scale, float* out, void* stre
  * bwd (dense-compat): atomically adds into the caller-zeroed dense gradient table. */
 int ctr_varlen_pool_fwd(const float* X, int64_t ldx, int64_t B, int col, int T, int len_col,
                         const float* table, int vocab, int D, int mode,
-                        float* dst, int64_t ld, int32_t* err_flag, void* stream);
+                        float* dst, int64_t ld, int32_t* err_flag, int id_mode, void* stream);
 int ctr_varlen_pool_bwd(const float* X, int64_t ldx, int64_t B, int col, int T, int len_col,
                         const float* table, int vocab, int D, int mode,
-                        const float* ddst, int64_t ld, float* dtable, void* stream);
+                        const float* ddst, int64_t ld, float* dtable, int id_mode, void* stream);
+
+/* ---- f2: fused row-wise optimizer on the row-gradient stream ------------------------------
+ * replaces: optim.step() + the embedding part of get_regularization_loss().backward()
+ *           (reference models/basemodel.py:262, 412-428, 447-461) for the tables, consuming the
+ *           (uniq, rowgrad) pairs of ctr_scatter_bwd_rowwise in place — no dense [V,D] gradient, no
+ *           sparse-COO hop.  Only rows that occur in the batch are touched ("lazy" semantics: identical
+ *           to the dense torch optimizer for sgd / adagrad at l2 = 0, to torch.optim.SparseAdam-style
+ *           row-wise moments for adam / rmsprop; L2 is applied to the touched rows as g += l2x2 * w).
+ *   hp (device, 8 floats, written by ctr_rowopt_tick so that a captured CUDA graph sees fresh values):
+ *      [0] step  [1] lr  [2] beta1 (rmsprop: alpha)  [3] beta2  [4] eps  [5] 1-beta1^step  [6] 1-beta2^step
+ *   ctr_rowopt_tick : step += 1 and refresh the bias corrections (one thread).
+ *   ctr_rowopt_step : for field f < n_fields and u < n_uniq[plan_col[f]]:
+ *        id = uniq[plan_col[f]*cap + u],  g = rowgrad[f*rowgrad_stride + u*D ..] + l2x2 * w
+ *        kind 0 sgd     : w -= lr * g
+ *        kind 1 adagrad : s1 += g^2;  w -= lr * g / (sqrt(s1) + eps)
+ *        kind 2 adam    : s1 = b1*s1 + (1-b1) g;  s2 = b2*s2 + (1-b2) g^2;
+ *                         w -= (lr / bc1) * s1 / (sqrt(s2) / sqrt(bc2) + eps)       (torch.optim.Adam)
+ *        kind 3 rmsprop : s1 = a*s1 + (1-a) g^2;  w -= lr * g / (sqrt(s1) + eps)
+ *      tables / state1 / state2: device arrays of n_fields pointers to [V_f, D] tensors (state unused by
+ *      the kind may be NULL).  row_div > 1: the tables are row shards, row = id (ids are already local).
+ *   ctr_rowgrad_combine : owner side of the sharded backward: sums the received
+ *        (row, gradient) pairs of field f that share a row, using a unique plan built over the receive
+ *        list (ctr_unique_plan with col_count): out[f][inv[b, f]] += recv[f][b] for b < count[f].
+ *        The rows u < n_uniq[plan_col[f]] of out are zeroed inside (n_uniq: the plan's distinct-row counts).
+ */
+enum { CTR_OPT_SGD = 0, CTR_OPT_ADAGRAD = 1, CTR_OPT_ADAM = 2, CTR_OPT_RMSPROP = 3 };
+int ctr_rowopt_tick(float* hp, void* stream);
+int ctr_rowopt_step(int kind, int64_t cap, const int32_t* n_uniq, const int32_t* uniq,
+                    int n_fields, int D, const float* rowgrad, int64_t rowgrad_stride,
+                    const int32_t* plan_col, float* const* tables, float* const* state1,
+                    float* const* state2, const float* hp, float l2x2, void* stream);
+int ctr_rowgrad_combine(int64_t cap, int n_fields, int D, const int32_t* count, const int32_t* n_uniq,
+                        const int32_t* inv, int n_plan_cols, const int32_t* plan_col, const float* recv,
+                        int64_t recv_stride, float* out, int64_t out_stride, void* stream);
+
+/* ---- f4: interaction ops of the adjacent models (WDL / NFM / AFM / IFM / DIFM reuse everything above)
+ * ctr_bipool_*  : BiInteractionPooling, reference layers/interaction.py:54-61:
+ *                 out[b,d] = 0.5 * ((sum_f E[b,f,d])^2 - sum_f E[b,f,d]^2);  bwd writes dE[b,f,d] = g[b,d] * (S[b,d] - E[b,f,d])
+ * ctr_refine_*  : input-aware re-weighting, reference models/ifm.py:83-88, models/difm.py:104-109 and the
+ *                 sparse_feat_refine_weight branch of Linear.forward (models/basemodel.py:82-84):
+ *                 m = softmax ? F * softmax_f(P) : P;  Er[b,f,:] = m[b,f] * E[b,f,:];  lin[b] = sum_f m[b,f] * L[b,f]
+ *                 (L = per-field linear weights of the sample, may be NULL; lin may be NULL).
+ *                 bwd: dP (through the softmax when set), dE = dEr * m, dL = dlin * m.
+ * ctr_afm_*     : AFMLayer, reference layers/interaction.py:250-331 (pairs in itertools.combinations order):
+ *                 out[b,:] = sum_pairs softmax_pairs(h . relu(W^T (e_i*e_j) + b)) (e_i*e_j)   ([B,D]: the attention
+ *                 output; dropout and the projection p are applied by the caller);  W [D,A], b [A], h [A].
+ *                 bwd (g = d out [B,D]) zero-fills and accumulates dW/db/dh, writes dE.
+ * ctr_fieldattn_*: the attention core of InteractingLayer (reference layers/interaction.py:372-392, used by DIFM):
+ *                 Y[b,i,:] = relu(concat_heads(softmax_j(Q_i . K_j * scale) V_j) + R[b,i,:]);  Q, K, V, R, Y: [B, F, D]
+ *                 contiguous (the four projections are GEMMs on the [B*F, D] view); bwd writes dQ, dK, dV, dR. */
+int ctr_fieldattn_fwd(const float* Q, const float* K, const float* V, const float* R, int F, int D, int H,
+                      float scale, float* Y, int64_t B, void* stream);
+int ctr_fieldattn_bwd(const float* Q, const float* K, const float* V, const float* Y, const float* dY, int F, int D,
+                      int H, float scale, float* dQ, float* dK, float* dV, float* dR, int64_t B, void* stream);
+int ctr_bipool_fwd(const float* E, int64_t se, int F, int D, float* out, int64_t so, int64_t B, void* stream);
+int ctr_bipool_bwd(const float* E, int64_t se, int F, int D, const float* g, int64_t sg, float* dE, int64_t sde,
+                   int64_t B, void* stream);
+int ctr_refine_fwd(const float* P, const float* E, int64_t se, const float* L, int F, int D, int softmax, float* m,
+                   float* Er, int64_t ser, float* lin, int64_t B, void* stream);
+int ctr_refine_bwd(const float* m, const float* E, int64_t se, const float* L, int F, int D, int softmax,
+                   const float* dEr, int64_t sder, const float* dlin, float* dP, float* dE, int64_t sde,
+                   float* dL, int64_t B, void* stream);
+int ctr_afm_fwd(const float* E, int64_t se, int F, int D, int A, const float* W, const float* b, const float* h,
+                float* out, int64_t B, void* stream);
+int ctr_afm_bwd(const float* E, int64_t se, int F, int D, int A, const float* W, const float* b, const float* h,
+                const float* g, float* dE, int64_t sde, float* dW, float* db, float* dh, int64_t B, void* stream);
 
 #ifdef __cplusplus
 }

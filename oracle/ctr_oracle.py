@@ -179,6 +179,51 @@ def fm(E):
     return 0.5 * (s * s - (E * E).sum(dim=1)).sum(dim=1, keepdim=True)
 
 
+def bi_interaction(E):
+    """0.5 ((Σ_f e)^2 − Σ_f e^2) keeping the embedding axis — restates reference
+    layers/interaction.py:54-61.  E [B,F,D] -> [B,1,D]."""
+    s = E.sum(dim=1, keepdim=True)
+    return 0.5 * (s * s - (E * E).sum(dim=1, keepdim=True))
+
+
+def afm_layer(params, prefix, rows):
+    """Attentional FM — restates reference layers/interaction.py:307-331 (dropout 0).
+    rows: list of F tensors [B,D] -> [B,1]."""
+    W, b = params[prefix + "attention_W"], params[prefix + "attention_b"]
+    h, p = params[prefix + "projection_h"], params[prefix + "projection_p"]
+    left, right = [], []
+    for r, c in itertools.combinations(rows, 2):
+        left.append(r.unsqueeze(1))
+        right.append(c.unsqueeze(1))
+    ip = torch.cat(left, dim=1) * torch.cat(right, dim=1)                      # [B,P,D]
+    att = torch.relu(torch.tensordot(ip, W, dims=([-1], [0])) + b)
+    score = torch.softmax(torch.tensordot(att, h, dims=([-1], [0])), dim=1)    # [B,P,1]
+    out = (score * ip).sum(dim=1)
+    return torch.tensordot(out, p, dims=([-1], [0]))
+
+
+def interacting_layer(params, prefix, E, head_num, use_res=True, scaling=True):
+    """Multi-head self-attention over the fields + residual + relu — restates reference
+    layers/interaction.py:352-394 (AutoInt's InteractingLayer as used by DIFM).  E [B,F,D]."""
+    D = E.shape[-1]
+    dh = D // head_num
+    q = torch.tensordot(E, params[prefix + "W_Query"], dims=([-1], [0]))
+    k = torch.tensordot(E, params[prefix + "W_key"], dims=([-1], [0]))
+    v = torch.tensordot(E, params[prefix + "W_Value"], dims=([-1], [0]))
+    q = torch.stack(torch.split(q, dh, dim=2))
+    k = torch.stack(torch.split(k, dh, dim=2))
+    v = torch.stack(torch.split(v, dh, dim=2))
+    ip = torch.einsum("bnik,bnjk->bnij", q, k)
+    if scaling:
+        ip = ip / dh ** 0.5
+    att = torch.softmax(ip, dim=-1)
+    res = torch.matmul(att, v)
+    res = torch.cat(torch.split(res, 1), dim=-1).squeeze(0)
+    if use_res:
+        res = res + torch.tensordot(E, params[prefix + "W_Res"], dims=([-1], [0]))
+    return torch.relu(res)
+
+
 def _activation(name, x):
     name = (name or "linear").lower()
     if name == "relu":
@@ -371,6 +416,39 @@ def model_logit(cfg, params, X):
             logit = logit + F.linear(dnn(params, "dnn.", x, act), params["dnn_linear.weight"])
         elif cross_num > 0:
             logit = logit + F.linear(cross(x), params["dnn_linear.weight"])
+    elif model == "WDL":
+        # restates reference models/wdl.py:62-78
+        logit = lin
+        if has_dnn_cols and len(hidden) > 0:
+            h = dnn(params, "dnn.", combined_dnn_input(rows, dvals, dt), act)
+            logit = logit + F.linear(h, params["dnn_linear.weight"])
+    elif model == "NFM":
+        # restates reference models/nfm.py:62-80 (bi_dropout = 0)
+        bi = bi_interaction(torch.stack(rows, dim=1))[:, 0]
+        h = dnn(params, "dnn.", combined_dnn_input([bi], dvals, dt), act)
+        logit = lin + F.linear(h, params["dnn_linear.weight"])
+    elif model == "AFM":
+        # restates reference models/afm.py:55-70
+        logit = lin
+        if rows:
+            if kw.get("use_attention", True):
+                logit = logit + afm_layer(params, "fm.", rows)
+            else:
+                logit = logit + fm(torch.stack(rows, dim=1))
+    elif model in ("IFM", "DIFM"):
+        # restates reference models/ifm.py:69-91 and models/difm.py:82-112
+        E = torch.stack(rows, dim=1)
+        nf = len(rows)
+        flat = combined_dnn_input(rows, [], dt)
+        if model == "IFM":
+            h = dnn(params, "factor_estimating_net.", flat, act)
+            m = nf * torch.softmax(F.linear(h, params["transform_weight_matrix_P.weight"]), dim=1)
+        else:
+            att = interacting_layer(params, "vector_wise_net.", E, kw.get("att_head_num", 4), kw.get("att_res", True))
+            m_vec = F.linear(att.reshape(att.shape[0], -1), params["transform_matrix_P_vec.weight"])
+            m_bit = F.linear(dnn(params, "bit_wise_net.", flat, act), params["transform_matrix_P_bit.weight"])
+            m = m_vec + m_bit
+        logit = linear_logit(params, Xd, cfg, findex, refine_weight=m) + fm(E * m.unsqueeze(-1))
     else:
         raise NotImplementedError(model)
     return logit + params["out.bias"]
@@ -400,7 +478,16 @@ def regularization_loss(cfg, params):
     base_l2_lin = 1e-5 if model in ("DCN", "DCNMix") else kw.get("l2_reg_linear", 1e-5)
     add([k for k in params if k.startswith("linear_model.")], base_l2_lin)
     dnn_w = [k for k in params if k.startswith("dnn.") and "weight" in k and "bn" not in k]
-    if model in ("DeepFM", "xDeepFM") and "dnn_linear.weight" in params:
+    if model == "AFM" and kw.get("use_attention", True):
+        add(["fm.attention_W"], kw.get("l2_reg_att", 1e-5))
+    if model == "IFM":
+        add([k for k in params if k.startswith("factor_estimating_net.") and "weight" in k and "bn" not in k] +
+            ["transform_weight_matrix_P.weight"], kw.get("l2_reg_dnn", 0))
+    if model == "DIFM":
+        add([k for k in params if (k.startswith("vector_wise_net.") or k.startswith("bit_wise_net.")) and
+             "weight" in k and "bn" not in k] + ["transform_matrix_P_vec.weight", "transform_matrix_P_bit.weight"],
+            kw.get("l2_reg_dnn", 0))
+    if model in ("DeepFM", "xDeepFM", "WDL", "NFM") and "dnn_linear.weight" in params:
         add(dnn_w, kw.get("l2_reg_dnn", 0))
         add(["dnn_linear.weight"], kw.get("l2_reg_dnn", 0))
     if model == "xDeepFM":

@@ -60,7 +60,7 @@ def randomize_zero_params(model, gen, std=0.05):
                 p.copy_(torch.randn(p.shape, generator=gen) * std)
 
 
-def run_model_case(name, cfg, batch, zipf=None, seed=7):
+def run_model_case(name, cfg, batch, zipf=None, seed=7, eval_mode=False):
     cls = getattr(RM, cfg["model"])
     lin = to_ref_columns(cfg["linear_columns"])
     dnn = to_ref_columns(cfg["dnn_columns"])
@@ -72,6 +72,8 @@ def run_model_case(name, cfg, batch, zipf=None, seed=7):
     gen = torch.Generator().manual_seed(seed)
     randomize_zero_params(model, gen)
     model.train()
+    if eval_mode:       # dropout > 0: deterministic only in eval mode
+        model.eval()
     X, y = O.synthetic_batch(cfg, batch, seed=seed + 100, zipf_alpha=zipf)
     captured = {}
 
@@ -161,6 +163,56 @@ def model_cases():
     return cases
 
 
+def extra_cases():
+    """Round 2: adjacent models and the branch toggles of the reference's own model tests
+    (tests/models/*_test.py, tests/utils.py:18-67): no sparse / no dense / no linear columns, cross_num=0,
+    empty CIN, dropout (eval), VarLen features under xDeepFM / FiBiNET / DCN."""
+    std = 0.05
+    cases = []
+    c5 = small_columns(5, 8, 3, dense2=True)
+    c6 = small_columns(6, 8, 2, seed=5)
+    sparse_only = [c for c in c5 if c["type"] == "sparse"]
+    dense_only = [c for c in c5 if c["type"] == "dense"]
+    cases.append(("wdl_small", O.make_cfg("WDL", c5, c5, dnn_hidden_units=[32, 16], init_std=std), 40))
+    cases.append(("nfm_small", O.make_cfg("NFM", c5, c5, dnn_hidden_units=[32, 16], init_std=std), 40))
+    cases.append(("afm_attention", O.make_cfg("AFM", sparse_only, sparse_only, use_attention=True, attention_factor=8,
+                                               init_std=std), 40))
+    cases.append(("afm_plain", O.make_cfg("AFM", sparse_only, sparse_only, use_attention=False, init_std=std), 24))
+    cases.append(("ifm_small", O.make_cfg("IFM", c5, c5, dnn_hidden_units=[32, 16], init_std=std), 40))
+    cases.append(("difm_small", O.make_cfg("DIFM", c5, c5, att_head_num=4, att_res=True, dnn_hidden_units=[32, 16],
+                                           init_std=std), 40))
+    crit = small_columns(26, 16, 13, vocab_lo=40, vocab_hi=120, seed=3)
+    cases.append(("nfm_criteo_shape", O.make_cfg("NFM", crit, crit, dnn_hidden_units=[128, 128], init_std=std), 32))
+    crit_s = [c for c in crit if c["type"] == "sparse"]
+    cases.append(("afm_criteo_shape", O.make_cfg("AFM", crit_s, crit_s, init_std=std), 16))
+    cases.append(("difm_criteo_shape", O.make_cfg("DIFM", crit, crit, dnn_hidden_units=[64, 32], init_std=std), 16))
+    # branch toggles
+    cases.append(("deepfm_nosparse", O.make_cfg("DeepFM", dense_only, dense_only, dnn_hidden_units=[16, 8],
+                                                init_std=std), 20))
+    cases.append(("deepfm_nodense", O.make_cfg("DeepFM", sparse_only, sparse_only, dnn_hidden_units=[16, 8],
+                                               init_std=std), 20))
+    cases.append(("deepfm_nolinear", O.make_cfg("DeepFM", [], c5, dnn_hidden_units=[16, 8], init_std=std), 20))
+    cases.append(("deepfm_dropout_eval", O.make_cfg("DeepFM", c5, c5, dnn_hidden_units=[32, 32], dnn_dropout=0.5,
+                                                    init_std=std), 24, None, 7, True))
+    cases.append(("dcnmix_cross0", O.make_cfg("DCNMix", c5, c5, cross_num=0, dnn_hidden_units=[16, 8],
+                                              init_std=std), 20))
+    cases.append(("dcn_cross0", O.make_cfg("DCN", c5, c5, cross_num=0, dnn_hidden_units=[16, 8], init_std=std), 20))
+    cases.append(("xdeepfm_nocin", O.make_cfg("xDeepFM", c6, c6, dnn_hidden_units=[16, 8], cin_layer_size=[],
+                                              init_std=std), 20))
+    cases.append(("xdeepfm_nolinear", O.make_cfg("xDeepFM", [], c6, dnn_hidden_units=[16], cin_layer_size=[8, 4],
+                                                 init_std=std), 20))
+    vl = c5 + [O.varlen_col("V_sum", 30, 8, 5, "sum"), O.varlen_col("V_mean", 30, 8, 4, "mean"),
+               O.varlen_col("V_max", 30, 8, 6, "max"),
+               O.varlen_col("V_len", 30, 8, 4, "mean", length_name="V_len_n")]
+    cases.append(("xdeepfm_varlen", O.make_cfg("xDeepFM", vl, vl, dnn_hidden_units=[16], cin_layer_size=[8, 4],
+                                               init_std=std), 24))
+    cases.append(("fibinet_varlen", O.make_cfg("FiBiNET", vl, vl, bilinear_type="each", dnn_hidden_units=[16, 8],
+                                               init_std=std), 24))
+    cases.append(("dcn_varlen", O.make_cfg("DCN", vl, vl, cross_num=2, dnn_hidden_units=[16, 8], init_std=std), 24))
+    cases.append(("wdl_varlen", O.make_cfg("WDL", vl, vl, dnn_hidden_units=[16, 8], init_std=std), 24))
+    return cases
+
+
 def layer_cases():
     """Reference layer modules on random inputs: outputs + grads wrt input and parameters."""
     g = torch.Generator().manual_seed(99)
@@ -208,7 +260,43 @@ def layer_cases():
     print("wrote layers.npz (%d arrays)" % len(out))
 
 
-def fit_case():
+def extra_layer_cases():
+    """Layers of the adjacent models (reference layers/interaction.py:37-61, 250-331, 334-394)."""
+    g = torch.Generator().manual_seed(123)
+    out = {}
+
+    def run(tag, module, x, as_list=False):
+        x = x.clone().requires_grad_(True)
+        y = module([x[:, i:i + 1, :] for i in range(x.shape[1])]) if as_list else module(x)
+        w = torch.randn(y.shape, generator=g)
+        (y * w).sum().backward()
+        out[tag + "/x"] = x.detach().numpy()
+        out[tag + "/y"] = y.detach().numpy()
+        out[tag + "/w"] = w.numpy()
+        out[tag + "/dx"] = x.grad.numpy()
+        for k, p in module.named_parameters():
+            out[tag + "/param/" + k] = p.detach().numpy()
+            out[tag + "/dparam/" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+
+    def rnd(*shape, scale=1.0):
+        return torch.randn(*shape, generator=g) * scale
+
+    def reinit(module, scale=0.3):
+        with torch.no_grad():
+            for p in module.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * scale)
+        return module
+
+    run("bipool", RI.BiInteractionPooling(), rnd(33, 26, 16, scale=0.5))
+    run("afm", reinit(RI.AFMLayer(16, 8)), rnd(21, 26, 16, scale=0.7), as_list=True)
+    run("afm_small", reinit(RI.AFMLayer(8, 4)), rnd(9, 5, 8), as_list=True)
+    run("interacting", reinit(RI.InteractingLayer(16, 4, True, scaling=True), 0.3), rnd(19, 26, 16, scale=0.7))
+    run("interacting_nores", reinit(RI.InteractingLayer(8, 2, False, scaling=False), 0.3), rnd(11, 5, 8))
+    np.savez_compressed(os.path.join(HERE, "layers_r2.npz"), **out)
+    print("wrote layers_r2.npz (%d arrays)" % len(out))
+
+
+def fit_case(optimizer="adam", l2=1e-5, fname="fit_criteo_sample"):
     """BASELINE config #1: the reference example pipeline on criteo_sample.txt, batch 64."""
     import pandas as pd
     from sklearn.preprocessing import LabelEncoder, MinMaxScaler
@@ -223,14 +311,14 @@ def fit_case():
     data[dense] = MinMaxScaler(feature_range=(0, 1)).fit_transform(data[dense])
     cols = [O.sparse_col(f, int(data[f].nunique()), 4) for f in sparse] + [O.dense_col(f, 1) for f in dense]
     cfg = O.make_cfg("DeepFM", cols, cols, dnn_hidden_units=[256, 128], init_std=1e-4,
-                     l2_reg_linear=1e-5, l2_reg_embedding=1e-5, l2_reg_dnn=0)
+                     l2_reg_linear=l2, l2_reg_embedding=l2, l2_reg_dnn=0)
     names = sparse + dense
     x = {n: data[n].values for n in names}
     y = data["label"].values.astype("float32")
     model = RM.DeepFM(to_ref_columns(cols), to_ref_columns(cols), task="binary", device="cpu",
-                      dnn_hidden_units=(256, 128))
+                      dnn_hidden_units=(256, 128), l2_reg_linear=l2, l2_reg_embedding=l2)
     init_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    model.compile("adam", "binary_crossentropy", metrics=["binary_crossentropy"])
+    model.compile(optimizer, "binary_crossentropy", metrics=["binary_crossentropy"])
     hist = model.fit({k: v.copy() for k, v in x.items()}, y, batch_size=64, epochs=3, verbose=0,
                      validation_split=0.2, shuffle=False)
     pred = model.predict({k: v.copy() for k, v in x.items()}, batch_size=64)
@@ -242,13 +330,21 @@ def fit_case():
         out["init/" + k] = v.numpy()
     for k, v in model.state_dict().items():
         out["final/" + k] = v.detach().numpy()
-    np.savez_compressed(os.path.join(HERE, "fit_criteo_sample.npz"), **out)
-    print("wrote fit_criteo_sample.npz history:", hist.history)
+    np.savez_compressed(os.path.join(HERE, fname + ".npz"), **out)
+    print("wrote %s.npz history:" % fname, hist.history)
 
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    for case in model_cases():
+    only_new = "--round2" in sys.argv          # keep the round-1 files byte-identical
+    if not only_new:
+        for case in model_cases():
+            run_model_case(*case)
+        layer_cases()
+        fit_case()
+    for case in extra_cases():
         run_model_case(*case)
-    layer_cases()
-    fit_case()
+    extra_layer_cases()
+    # the fused row-wise optimizer equals the dense torch optimizer for sgd / adagrad at l2 = 0
+    fit_case("sgd", 0.0, "fit_sgd_l2zero")
+    fit_case("adagrad", 0.0, "fit_adagrad_l2zero")

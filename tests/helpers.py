@@ -9,7 +9,7 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 MODEL_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                     if os.path.basename(p) not in ("layers.npz", "fit_criteo_sample.npz"))
+                     if not os.path.basename(p).startswith(("layers", "fit_")))
 
 
 def load_case(name):
@@ -26,8 +26,8 @@ def load_case(name):
     return case
 
 
-def load_layers():
-    z = np.load(os.path.join(GOLDEN_DIR, "layers.npz"), allow_pickle=False)
+def load_layers(fname="layers.npz"):
+    z = np.load(os.path.join(GOLDEN_DIR, fname), allow_pickle=False)
     out = {}
     for k in z.files:
         tag, rest = k.split("/", 1)
@@ -39,6 +39,8 @@ def rel_err(a, b):
     """max|a-b| / max|b| — the parity metric of SURVEY.md §7 hard part 2."""
     a = torch.as_tensor(a).detach().to(torch.float64).reshape(-1)
     b = torch.as_tensor(b).detach().to(torch.float64).reshape(-1)
+    if b.numel() == 0:
+        return 0.0 if a.numel() == 0 else float("inf")
     denom = float(b.abs().max())
     if denom == 0.0:
         return float((a - b).abs().max())

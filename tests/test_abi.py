@@ -40,7 +40,7 @@ def test_library_builds_and_exports_every_symbol():
     for name in parse_header():
         assert name in exported, name
     lib = _lib.load()
-    assert lib.ctr_version() == 1
+    assert lib.ctr_version() == 2
     for name in _lib.exported_symbols():
         assert hasattr(lib, name)
 

@@ -58,9 +58,22 @@ LAYER_FUNCS = {
 }
 
 
-@pytest.mark.parametrize("tag", sorted(LAYER_FUNCS))
+LAYER_FUNCS_R2 = {
+    "bipool": lambda L, x: O.bi_interaction(x),
+    "afm": lambda L, x: O.afm_layer(L, "", [x[:, i] for i in range(x.shape[1])]),
+    "afm_small": lambda L, x: O.afm_layer(L, "", [x[:, i] for i in range(x.shape[1])]),
+    "interacting": lambda L, x: O.interacting_layer(L, "", x, 4, True, True),
+    "interacting_nores": lambda L, x: O.interacting_layer(L, "", x, 2, False, False),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(LAYER_FUNCS) + sorted(LAYER_FUNCS_R2))
 def test_layer_matches_reference(tag):
-    layer = load_layers()[tag]
+    if tag in LAYER_FUNCS_R2:
+        layer = load_layers("layers_r2.npz")[tag]
+        LAYER_FUNCS[tag] = LAYER_FUNCS_R2[tag]
+    else:
+        layer = load_layers()[tag]
     P = {k: v.clone().requires_grad_(True) for k, v in _params(layer).items()}
     x = layer["x"].clone().requires_grad_(True)
     y = LAYER_FUNCS[tag](P, x)
