@@ -34,6 +34,7 @@ SIGNATURES = {
     "ctr_p2p_export": [_P, _P],
     "ctr_p2p_open": [_P, _P],
     "ctr_p2p_close": [_P],
+    "ctr_p2p_barrier": [_P, _P, c_int, c_int, _P, _P],
     "ctr_shard_request": [_P, c_i64, c_i64, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, c_i64, _P, c_int, _P],
     "ctr_shard_serve": [c_int, c_int, c_int, _P, _P, c_i64, _P, _P, _P, _P, _P],
     "ctr_gather_fwd_exchanged": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P,
@@ -85,6 +86,8 @@ SIGNATURES = {
     "ctr_afm_bwd": [_P, c_i64, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_i64, _P, _P, _P, c_i64, _P],
     "ctr_fieldattn_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_f32, _P, c_i64, _P],
     "ctr_fieldattn_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_f32, _P, _P, _P, _P, c_i64, _P],
+    "ctr_bce_sum_fwd": [_P, _P, c_i64, _P, _P],
+    "ctr_bce_sum_bwd": [_P, _P, _P, c_i64, _P, _P],
     "ctr_rowopt_tick": [_P, _P],
     "ctr_rowopt_step": [c_int, c_i64, _P, _P, c_int, c_int, _P, c_i64, _P, _P, _P, _P, _P, c_f32, _P],
     "ctr_rowgrad_combine": [c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, c_i64, _P, c_i64, _P],

@@ -250,18 +250,39 @@ __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const float* __restrict
     }
 }
 
+// dH[b, n] (+)= g[b] * w[n]: a block is (256 / nq) rows x nq column quads, every thread keeps its four w values
+// in registers and walks down the rows: 128-bit coalesced stores, no per-element index arithmetic
+// (round 1: one scalar store and a 64-bit division per element, 0.2 ms for [65536, 557]).
+template <bool VEC>
 __global__ void __launch_bounds__(256) rowdot_bwd_dh_kernel(const float* __restrict__ w,
                                                             const float* __restrict__ g, int64_t B,
-                                                            int N, float* dH, int64_t lddh,
+                                                            int N, int nq_pad, float* dH, int64_t lddh,
                                                             int accumulate) {
-    const int64_t total = B * N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / N;
-        const int n = (int)(i - b * N);
-        const float v = __ldg(g + b) * __ldg(w + n);
-        float* p = dH + b * lddh + n;
-        *p = accumulate ? *p + v : v;
+    const int q = threadIdx.x % nq_pad, rsub = threadIdx.x / nq_pad, rows_per_block = blockDim.x / nq_pad;
+    const int step = VEC ? 4 * nq_pad : nq_pad;
+    for (int n0 = VEC ? 4 * q : q; n0 < N; n0 += step) {
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        w4.x = __ldg(w + n0);
+        if (VEC) {                                  // columns past N are row padding: they receive zeros
+            if (n0 + 1 < N) w4.y = __ldg(w + n0 + 1);
+            if (n0 + 2 < N) w4.z = __ldg(w + n0 + 2);
+            if (n0 + 3 < N) w4.w = __ldg(w + n0 + 3);
+        }
+        for (int64_t b = (int64_t)blockIdx.x * rows_per_block + rsub; b < B; b += (int64_t)gridDim.x * rows_per_block) {
+            const float gv = __ldg(g + b);
+            float* p = dH + b * lddh + n0;
+            if (VEC) {
+                float4 v = make_float4(gv * w4.x, gv * w4.y, gv * w4.z, gv * w4.w);
+                if (accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(p);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(p) = v;
+            } else {
+                const float v = gv * w4.x;
+                *p = accumulate ? *p + v : v;
+            }
+        }
     }
 }
 
@@ -528,11 +549,19 @@ extern "C" int ctr_rowdot_bwd(const float* H, int64_t ldh, const float* w, const
     CTR_ARG(!dw || H, "ctr_rowdot_bwd: H required for dw");
     cudaStream_t st = as_stream(stream);
     if (dH && B > 0) {
-        int64_t blocks = ceil_div64(B * N, 256 * 4);
+        // vector form: 16-byte aligned rows whose padding up to round_up(N, 4) exists (it is written with zeros)
+        const int64_t n4 = ((int64_t)N + 3) / 4 * 4;
+        const bool vec = (lddh % 4 == 0) && lddh >= n4 && ((reinterpret_cast<uintptr_t>(dH) & 15) == 0);
+        const int nq = vec ? (int)(n4 / 4) : N;
+        int nq_pad = 1;
+        while (nq_pad < nq && nq_pad < 256) nq_pad <<= 1;
+        const int rows_per_block = 256 / nq_pad;
+        int64_t blocks = ceil_div64(B, (int64_t)rows_per_block * 8);
         const int64_t cap = (int64_t)ctr_sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        rowdot_bwd_dh_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, g, B, N, dH, lddh, accumulate_dh);
+        if (vec) rowdot_bwd_dh_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(w, g, B, N, nq_pad, dH, lddh, accumulate_dh);
+        else rowdot_bwd_dh_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(w, g, B, N, nq_pad, dH, lddh, accumulate_dh);
         CTR_LAUNCH_OK("rowdot_bwd_dh_kernel");
     }
     if (dw) return launch_colsum(H, ldh, 1, nullptr, 0, 0, 0, g, B, N, dw, st);

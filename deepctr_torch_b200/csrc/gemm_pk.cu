@@ -513,6 +513,60 @@ __device__ __forceinline__ void epi_store(const GemmArgs& g, float4 v, float4 b4
     }
 }
 
+// Epilogue of one CTA tile (MT accumulators of 128 x BN in tensor memory) by 16 warps (CTA warps 2..17).
+// Four warps per TMEM lane quadrant, interleaved over the 32-column chunks.  tcgen05.ld hands every
+// thread ONE row (32 consecutive columns); written like that to C a warp would touch 32 different rows
+// per store.  So each chunk is transposed through a padded per-warp staging tile in shared memory (the
+// pipeline stages are free once accum_bar fired) and the epilogue math + stores run in the coalesced
+// domain: 8 lanes cover 128 contiguous bytes of a row.
+template <int EPI>
+__device__ __forceinline__ void tile_epilogue(const GemmArgs& g, uint32_t tmem_base, unsigned char* smem_raw, int wid, int lane,
+                                              int64_t m_tile0, int MT, int BN, int64_t n0, bool split) {
+    const int ew = wid - 2;
+    const int quad = wid & 3;                         // TMEM lane quadrant this warp may read
+    const int cgrp = ew >> 2;
+    float* stg = reinterpret_cast<float*>(smem_raw) + (size_t)ew * (32 * PK_STG_PITCH);
+    const int nchunks = (BN + 31) / 32;
+    for (int mt = 0; mt < MT; ++mt) {
+        const int64_t m_base = m_tile0 + (int64_t)mt * PK_AR + quad * 32;
+        if (m_base >= g.M) break;                     // warp-uniform
+        for (int ci = cgrp; ci < nchunks; ci += PK_CONV_WARPS / 4) {
+            const int c0 = ci * 32;
+            if (n0 + c0 >= g.N) break;                // warp-uniform
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c0), raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * PK_STG_PITCH + 4 * j) =
+                    make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+            __syncwarp();
+            const int colq = lane & 7;
+            const int col = c0 + 4 * colq;            // column inside the CTA's N tile
+            const int64_t n = n0 + col;
+            // columns of this chunk that belong to the tile AND to the matrix
+            int nvalid = 0;
+            if (col < BN && n < g.N) {
+                nvalid = BN - col < 4 ? BN - col : 4;
+                if (g.N - n < nvalid) nvalid = (int)(g.N - n);
+            }
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((EPI == EPI_BIAS_ACT || EPI == EPI_CROSS) && g.bias && nvalid > 0)
+                b4 = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
+            // not unrolled on purpose: the body (with its activation variants) stays a few dozen
+            // instructions, so the whole epilogue fits the instruction cache
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                const int64_t m = m_base + r;
+                const float4 v = *reinterpret_cast<const float4*>(stg + r * PK_STG_PITCH + 4 * colq);
+                if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, b4, m, n, nvalid, split);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -679,57 +733,230 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             cp_async_wait<0>();
         }
         // ------------------------------ epilogue (16 warps) ---------------------------------
-        // Four warps per TMEM lane quadrant, interleaved over the 32-column chunks.  tcgen05.ld hands every
-        // thread ONE row (32 consecutive columns); written like that to C a warp would touch 32
-        // different rows per store.  So each chunk is transposed through a padded per-warp staging
-        // tile in shared memory (the pipeline stages are free once accum_bar fires) and the epilogue
-        // math + stores run in the coalesced domain: 8 lanes cover 128 contiguous bytes of a row.
-        const int ew = wid - 2;
-        const int quad = wid & 3;                         // TMEM lane quadrant this warp may read
-        const int cgrp = ew >> 2;
-        float* stg = reinterpret_cast<float*>(smem_raw) + (size_t)ew * (32 * PK_STG_PITCH);
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int64_t n0 = nblk * BN;
-        const int nchunks = (BN + 31) / 32;
-        for (int mt = 0; mt < MT; ++mt) {
-            const int64_t m_base = (mblk * MT + mt) * PK_AR + quad * 32;
-            if (m_base >= g.M) break;                     // warp-uniform
-            for (int ci = cgrp; ci < nchunks; ci += PK_CONV_WARPS / 4) {
-                const int c0 = ci * 32;
-                if (n0 + c0 >= g.N) break;                // warp-uniform
-                uint32_t raw[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c0), raw);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * PK_STG_PITCH + 4 * j) =
-                        make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
-                __syncwarp();
-                const int colq = lane & 7;
-                const int col = c0 + 4 * colq;            // column inside the CTA's N tile
-                const int64_t n = n0 + col;
-                // columns of this chunk that belong to the tile AND to the matrix
-                int nvalid = 0;
-                if (col < BN && n < g.N) {
-                    nvalid = BN - col < 4 ? BN - col : 4;
-                    if (g.N - n < nvalid) nvalid = (int)(g.N - n);
-                }
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((EPI == EPI_BIAS_ACT || EPI == EPI_CROSS) && g.bias && nvalid > 0)
-                    b4 = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
-                // not unrolled on purpose: the body (with its activation variants) stays a few dozen
-                // instructions, so the whole epilogue fits the instruction cache
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 4 * i + (lane >> 3);
-                    const int64_t m = m_base + r;
-                    const float4 v = *reinterpret_cast<const float4*>(stg + r * PK_STG_PITCH + 4 * colq);
-                    if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, b4, m, n, nvalid, split);
-                }
-                __syncwarp();
+        tile_epilogue<EPI>(g, tmem_base, smem_raw, wid, lane, mblk * MT * PK_AR, MT, BN, nblk * BN, split);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (wid == 1) {
+        tc_fence_after();
+        tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TS engine (round 2): the streamed operand A goes through TENSOR MEMORY instead of shared memory.
+//
+//   C[m,n] = epilogue( sum_k A(m,k) * W(n,k) )     A: activations [M, K] row-major (K contiguous),
+//                                                  W: weights, pre-split + pre-tiled once per call (pack_*)
+//
+// Why: in the SS engine above every fp32 of A crosses shared memory four times (cp.async in, read, hi and
+// lo written back) and is then read three more times by the MMAs; with the weight tiles that is ~156 B/clk
+// against the 128 B/clk an SM's shared memory delivers — the tensor pipe idles (run 18: 15-37 %).
+// tcgen05.mma takes its A operand from tensor memory as well (probe: scripts/probe_umma.cu, bit-identical
+// to the shared-memory form), one TMEM lane per row and one 32-bit column per k.  So:
+//   * a converter warp copies ITS 32 rows x 16 k of A with coalesced cp.async (4 lanes = 64 contiguous
+//     bytes of a row) into a raw staging tile, every thread then reads its own row back (conflict-free,
+//     80-byte pitch), splits it into hi/lo and writes both halves straight into its TMEM lane with
+//     tcgen05.st: no hi/lo tile in shared memory, no generic->async proxy fence, no A reads by the MMA;
+//   * shared memory only carries the weight stages (TMA in, MMA out) and the 10 KB raw tiles: ~125 B/clk
+//     at the MMA-bound rate;
+//   * 16 converter warps = 4 groups of 4 warps (one warp per TMEM lane quadrant); a group owns every 4th
+//     (k stage, M tile) item, so four items are in conversion while the MMAs of earlier ones run;
+//   * TMEM: MT accumulators of BN columns (MT * BN <= 256) + a ring of A slots (32 columns = 16 k x {hi, lo}).
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_NG = 4;                          // converter groups
+constexpr int TS_RAW_PITCH = 20;                  // floats per row of a raw item (16 k + 4 padding: conflict-free LDS.128)
+constexpr uint32_t TS_RAW_TILE = PK_AR * TS_RAW_PITCH * 4;    // 10 240 bytes: 128 rows
+
+struct TsParams {
+    GemmArgs g;
+    const float* Bp;                 // packed W tiles (row blocks of BN)
+    int64_t nkb;
+    int BN, MT, SB, SLOTS, RAWD, tmem_cols, a_col0, has_mask;
+    uint32_t off_raw, off_bar, raw_item_bytes;
+};
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+            taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const GemmArgs& g = p.g;
+    const int BN = p.BN, MT = p.MT, SB = p.SB, SLOTS = p.SLOTS;
+    const uint32_t b_stage = (uint32_t)BN * 128u;
+    unsigned char* ringB = smem_raw;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw + p.off_bar);
+    uint64_t* b_empty = b_full + SB;
+    uint64_t* a_full = b_empty + SB;                  // [MT * SLOTS]
+    uint64_t* a_empty = a_full + MT * SLOTS;
+    uint64_t* accum_bar = a_empty + MT * SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int64_t mblk = blockIdx.y, nblk = blockIdx.x;
+    const int nkb = (int)p.nkb;
+
+    if (tid == 0) {
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < MT * SLOTS; ++s) {
+            mbar_init(&a_full[s], 4);                 // the four warps of the group that filled the slot
+            mbar_init(&a_empty[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wid == 0) {
+        // ------------------------------ TMA producer: weight stages ------------------------------
+        if (lane == 0) {
+            const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
+            int sb = 0;
+            uint32_t phb = 1;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&b_empty[sb], phb);
+                mbar_expect_tx(&b_full[sb], b_stage);
+                bulk_g2s(ringB + (size_t)sb * b_stage, b_src + (nblk * p.nkb + i) * (int64_t)b_stage, b_stage, &b_full[sb]);
+                if (++sb == SB) { sb = 0; phb ^= 1u; }
             }
         }
+        __syncwarp();
+    } else if (wid == 1) {
+        // ------------------------------ MMA issuer ------------------------------------------------
+        const uint32_t idesc = tf32_idesc(BN);
+        const uint32_t b_lbo = (uint32_t)BN * 16u;
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int i = 0; i < nkb; ++i) {
+            const int slot = i % SLOTS;
+            const uint32_t pa = (uint32_t)((i / SLOTS) & 1);
+            mbar_wait(&b_full[sb], phb);
+            for (int mt = 0; mt < MT; ++mt) mbar_wait(&a_full[mt * SLOTS + slot], pa);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
+#pragma unroll
+                for (int j = 0; j < PK_KB / 8; ++j) {
+                    const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + (mt * SLOTS + slot) * 32 + 8 * j);
+                        const uint32_t a_lo = a_hi + 16u;
+                        const uint32_t d = tmem_base + (uint32_t)(mt * BN);
+                        umma_tf32_ts(d, a_lo, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
+                        umma_tf32_ts(d, a_hi, dbl, idesc, 1u);
+                        umma_tf32_ts(d, a_hi, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(&b_empty[sb]);                // frees the stage / the slots when these MMAs retire
+                for (int mt = 0; mt < MT; ++mt) umma_commit(&a_empty[mt * SLOTS + slot]);
+                if (i == nkb - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+        }
+    } else {
+        // ------------------------------ converters (4 groups x 4 warps), then epilogue ------------
+        const int cw = wid - 2;
+        const int grp = cw >> 2;
+        const int quad = wid & 3;                          // TMEM lane quadrant of this warp = its 32 rows of the M tile
+        const int n_items = nkb * MT;
+        unsigned char* raw_grp = smem_raw + p.off_raw + (size_t)grp * p.RAWD * p.raw_item_bytes;
+        const float* Aptr = g.A;
+        const float* Mptr = g.amask;
+        const int64_t sam = g.sam, smm = g.smm;
+        const int mask_act = g.amask_act;
+        // cp.async mapping: instruction j moves rows 8j + lane/4 of the warp's 32, chunk lane%4 (64 contiguous bytes per row)
+        const int cp_row = lane >> 2, cp_chunk = lane & 3;
+        int issued = 0;                                    // items of this group issued so far
+        auto issue = [&]() {
+            const int it = grp + issued * TS_NG;
+            if (it < n_items) {
+                const int i = it / MT, mt = it - i * MT;
+                unsigned char* buf = raw_grp + (size_t)(issued % p.RAWD) * p.raw_item_bytes;
+                const int64_t k0 = (int64_t)i * PK_KB + cp_chunk * 4;
+                int kbytes = (int)(g.K - k0) * 4;
+                kbytes = kbytes > 16 ? 16 : (kbytes < 0 ? 0 : kbytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rt = quad * 32 + 8 * j + cp_row;
+                    const int64_t row = (mblk * MT + mt) * (int64_t)PK_AR + rt;
+                    const int bytes = row < g.M ? kbytes : 0;
+                    float* dst = reinterpret_cast<float*>(buf) + rt * TS_RAW_PITCH + cp_chunk * 4;
+                    cp_async16(dst, bytes ? Aptr + row * sam + k0 : Aptr, bytes);
+                    if (p.has_mask)
+                        cp_async16(reinterpret_cast<float*>(buf + TS_RAW_TILE) + rt * TS_RAW_PITCH + cp_chunk * 4,
+                                   bytes ? Mptr + row * smm + k0 : Mptr, bytes);
+                }
+            }
+            cp_async_commit();
+            ++issued;
+        };
+        for (int d = 0; d < p.RAWD; ++d) issue();
+        int done = 0;
+        for (int it = grp; it < n_items; it += TS_NG, ++done) {
+            const int i = it / MT, mt = it - i * MT;
+            const int slot = i % SLOTS;
+            if (p.RAWD == 3) cp_async_wait<2>();
+            else if (p.RAWD == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            __syncwarp();                                  // the warp's lanes copied each other's rows
+            const unsigned char* buf = raw_grp + (size_t)(done % p.RAWD) * p.raw_item_bytes;
+            const float* myrow = reinterpret_cast<const float*>(buf) + (quad * 32 + lane) * TS_RAW_PITCH;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 v = *reinterpret_cast<const float4*>(myrow + 4 * c);
+                if (p.has_mask) v = pk_mask4(v, *reinterpret_cast<const float4*>(myrow + TS_RAW_TILE / 4 + 4 * c), mask_act);
+                split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+                split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+                split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+                split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+            }
+            __syncwarp();                                  // every lane has read its row: the raw tile may be refilled
+            issue();
+            mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + (mt * SLOTS + slot) * 32);
+            tmem_st16(taddr, hi);
+            tmem_st16(taddr + 16u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[mt * SLOTS + slot]);
+        }
+        cp_async_wait<0>();
+        // ------------------------------ epilogue (16 warps) ---------------------------------------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        tile_epilogue<EPI>(g, tmem_base, smem_raw, wid, lane, mblk * MT * PK_AR, MT, BN, nblk * BN, false);
         tc_fence_before();
     }
     __syncthreads();
@@ -916,7 +1143,92 @@ int gemm_pack_operand(const float* P, int64_t s_row, int64_t s_k, int64_t n_rows
     return launch_pack(pa, st);
 }
 
+// TS engine: eligible when A is a big K-contiguous fp32 matrix (activations) and B is small enough to be packed
+// (weights), no split-K.  Returns -3 when the shape does not qualify (the caller continues with the SS engine).
+static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
+    const char* e = getenv("CTR_GEMM_TS");
+    if (e && e[0] == '0') return -3;
+    if (g.M < 4 * PK_AR || g.K < 16 || g.N < 16 || g.accumulate) return -3;
+    if (stream_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk) != OP_KVEC) return -3;
+    if (g.bmask) return -3;
+    const int64_t gn = ceil_div64(g.N, 256);
+    const int BN = (int)(ceil_div64(ceil_div64(g.N, gn), 16) * 16);
+    const int MT = (BN <= 128 && g.M >= 2 * PK_AR * ctr_sm_count()) ? 2 : 1;
+    const int64_t nkb = ceil_div64(g.K, PK_KB);
+    const int64_t b_bytes = gn * nkb * (int64_t)BN * 128;
+    if (b_bytes > kStreamThresholdBytes) return -3;           // B is not a "small weight" operand
+    const int64_t a_packed = ceil_div64(g.M, PK_AR) * nkb * (int64_t)PK_AR * 128;
+    if (a_packed <= kStreamThresholdBytes) return -3;         // small A: the all-packed SS path is fine
+    const int dev = current_device();
+    void* scratch = g_scratch[dev];
+    if (!scratch || g_scratch_bytes[dev] < b_bytes) return -3;
+    TsParams p{};
+    p.g = g;
+    p.Bp = reinterpret_cast<const float*>(scratch);
+    p.nkb = nkb;
+    p.BN = BN;
+    p.MT = MT;
+    p.has_mask = g.amask ? 1 : 0;
+    p.a_col0 = MT * BN;
+    int cols_left = 512 - p.a_col0;
+    p.SLOTS = cols_left / (32 * MT);
+    if (p.SLOTS > 8) p.SLOTS = 8;
+    if (p.SLOTS < 2) return -3;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.a_col0 + MT * p.SLOTS * 32) p.tmem_cols <<= 1;
+    p.raw_item_bytes = TS_RAW_TILE * (p.has_mask ? 2u : 1u);
+    const int64_t budget = 232448 - 1024;
+    const int64_t b_stage = (int64_t)BN * 128;
+    const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;
+    p.SB = 0;
+    for (int rawd = 3; rawd >= 1 && !p.SB; --rawd)
+        for (int sbn = 5; sbn >= 3 && !p.SB; --sbn) {
+            const int64_t need = sbn * b_stage + (int64_t)TS_NG * rawd * p.raw_item_bytes;
+            if (need <= budget) {
+                p.SB = sbn;
+                p.RAWD = rawd;
+            }
+        }
+    if (!p.SB) return -3;
+    int64_t rings = p.SB * b_stage;
+    p.off_raw = (uint32_t)rings;
+    int64_t end = rings + (int64_t)TS_NG * p.RAWD * p.raw_item_bytes;
+    if (end < stg) end = stg;
+    p.off_bar = (uint32_t)((end + 15) / 16 * 16);
+    const size_t smem = p.off_bar + (size_t)(2 * p.SB + 2 * MT * p.SLOTS + 1) * sizeof(uint64_t) + 16;
+    if (smem > 232448) return -3;
+    const int64_t gm = ceil_div64(g.M, (int64_t)PK_AR * MT);
+    if (gm > 65535) return -3;
+    PackArgs pb{g.B, g.sbn, g.sbk, nullptr, 0, 0, 0, g.N, g.K, BN, gn, nkb, reinterpret_cast<float*>(scratch)};
+    int rc;
+    if ((rc = launch_pack(pb, st)) != 0) return rc;
+    static bool configured = false;
+    if (!configured) {
+        const int max_smem = 232448;
+        CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)gn, (unsigned)gm, 1);
+    switch (g.epilogue) {
+        case EPI_BIAS_ACT: gemm_ts_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_MUL_ACTGRAD: gemm_ts_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_CROSS: gemm_ts_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_MUL: gemm_ts_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p); break;
+        default: gemm_ts_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
+    }
+    CTR_LAUNCH_OK("gemm_ts_kernel");
+    return 0;
+}
+
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
+    {
+        const int rc_ts = launch_gemm_ts(g, st);
+        if (rc_ts != -3) return rc_ts;
+    }
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);
     if (!c.ok) return -3;     // no shared-memory plan for this shape: the caller uses the first-generation engine

@@ -241,7 +241,47 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(ServeArgs a) {
     }
 }
 
+// Device-side barrier over peer memory: rank r bumps its private epoch, stores it into slot [r] of every
+// peer's flag array (after a system-scope fence, so everything this stream wrote to peer memory before is
+// visible first) and spins until all of its own slots reached the epoch.  One block, one thread per peer.
+// Replaces the NCCL all-reduce "barriers" of the row exchange (two per forward in round 1).  The spin is
+// bounded: a missing peer sets bit 2 of err_flag instead of hanging the GPU.
+__global__ void p2p_barrier_kernel(int32_t* const* peer_flags, int32_t* epoch_ctr, int G, int me, int32_t* err_flag) {
+    __shared__ int32_t s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = *epoch_ctr + 1;
+        *epoch_ctr = s_epoch;
+    }
+    __syncthreads();
+    const int32_t e = s_epoch;
+    const int r = threadIdx.x;
+    if (r < G) {
+        __threadfence_system();
+        volatile int32_t* remote = peer_flags[r] + me;
+        *remote = e;
+        __threadfence_system();
+        volatile int32_t* mine = peer_flags[me] + r;
+        long long spins = 0;
+        while (*mine - e < 0) {
+            if (++spins > (1ll << 26)) {      // tens of seconds: a peer died or never launched
+                atomicOr(err_flag, 4);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace
+
+extern "C" int ctr_p2p_barrier(int32_t* const* peer_flags, int32_t* epoch_ctr, int n_shards, int rank, int32_t* err_flag,
+                               void* stream) {
+    CTR_ARG(peer_flags && epoch_ctr && err_flag && n_shards >= 1 && n_shards <= PUSH_MAX_G && rank >= 0 && rank < n_shards,
+            "ctr_p2p_barrier: bad arguments");
+    p2p_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(peer_flags, epoch_ctr, n_shards, rank, err_flag);
+    CTR_LAUNCH_OK("p2p_barrier_kernel");
+    return 0;
+}
 
 extern "C" int ctr_p2p_alloc(int64_t bytes, void** ptr) {
     CTR_ARG(ptr && bytes > 0, "ctr_p2p_alloc: bad arguments");

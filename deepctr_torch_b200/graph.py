@@ -10,7 +10,8 @@ tensors; tables: dense or per-unique-row sparse COO, depending on ``model.table_
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
+
+from . import ops
 
 
 class GraphedStep:
@@ -22,7 +23,7 @@ class GraphedStep:
         n_cols = max(e for _, e in model.feature_index.values())
         self.X = torch.zeros(batch_size, n_cols, device=dev, dtype=torch.float32)
         self.y = torch.zeros(batch_size, device=dev, dtype=torch.float32)
-        self.loss_fn = loss_fn or F.binary_cross_entropy
+        self.loss_fn = loss_fn or ops.binary_cross_entropy
         self.with_reg = with_reg
         model.train()
         side = torch.cuda.Stream(device=dev)
@@ -132,7 +133,7 @@ class ShardedGraphedStep:
         n_cols = max(e for _, e in model.feature_index.values())
         self.X = torch.zeros(batch_size, n_cols, device=dev, dtype=torch.float32)
         self.y = torch.zeros(batch_size, device=dev, dtype=torch.float32)
-        self.loss_fn = loss_fn or F.binary_cross_entropy
+        self.loss_fn = loss_fn or ops.binary_cross_entropy
         model.train()
         if warmup % 2:
             warmup += 1                                  # leave the parity where it started

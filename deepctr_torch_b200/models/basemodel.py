@@ -323,7 +323,7 @@ class BaseModel(nn.Module):
 
     def _get_loss_func_single(self, loss):
         if loss == "binary_crossentropy":
-            return F.binary_cross_entropy
+            return ops.binary_cross_entropy
         if loss == "mse":
             return F.mse_loss
         if loss == "mae":
@@ -404,6 +404,9 @@ class BaseModel(nn.Module):
         by the same ``DataLoader(shuffle=...)`` machinery as the reference, so the RNG consumption and
         the batch composition are identical."""
         dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("deepctr_torch_b200 models run on CUDA only (construct with device='cuda:0'); "
+                               "there is no CPU implementation of the hot path")
         n = X_all.shape[0]
         order = DataLoader(Data.TensorDataset(torch.arange(n)), shuffle=shuffle, batch_size=batch_size)
         shard = getattr(self, "sharded", None)

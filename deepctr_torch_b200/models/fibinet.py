@@ -1,5 +1,4 @@
 """FiBiNET — same constructor and ``state_dict`` as reference ``deepctr_torch/models/fibinet.py:39-102``."""
-import torch
 import torch.nn as nn
 
 from .. import ops
@@ -37,16 +36,13 @@ class FiBiNET(BaseModel):
 
     def forward(self, X):
         E, dnn_input, lin, _, _ = self.embed(X)
-        B = X.shape[0]
         W = self.Bilinear.stacked_weight()           # shared by both passes (fibinet.py:82-83)
         senet_out = self.SE(E)
-        p_se = self.Bilinear(senet_out, W)
-        p_raw = self.Bilinear(E, W)
-        parts = [p_se.reshape(B, -1), p_raw.reshape(B, -1)]   # SENET branch first
-        n_dense = dnn_input.shape[1] - E.shape[1] * E.shape[2]
-        if n_dense > 0:
-            parts.append(dnn_input[:, E.shape[1] * E.shape[2]:])
-        dnn_logit = ops.rowdot(self.dnn(torch.cat(parts, dim=1)), self.dnn_linear.weight)
+        n_emb = E.shape[1] * E.shape[2]
+        dense = dnn_input[:, n_emb:] if dnn_input.shape[1] > n_emb else None
+        # [bilinear(SENET(E)) | bilinear(E) | dense]: both passes write straight into the tower's input
+        x = ops.fibinet_dnn_input(senet_out, E, W, self.Bilinear.bilinear_type, dense)
+        dnn_logit = ops.rowdot(self.dnn(x), self.dnn_linear.weight)
         if len(self.linear_feature_columns) > 0 and len(self.dnn_feature_columns) > 0:
             terms = [lin, dnn_logit]
         elif len(self.linear_feature_columns) == 0:

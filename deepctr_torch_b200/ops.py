@@ -729,13 +729,14 @@ class _CrossVector(torch.autograd.Function):
         L = kernels.shape[0]
         kv = kernels.reshape(L, n).contiguous()
         bv = bias.reshape(L, n).contiguous()
-        out = torch.empty(B, n, device=x.device, dtype=torch.float32)
+        ldo = _round4(n)                  # 16-byte aligned rows: the register kernels move 128 bits per lane
+        out_full = torch.empty(B, ldo, device=x.device, dtype=torch.float32)
         s = torch.empty(B, max(L, 1), device=x.device, dtype=torch.float32)
-        _lib.call("ctr_cross_vector_fwd", _ptr(x), x.stride(0), _ptr(kv), _ptr(bv), L, n, _ptr(out), n,
+        _lib.call("ctr_cross_vector_fwd", _ptr(x), x.stride(0), _ptr(kv), _ptr(bv), L, n, _ptr(out_full), ldo,
                   _ptr(s), B, _stream())
         ctx.save_for_backward(x, kv, bv, s)
         ctx.shapes = (kernels.shape, bias.shape)
-        return out
+        return out_full[:, :n] if ldo != n else out_full
 
     @staticmethod
     @_on_device
@@ -918,6 +919,60 @@ class _Bilinear(torch.autograd.Function):
         _lib.call("ctr_bilinear_bwd", _ptr(E), E.stride(0), F, D, _ptr(Wc), ctx.wsel, _ptr(dout), P * D,
                   _ptr(dE), F * D, _ptr(dW), B, _stream())
         return dE, dW, None
+
+
+class _FibinetInput(torch.autograd.Function):
+    """FiBiNET's DNN input [bilinear(SENET(E)) | bilinear(E) | dense] (reference models/fibinet.py:82-87) written
+    ONCE, in place: both bilinear passes store straight into their column ranges of the padded [B, ld] buffer the
+    tower consumes (batch stride `so` of ctr_bilinear_fwd), the backward reads the tower's input gradient through
+    strided views — no [B,650,D] intermediates, no 2.7 GB torch.cat at BASELINE config #4."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, E_se, E, W, wsel, dense):
+        _require_cuda(E, "bilinear input")
+        B, F, D = E.shape
+        E, E_se = _block3(E), _block3(E_se)
+        Wc = W.contiguous()
+        P = F * (F - 1) // 2
+        nd = dense.shape[1] if dense is not None else 0
+        width = 2 * P * D + nd
+        ld = _round4(width)
+        buf = torch.empty(B, ld, device=E.device, dtype=torch.float32)
+        if ld > 2 * P * D:
+            tail = buf[:, 2 * P * D:]
+            if nd:
+                tail[:, :nd].copy_(dense)
+            if ld > width:
+                tail[:, nd:].zero_()
+        ensure_scratch_bytes(E.device, 8 << 20)      # packed weight blocks of the GEMM formulation
+        _lib.call("ctr_bilinear_fwd", _ptr(E_se), E_se.stride(0), F, D, _ptr(Wc), wsel, _ptr(buf), ld, B, _stream())
+        _lib.call("ctr_bilinear_fwd", _ptr(E), E.stride(0), F, D, _ptr(Wc), wsel,
+                  _vp(buf.data_ptr() + 4 * P * D), ld, B, _stream())
+        ctx.wsel, ctx.dims = wsel, (B, F, D, P, width)
+        ctx.save_for_backward(E_se, E, Wc)
+        return buf
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dbuf):
+        E_se, E, Wc = ctx.saved_tensors
+        B, F, D, P, width = ctx.dims
+        dbuf = _rowmajor(dbuf)
+        sdo = dbuf.stride(0)
+        outs = []
+        for k, src in enumerate((E_se, E)):
+            dE = torch.zeros(B, F, D, device=E.device, dtype=torch.float32)
+            dW = torch.empty_like(Wc)
+            _lib.call("ctr_bilinear_bwd", _ptr(src), src.stride(0), F, D, _ptr(Wc), ctx.wsel,
+                      _vp(dbuf.data_ptr() + 4 * k * P * D), sdo, _ptr(dE), F * D, _ptr(dW), B, _stream())
+            outs.append((dE, dW))
+        return outs[0][0], outs[1][0], outs[0][1] + outs[1][1], None, None
+
+
+def fibinet_dnn_input(E_se, E, W, bilinear_type, dense=None):
+    """Padded [B, round_up(2*P*D + n_dense, 4)] DNN input of FiBiNET (SENET branch first)."""
+    return _FibinetInput.apply(E_se, E, W, BILINEAR_SEL[bilinear_type], dense)
 
 
 def bilinear(E, W, bilinear_type):
@@ -1148,3 +1203,37 @@ class _FieldAttn(torch.autograd.Function):
 def field_attention(Q, K, V, R, heads, scale):
     """relu(multi-head softmax(QK^T * scale) V + R) over the field axis, all [B,F,D]."""
     return _FieldAttn.apply(Q, K, V, R, int(heads), float(scale))
+
+
+# ----------------------------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------------------------
+class _BceSum(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, y_pred, y):
+        p = y_pred.reshape(-1).contiguous()
+        t = y.reshape(-1).to(torch.float32).contiguous()
+        out = torch.empty(1, device=p.device, dtype=torch.float32)
+        _lib.call("ctr_bce_sum_fwd", _ptr(p), _ptr(t), p.numel(), _ptr(out), _stream())
+        ctx.save_for_backward(p, t)
+        ctx.shape = y_pred.shape
+        return out.reshape(())
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        g = g.reshape(1).contiguous()
+        dp = torch.empty_like(p)
+        _lib.call("ctr_bce_sum_bwd", _ptr(p), _ptr(t), _ptr(g), p.numel(), _ptr(dp), _stream())
+        return dp.view(ctx.shape), None
+
+
+def binary_cross_entropy(y_pred, y, reduction="mean", **kw):
+    """Drop-in for ``torch.nn.functional.binary_cross_entropy``: the summed loss of ``fit`` (reference
+    basemodel.py:254) runs on the library's kernels; other reductions / CPU tensors go to torch."""
+    if reduction == "sum" and not kw and isinstance(y_pred, torch.Tensor) and y_pred.is_cuda \
+            and y_pred.dtype == torch.float32 and y_pred.numel() == y.numel():
+        return _BceSum.apply(y_pred, y)
+    return torch.nn.functional.binary_cross_entropy(y_pred, y, reduction=reduction, **kw)

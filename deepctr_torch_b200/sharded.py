@@ -84,6 +84,7 @@ class ArenaLayout:
         # BASELINE config #5, nothing on a 180 GB part, and a skewed id distribution can never overflow
         n_cols = n_id_cols if n_id_cols is not None else max(self.n_emb, self.n_lin, 1)
         self.xcap = batch * n_cols
+        self.flags = take(max(world, 1) * 4)            # device-side barrier flags (ctr_p2p_barrier)
         self.x = {"req_cnt": take(world * 4), "req": take(world * self.xcap * 8),
                   "resp_emb": take(world * self.xcap * max(dim, 1) * 4), "resp_lin": take(world * self.xcap * 4)}
         self.nbytes = cursor
@@ -233,6 +234,9 @@ class ShardedPlan(ops.GatherPlan):
         self.x_resp_lin_local = torch.tensor([me + x["resp_lin"] + o * cap * 4 for o in range(world)], **i64)
         self.x_token = torch.zeros(1, device=dev)
         self._x_where = {}
+        self.bar_flags = torch.tensor([arena.peer_ptr[s] + layout.flags for s in range(world)], **i64)
+        self.bar_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.use_nccl_barrier = os.environ.get("CTR_SHARD_BARRIER", "p2p") == "nccl"
 
     def exchange_rows(self, X, B, group=None):
         """Requests -> barrier -> owners serve -> barrier; returns where[B, n_cols] for the gather."""
@@ -245,12 +249,21 @@ class ShardedPlan(ops.GatherPlan):
                   ops._ptr(self.plan_vocab), self.world, self.rank, ops._ptr(self.x_cnt_to), ops._ptr(self.x_inbox_req),
                   ops._ptr(self.x_inbox_cnt), ops._ptr(where), self.x_cap, ops._ptr(self.err_flag), self.id_mode,
                   ops._stream())
-        dist.all_reduce(self.x_token, group=group)        # every request list is complete
+        self.barrier(group)                                # every request list is complete
         _lib.call("ctr_shard_serve", self.world, self.rank, self.D, ctypes.c_void_p(self.x_req_cnt), ctypes.c_void_p(self.x_req),
                   self.x_cap, ops._ptr(self.x_emb_of_col), ops._ptr(self.x_lin_of_col), ops._ptr(self.x_resp_emb_remote),
                   ops._ptr(self.x_resp_lin_remote), ops._stream())
-        dist.all_reduce(self.x_token, group=group)        # every response buffer is complete
+        self.barrier(group)                                # every response buffer is complete
         return where
+
+    def barrier(self, group=None):
+        """All ranks' work enqueued so far (incl. their stores into peer memory) precedes everything enqueued
+        after it: a flag exchange over NVLink inside one tiny kernel (CTR_SHARD_BARRIER=nccl: an all-reduce)."""
+        if self.use_nccl_barrier:
+            dist.all_reduce(self.x_token, group=group)
+        else:
+            _lib.call("ctr_p2p_barrier", ops._ptr(self.bar_flags), ops._ptr(self.bar_epoch), self.world, self.rank,
+                      ops._ptr(self.err_flag), ops._stream())
 
     def table_ptrs(self):
         return self._emb_ptrs, self._lin_ptrs

@@ -144,6 +144,12 @@ int ctr_p2p_free(void* ptr);
 int ctr_p2p_export(void* ptr, unsigned char* handle64);
 int ctr_p2p_open(const unsigned char* handle64, void** peer_ptr);
 int ctr_p2p_close(void* peer_ptr);
+/* device-side barrier of the n_shards ranks over peer memory (no NCCL): peer_flags[r] = rank r's int32
+ * [n_shards] flag array (peer pointers, zero-initialised), epoch_ctr = this rank's private int32 counter.
+ * Orders everything this stream wrote to peer memory before the call ahead of every peer's work after it.
+ * A peer that never arrives sets bit 2 of *err_flag after a bounded spin. */
+int ctr_p2p_barrier(int32_t* const* peer_flags, int32_t* epoch_ctr, int n_shards, int rank, int32_t* err_flag,
+                    void* stream);
 int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
                      int n_emb, int D, const float* emb_rowgrad, int64_t emb_rowgrad_stride,
                      const int32_t* emb_plan_col,
@@ -343,6 +349,12 @@ int ctr_bilinear_bwd(const float* E, int64_t se, int F, int D, const float* W, i
 /* ---- a16: whole-table L2 term (reference models/basemodel.py:412-428) --------------------
  * out[0] += scale * sum(w^2) over n elements */
 int ctr_sumsq_acc(const float* w, int64_t n, float scale, float* out, void* stream);
+
+/* ---- a16: the loss of fit(): F.binary_cross_entropy(y_pred, y, reduction='sum') (reference
+ * models/basemodel.py:254) with ATen's clamps (log >= -100; gradient denominator >= 1e-12).
+ * fwd: out[0] = sum_b -(y log p + (1-y) log(1-p));  bwd: d_pred[b] = g[0] * (p - y) / max(p (1-p), 1e-12) */
+int ctr_bce_sum_fwd(const float* y_pred, const float* y, int64_t B, float* out, void* stream);
+int ctr_bce_sum_bwd(const float* y_pred, const float* y, const float* g, int64_t B, float* d_pred, void* stream);
 
 /* ---- VarLenSparseFeat pooled lookup (reference inputs.py:141-155, layers/sequence.py:49-77)
  * ids X[b, col .. col+T); mask = (id != 0) when len_col < 0, else t < (int)X[b,len_col].

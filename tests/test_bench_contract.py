@@ -17,7 +17,10 @@ def test_reference_arm_prints_the_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isdir(os.path.join(REPO, "baseline", "_ref", "deepctr_torch")) or os.path.isdir("/root/reference")
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["steps"] == 1 and "workload" in line["config"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
