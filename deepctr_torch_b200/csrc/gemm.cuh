@@ -41,6 +41,7 @@ inline GemmArgs gemm_args_default() {
 // 3xTF32 kernel (gemm_tc.cu) and the FP32 FFMA tiles (gemm.cu)
 int launch_sgemm(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+unsigned long long* ctr_debug_buffer();          // buffer registered with ctr_debug_set_buffer (or NULL)
 // packed-operand engine (gemm_pk.cu): needs the scratch registered with ctr_set_scratch
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st);
 int64_t gemm_pk_scratch_bytes(int64_t M, int64_t N, int64_t K);

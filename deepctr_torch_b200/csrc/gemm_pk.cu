@@ -195,6 +195,29 @@ __global__ void __launch_bounds__(256) pack_generic_kernel(PackArgs a) {
     }
 }
 
+// fp32 tiles WITHOUT the split (TS engine, b_raw): same chunk layout, one part only — tile = R rows x 16 k =
+// [4 chunks] x [R rows] x 16 bytes.  kind::tf32 ignores the low 13 mantissa bits of what it reads (probe mode 4:
+// 16384 / 16384 products match truncation), so the raw tile IS the hi operand; the CTA derives lo itself.
+__global__ void __launch_bounds__(256) pack_raw_kernel(PackArgs a) {
+    const int64_t rows_pad = a.n_rb * a.R;
+    const int64_t total = rows_pad * a.nkb * 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cg = i / rows_pad, row = i - cg * rows_pad;
+        const int64_t kb = cg >> 2;
+        const int c = (int)(cg & 3);
+        const int64_t rb = row / a.R;
+        const int r = (int)(row - rb * a.R);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pv = &v.x;
+        for (int e = 0; e < 4; ++e) {
+            const int64_t k = cg * 4 + e;
+            if (row < a.n_rows && k < a.K) pv[e] = __ldg(a.P + row * a.s_row + k * a.s_k);
+        }
+        *reinterpret_cast<float4*>(a.out + (rb * a.nkb + kb) * (int64_t)(16 * a.R) + ((int64_t)c * a.R + r) * 4) = v;
+    }
+}
+
 bool pk_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int launch_pack(const PackArgs& a, cudaStream_t st) {
@@ -776,7 +799,18 @@ struct TsParams {
     int64_t nkb;
     int BN, MT, SB, SLOTS, RAWD, tmem_cols, a_col0, has_mask;
     uint32_t off_raw, off_bar, raw_item_bytes;
+    unsigned long long* dbg;         // optional clock64 timeline of CTA (0,0) (ctr_debug_set_buffer): [event][64 stages]
+    int b_rep; int64_t b_rep_bytes;  // experiment: b_rep replicas of the packed weights, CTA y uses replica y % b_rep
+    int b_raw;                       // weight stages arrive as raw fp32 tiles (half the bytes): hi = the raw tile, lo derived in the CTA
+    int b_lsu;                       // fetch the second half of every weight stage with cp.async from the producer warp's 32 lanes
+    int tma_split, sleep_ns;         // experiments: weight stage fetched as tma_split bulk copies; back-off of the converters' waits
+    int CL;                          // thread-block cluster size along the M tiles: every weight stage is read from L2 once
+                                     // per cluster (each CTA fetches 1/CL of it and multicasts it to all of them)
 };
+#define TS_DBG(ev, idx)                                                             \
+    do {                                                                            \
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 64) p.dbg[(ev) * 64 + (idx)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -797,9 +831,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[7 * 64 + 2] = clock64();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
     const int BN = p.BN, MT = p.MT, SB = p.SB, SLOTS = p.SLOTS;
@@ -810,7 +867,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
     uint64_t* a_full = b_empty + SB;                  // [MT * SLOTS]
     uint64_t* a_empty = a_full + MT * SLOTS;
     uint64_t* accum_bar = a_empty + MT * SLOTS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* b_rawfull = accum_bar + 1;              // [SB] raw fp32 weight tile landed (b_raw)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_rawfull + SB);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int64_t mblk = blockIdx.y, nblk = blockIdx.x;
@@ -818,8 +876,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < SB; ++s) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_rawfull[s], 1);
+            // TMA transaction (+ the 32 lanes' cp.async halves) — or, b_raw, the four warps that derived the lo half
+            mbar_init(&b_full[s], p.b_raw ? 4 : (p.b_lsu ? 33 : 1));
+            mbar_init(&b_empty[s], p.CL);             // every CTA of the cluster has finished reading the stage
         }
         for (int s = 0; s < MT * SLOTS; ++s) {
             mbar_init(&a_full[s], 4);                 // the four warps of the group that filled the slot
@@ -831,22 +891,43 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
     if (wid == 1) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
+    if (p.CL > 1) cluster_sync_all();                 // peers' barriers exist before anything is signalled remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint16_t cl_mask = (uint16_t)((1u << p.CL) - 1u);
 
     if (wid == 0) {
-        // ------------------------------ TMA producer: weight stages ------------------------------
-        if (lane == 0) {
-            const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
-            int sb = 0;
-            uint32_t phb = 1;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&b_empty[sb], phb);
-                mbar_expect_tx(&b_full[sb], b_stage);
-                bulk_g2s(ringB + (size_t)sb * b_stage, b_src + (nblk * p.nkb + i) * (int64_t)b_stage, b_stage, &b_full[sb]);
-                if (++sb == SB) { sb = 0; phb ^= 1u; }
+        // ------------------------------ producer: weight stages -----------------------------------
+        // TMA bulk copies (one lane); with b_lsu the second half of a stage travels through the LSU path instead
+        // (cp.async by all 32 lanes, completion reported to the same mbarrier): the bulk-copy path alone delivered
+        // ~19-34 B/clk per SM from L2 (3 800 cycles per 32 KB copy, runs r2-5..7), below the 39 B/clk the MMAs consume
+        const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp) + (int64_t)(mblk % p.b_rep) * p.b_rep_bytes;
+        const uint32_t tma_bytes = (p.b_lsu || p.b_raw) ? b_stage / 2 : b_stage;
+        uint64_t* const tma_bar = p.b_raw ? b_rawfull : b_full;
+        const uint32_t slice = tma_bytes / (uint32_t)p.CL, my = (p.CL > 1) ? cluster_ctarank() * slice : 0u;
+        int sb = 0;
+        uint32_t phb = 1;
+        for (int i = 0; i < nkb; ++i) {
+            mbar_wait(&b_empty[sb], phb);
+            const unsigned char* stage_src = b_src + (nblk * p.nkb + i) * (int64_t)(p.b_raw ? b_stage / 2 : b_stage);
+            unsigned char* stage_dst = ringB + (size_t)sb * b_stage;
+            if (lane == 0) {
+                TS_DBG(6, i);
+                mbar_expect_tx(&tma_bar[sb], tma_bytes);    // own slice + the peers' multicast slices
+                const uint32_t piece = slice / (uint32_t)p.tma_split;
+                for (int q = 0; q < p.tma_split; ++q) {
+                    if (p.CL > 1) bulk_g2s_mcast(stage_dst + my + q * piece, stage_src + my + q * piece, piece, &tma_bar[sb], cl_mask);
+                    else bulk_g2s(stage_dst + my + q * piece, stage_src + my + q * piece, piece, &tma_bar[sb]);
+                }
             }
+            if (p.b_lsu) {
+                for (uint32_t off = tma_bytes + (uint32_t)lane * 16u; off < b_stage; off += 32u * 16u)
+                    cp_async16(stage_dst + off, stage_src + off, 16);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&b_full[sb])) : "memory");
+            }
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
         }
+        if (p.b_lsu) cp_async_wait<0>();
         __syncwarp();
     } else if (wid == 1) {
         // ------------------------------ MMA issuer ------------------------------------------------
@@ -858,7 +939,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             const int slot = i % SLOTS;
             const uint32_t pa = (uint32_t)((i / SLOTS) & 1);
             mbar_wait(&b_full[sb], phb);
+            if (lane == 0) TS_DBG(0, i);
             for (int mt = 0; mt < MT; ++mt) mbar_wait(&a_full[mt * SLOTS + slot], pa);
+            if (lane == 0) TS_DBG(1, i);
+            if (p.b_lsu) fence_async_smem();              // cp.async (generic proxy) half of the stage -> tcgen05.mma (async proxy)
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
@@ -875,9 +959,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
                         umma_tf32_ts(d, a_hi, dbh, idesc, 1u);
                     }
                 }
-                umma_commit(&b_empty[sb]);                // frees the stage / the slots when these MMAs retire
+                // frees the stage (in every CTA of the cluster) / the slots when these MMAs retire
+                if (p.CL > 1) umma_commit_mcast(&b_empty[sb], cl_mask);
+                else umma_commit(&b_empty[sb]);
                 for (int mt = 0; mt < MT; ++mt) umma_commit(&a_empty[mt * SLOTS + slot]);
                 if (i == nkb - 1) umma_commit(accum_bar);
+                TS_DBG(2, i);
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; phb ^= 1u; }
@@ -928,6 +1015,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             else if (p.RAWD == 2) cp_async_wait<1>();
             else cp_async_wait<0>();
             __syncwarp();                                  // the warp's lanes copied each other's rows
+            if (quad == 0 && lane == 0) TS_DBG(3, i);
             const unsigned char* buf = raw_grp + (size_t)(done % p.RAWD) * p.raw_item_bytes;
             const float* myrow = reinterpret_cast<const float*>(buf) + (quad * 32 + lane) * TS_RAW_PITCH;
             float hi[16], lo[16];
@@ -942,7 +1030,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             __syncwarp();                                  // every lane has read its row: the raw tile may be refilled
             issue();
-            mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            if (p.sleep_ns > 0) {
+                while (!mbar_try_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1))) __nanosleep(p.sleep_ns);
+            } else {
+                mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            }
+            if (quad == 0 && lane == 0) TS_DBG(4, i);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + (mt * SLOTS + slot) * 32);
             tmem_st16(taddr, hi);
@@ -951,15 +1044,40 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[mt * SLOTS + slot]);
+            if (quad == 0 && lane == 0) TS_DBG(5, i);
+            if (p.b_raw && mt == 0) {
+                // the weight stage of this k block arrived as raw fp32 (= hi after the tensor core's truncation):
+                // lo = RN_tf32(w - trunc(w)), elementwise over the tile (the chunk layout does not matter)
+                const int sbi = i % SB;
+                mbar_wait(&b_rawfull[sbi], (uint32_t)((i / SB) & 1));
+                float4* hi4 = reinterpret_cast<float4*>(ringB + (size_t)sbi * b_stage);
+                float4* lo4 = reinterpret_cast<float4*>(ringB + (size_t)sbi * b_stage + b_stage / 2);
+                const int n4 = (int)(b_stage / 32);           // float4 per half
+                for (int q = (cw & 3) * 32 + lane; q < n4; q += 128) {
+                    const float4 w = hi4[q];
+                    float4 l;
+                    l.x = rn_tf32(w.x - __uint_as_float(__float_as_uint(w.x) & 0xFFFFE000u));
+                    l.y = rn_tf32(w.y - __uint_as_float(__float_as_uint(w.y) & 0xFFFFE000u));
+                    l.z = rn_tf32(w.z - __uint_as_float(__float_as_uint(w.z) & 0xFFFFE000u));
+                    l.w = rn_tf32(w.w - __uint_as_float(__float_as_uint(w.w) & 0xFFFFE000u));
+                    lo4[q] = l;
+                }
+                fence_async_smem();                           // generic-proxy stores -> async proxy (tcgen05.mma)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[sbi]);
+            }
         }
         cp_async_wait<0>();
         // ------------------------------ epilogue (16 warps) ---------------------------------------
         mbar_wait(accum_bar, 0);
+        if (wid == 2 && lane == 0) TS_DBG(7, 0);
         tc_fence_after();
         tile_epilogue<EPI>(g, tmem_base, smem_raw, wid, lane, mblk * MT * PK_AR, MT, BN, nblk * BN, false);
+        if (wid == 2 && lane == 0) TS_DBG(7, 1);
         tc_fence_before();
     }
     __syncthreads();
+    if (p.CL > 1) cluster_sync_all();                 // nobody leaves while a peer may still multicast into / signal this CTA
     if (wid == 1) {
         tc_fence_after();
         tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
@@ -1155,6 +1273,9 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     const int BN = (int)(ceil_div64(ceil_div64(g.N, gn), 16) * 16);
     const int MT = (BN <= 128 && g.M >= 2 * PK_AR * ctr_sm_count()) ? 2 : 1;
     const int64_t nkb = ceil_div64(g.K, PK_KB);
+    // fewer tiles than SMs: the SS engine splits K across CTAs (and its shorter accumulation chains lose less to the
+    // tensor core's truncating fp32 adds: 1.2e-6 vs 1.2e-5 at K = 1664)
+    if (ceil_div64(g.M, (int64_t)PK_AR * MT) * gn < ctr_sm_count() && nkb >= 16) return -3;
     const int64_t b_bytes = gn * nkb * (int64_t)BN * 128;
     if (b_bytes > kStreamThresholdBytes) return -3;           // B is not a "small weight" operand
     const int64_t a_packed = ceil_div64(g.M, PK_AR) * nkb * (int64_t)PK_AR * 128;
@@ -1169,6 +1290,7 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     p.BN = BN;
     p.MT = MT;
     p.has_mask = g.amask ? 1 : 0;
+    p.dbg = ctr_debug_buffer();
     p.a_col0 = MT * BN;
     int cols_left = 512 - p.a_col0;
     p.SLOTS = cols_left / (32 * MT);
@@ -1180,9 +1302,53 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     const int64_t budget = 232448 - 1024;
     const int64_t b_stage = (int64_t)BN * 128;
     const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;
+    // cluster of CL CTAs (consecutive M tiles, same weight tiles): every CTA fetches 1/CL of a weight stage and
+    // multicasts it, so the L2 -> SM traffic of the weights drops CL-fold (run r2-5 timeline: 32 KB per 128 x 16
+    // stage from L2 was the pacing item, 3 800 cycles per copy with four in flight).  CTR_TS_CLUSTER=1|2|4.
+    {
+        static int cl_env = -1;
+        if (cl_env < 0) {
+            const char* ce = getenv("CTR_TS_CLUSTER");
+            cl_env = ce ? atoi(ce) : 1;
+            if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
+        }
+        p.CL = cl_env;
+        while (p.CL > 1 && (b_stage % (16 * p.CL)) != 0) p.CL >>= 1;
+    }
+    // the weight ring wants depth (the copies' latency is ~4 stages of MMA time), the raw tiles need little: the
+    // converters run far ahead of the MMAs anyway
+    static int sb_env = -1, rawd_env = -1, split_env = 1, sleep_env = 0;
+    if (sb_env < 0) {
+        const char* e1 = getenv("CTR_TS_SB");
+        const char* e2 = getenv("CTR_TS_RAWD");
+        const char* e3 = getenv("CTR_TS_TMA_SPLIT");
+        const char* e4 = getenv("CTR_TS_SLEEP");
+        sb_env = e1 ? atoi(e1) : 0;
+        rawd_env = e2 ? atoi(e2) : 0;
+        split_env = e3 ? atoi(e3) : 1;
+        sleep_env = e4 ? atoi(e4) : 0;
+        if (split_env != 1 && split_env != 2 && split_env != 4 && split_env != 8) split_env = 1;
+    }
+    p.tma_split = split_env;
+    p.sleep_ns = sleep_env;
+    {
+        static int lsu_env = -1;
+        if (lsu_env < 0) {
+            const char* e5 = getenv("CTR_TS_BLSU");
+            lsu_env = (e5 && e5[0] == '1') ? 1 : 0;
+        }
+        p.b_lsu = (lsu_env && p.CL == 1) ? 1 : 0;
+        static int raw_env = -1;
+        if (raw_env < 0) {
+            const char* e6 = getenv("CTR_TS_BRAW");
+            raw_env = (e6 && e6[0] == '0') ? 0 : 1;
+        }
+        p.b_raw = raw_env;
+        if (p.b_raw) p.b_lsu = 0;
+    }
     p.SB = 0;
-    for (int rawd = 3; rawd >= 1 && !p.SB; --rawd)
-        for (int sbn = 5; sbn >= 3 && !p.SB; --sbn) {
+    for (int rawd = (rawd_env ? rawd_env : 2); rawd >= 1 && !p.SB; --rawd)
+        for (int sbn = (sb_env ? sb_env : 6); sbn >= 3 && !p.SB; --sbn) {
             const int64_t need = sbn * b_stage + (int64_t)TS_NG * rawd * p.raw_item_bytes;
             if (need <= budget) {
                 p.SB = sbn;
@@ -1195,13 +1361,36 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     int64_t end = rings + (int64_t)TS_NG * p.RAWD * p.raw_item_bytes;
     if (end < stg) end = stg;
     p.off_bar = (uint32_t)((end + 15) / 16 * 16);
-    const size_t smem = p.off_bar + (size_t)(2 * p.SB + 2 * MT * p.SLOTS + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = p.off_bar + (size_t)(3 * p.SB + 2 * MT * p.SLOTS + 1) * sizeof(uint64_t) + 16;
     if (smem > 232448) return -3;
-    const int64_t gm = ceil_div64(g.M, (int64_t)PK_AR * MT);
+    int64_t gm = ceil_div64(g.M, (int64_t)PK_AR * MT);
+    gm = ceil_div64(gm, p.CL) * p.CL;               // whole clusters: a CTA past the matrix only feeds its peers' weight stages
     if (gm > 65535) return -3;
     PackArgs pb{g.B, g.sbn, g.sbk, nullptr, 0, 0, 0, g.N, g.K, BN, gn, nkb, reinterpret_cast<float*>(scratch)};
     int rc;
-    if ((rc = launch_pack(pb, st)) != 0) return rc;
+    if (p.b_raw) {
+        int64_t blocks = ceil_div64(gn * BN * nkb * 4, 256);
+        if (blocks > (int64_t)ctr_sm_count() * 8) blocks = (int64_t)ctr_sm_count() * 8;
+        pack_raw_kernel<<<(unsigned)blocks, 256, 0, st>>>(pb);
+        CTR_LAUNCH_OK("pack_raw_kernel");
+    } else if ((rc = launch_pack(pb, st)) != 0) {
+        return rc;
+    }
+    {
+        static int rep_env = -1;
+        if (rep_env < 0) {
+            const char* e7 = getenv("CTR_TS_BREP");
+            rep_env = e7 ? atoi(e7) : 1;
+            if (rep_env < 1) rep_env = 1;
+        }
+        const int64_t one = (p.b_raw ? b_bytes / 2 : b_bytes);
+        p.b_rep_bytes = (one + 255) / 256 * 256;
+        p.b_rep = rep_env;
+        while (p.b_rep > 1 && p.b_rep * p.b_rep_bytes > g_scratch_bytes[dev]) p.b_rep >>= 1;
+        for (int r = 1; r < p.b_rep; ++r)
+            CTR_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(scratch) + r * p.b_rep_bytes, scratch, (size_t)one,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
     static bool configured = false;
     if (!configured) {
         const int max_smem = 232448;
@@ -1212,13 +1401,24 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
         CTR_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
-    dim3 grid((unsigned)gn, (unsigned)gm, 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)gn, (unsigned)gm, 1);
+    cfg.blockDim = dim3(PK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)p.CL;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     switch (g.epilogue) {
-        case EPI_BIAS_ACT: gemm_ts_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_MUL_ACTGRAD: gemm_ts_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_CROSS: gemm_ts_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_MUL: gemm_ts_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p); break;
-        default: gemm_ts_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_BIAS_ACT: CTR_CUDA(cudaLaunchKernelEx(&cfg, gemm_ts_kernel<EPI_BIAS_ACT>, p)); break;
+        case EPI_MUL_ACTGRAD: CTR_CUDA(cudaLaunchKernelEx(&cfg, gemm_ts_kernel<EPI_MUL_ACTGRAD>, p)); break;
+        case EPI_CROSS: CTR_CUDA(cudaLaunchKernelEx(&cfg, gemm_ts_kernel<EPI_CROSS>, p)); break;
+        case EPI_MUL: CTR_CUDA(cudaLaunchKernelEx(&cfg, gemm_ts_kernel<EPI_MUL>, p)); break;
+        default: CTR_CUDA(cudaLaunchKernelEx(&cfg, gemm_ts_kernel<EPI_STORE>, p)); break;
     }
     CTR_LAUNCH_OK("gemm_ts_kernel");
     return 0;

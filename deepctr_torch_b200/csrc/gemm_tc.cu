@@ -431,6 +431,7 @@ int pick_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int
 }  // namespace
 
 static unsigned long long* g_dbg_buf = nullptr;
+unsigned long long* ctr_debug_buffer() { return g_dbg_buf; }
 extern "C" int ctr_debug_set_buffer(void* ptr) {
     g_dbg_buf = reinterpret_cast<unsigned long long*>(ptr);
     return 0;

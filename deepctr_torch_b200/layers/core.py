@@ -28,13 +28,16 @@ class DNN(nn.Module):
         self.use_bn = use_bn
         if len(hidden_units) == 0:
             raise ValueError("hidden_units is empty!!")
-        if not isinstance(activation, str) or activation.lower() not in ops.ACT_CODES:
+        if not isinstance(activation, str) or activation.lower() not in tuple(ops.ACT_CODES) + ("prelu",):
             raise NotImplementedError("DNN activation %r is not implemented by the CUDA tower" % (activation,))
         self.activation = activation.lower()
         units = [inputs_dim] + list(hidden_units)
         self.linears = nn.ModuleList([nn.Linear(units[i], units[i + 1]) for i in range(len(units) - 1)])
         if self.use_bn:
             self.bn = nn.ModuleList([nn.BatchNorm1d(units[i + 1]) for i in range(len(units) - 1)])
+        if self.activation == "prelu":
+            # same container and key names as the reference (`activation_layers.<i>.weight`, core.py:110-111)
+            self.activation_layers = nn.ModuleList([nn.PReLU() for _ in range(len(units) - 1)])
         for name, tensor in self.linears.named_parameters():
             if "weight" in name:
                 nn.init.normal_(tensor, mean=0, std=init_std)
@@ -42,6 +45,15 @@ class DNN(nn.Module):
 
     def forward(self, inputs):
         x = inputs
+        if self.activation == "prelu":
+            for i, lin in enumerate(self.linears):
+                x = ops.dnn_layer(x, lin.weight, lin.bias, "linear")
+                if self.use_bn:
+                    x = self.bn[i](x)
+                x = ops.prelu(x, self.activation_layers[i].weight)
+                if self.dropout_rate > 0:
+                    x = F.dropout(x, self.dropout_rate, self.training)
+            return x
         if not self.use_bn and not (self.dropout_rate > 0 and self.training):
             # the whole stack as one autograd node: the backward hands dZ from layer to layer
             return ops.dnn_tower(x, self.activation, [lin.weight for lin in self.linears],

@@ -202,8 +202,6 @@ class BaseModel(nn.Module):
         if self.table_grad != "dense":
             raise NotImplementedError("per-field linear terms (IFM / DIFM) need table_grad='dense'")
         main = self._gather_plan(X.device)
-        if main.lin_varlen:
-            raise NotImplementedError("per-field linear terms with VarLenSparseFeat linear columns")
         lp = getattr(self, "_lin_plan", None)
         if lp is None or lp.device != X.device or lp.id_mode != main.id_mode:
             fi = self.feature_index
@@ -217,6 +215,14 @@ class BaseModel(nn.Module):
         ldw = self.linear_model.weight if lp.n_lin_dense > 0 else None
         blk, lin, _ = ops.fused_input(X, lp, ldw, want_blk=lp.n_emb > 0, want_fm=False, grad_mode="dense")
         L = blk[:, :lp.n_emb] if lp.n_emb > 0 else None
+        if main.lin_varlen:        # pooled dim-1 rows of the VarLen linear columns follow the sparse ones (basemodel.py:74-77)
+            parts = [L] if L is not None else []
+            for c in main.lin_varlen:
+                s, e = self.feature_index[c.name]
+                lcol = self.feature_index[c.length_name][0] if c.length_name is not None else None
+                parts.append(ops.varlen_pool(X, self.linear_model.embedding_dict[c.embedding_name].weight, s, e - s,
+                                             lcol, c.combiner, main.err_flag, main.id_mode))
+            L = torch.cat(parts, dim=1)
         return L, (lin if ldw is not None else None)
 
     def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):

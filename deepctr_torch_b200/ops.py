@@ -276,7 +276,7 @@ class _FusedInput(torch.autograd.Function):
                       plan.n_shards, plan.id_mode, _stream())
         ctx.plan_event = None
         ctx.lease = None
-        if grad_mode in ("rowwise", "sharded") and torch.is_grad_enabled() and B > 0:
+        if grad_mode in ("rowwise", "sharded") and torch.is_grad_enabled() and B > 0 and plan.plan_cols_host:
             # the duplicate-free plan of the backward depends only on X: build it now on a side stream
             # so that it overlaps the forward tower instead of sitting on the backward's critical path.
             # The workspace belongs to THIS autograd node (a second forward must not overwrite it).
@@ -347,6 +347,8 @@ class _FusedInput(torch.autograd.Function):
                       _ptr(d_fm), _ptr(d_lin), plan.id_mode, _stream())
             return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
         # row-wise: (unique ids, summed row grads) per table
+        if not plan.plan_cols_host:            # no sparse feature at all: nothing to scatter
+            return (None, None, d_ldw, None, None, None) + tuple(grads_emb) + tuple(grads_lin)
         lease = ctx.lease
         n_plan = len(plan.plan_cols_host)
         if lease is not None:
@@ -1237,3 +1239,30 @@ def binary_cross_entropy(y_pred, y, reduction="mean", **kw):
             and y_pred.dtype == torch.float32 and y_pred.numel() == y.numel():
         return _BceSum.apply(y_pred, y)
     return torch.nn.functional.binary_cross_entropy(y_pred, y, reduction=reduction, **kw)
+
+
+class _PReLU(torch.autograd.Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, z, alpha):
+        _require_cuda(z, "PReLU input")
+        zc = z.contiguous()
+        y = torch.empty_like(zc)
+        _lib.call("ctr_prelu_fwd", _ptr(zc), _ptr(alpha), zc.numel(), _ptr(y), _stream())
+        ctx.save_for_backward(zc, alpha)
+        return y
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dy):
+        zc, alpha = ctx.saved_tensors
+        dy = dy.contiguous()
+        dz = torch.empty_like(zc)
+        dalpha = torch.empty_like(alpha)
+        _lib.call("ctr_prelu_bwd", _ptr(zc), _ptr(alpha), _ptr(dy), zc.numel(), _ptr(dz), _ptr(dalpha), _stream())
+        return dz, dalpha
+
+
+def prelu(z, alpha):
+    """nn.PReLU() with a single slope (reference layers/activation.py:61-62)."""
+    return _PReLU.apply(z, alpha)

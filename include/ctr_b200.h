@@ -37,7 +37,7 @@ int         ctr_debug_set_buffer(void* dev_u64_buffer);   /* optional: per-stage
 int64_t     ctr_launch_count(void);       /* kernels launched by this library so far (process-wide) */
 
 /* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
-enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3, CTR_ACT_PRELU = 4 };
+enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3 };
 enum { CTR_IDS_F32 = 0, CTR_IDS_I32BITS = 1 };
 
 /* ---- a4+a5+a6+a7: fused multi-slot gather + linear term + FM + dnn_input assembly --------
@@ -355,6 +355,12 @@ int ctr_sumsq_acc(const float* w, int64_t n, float scale, float* out, void* stre
  * fwd: out[0] = sum_b -(y log p + (1-y) log(1-p));  bwd: d_pred[b] = g[0] * (p - y) / max(p (1-p), 1e-12) */
 int ctr_bce_sum_fwd(const float* y_pred, const float* y, int64_t B, float* out, void* stream);
 int ctr_bce_sum_bwd(const float* y_pred, const float* y, const float* g, int64_t B, float* d_pred, void* stream);
+
+/* PReLU with one learnable slope (reference layers/activation.py:61-62, `dnn_activation='prelu'`): elementwise over n
+ * values; bwd zero-fills and accumulates dalpha[0] = sum dy * min(z, 0) */
+int ctr_prelu_fwd(const float* z, const float* alpha, int64_t n, float* y, void* stream);
+int ctr_prelu_bwd(const float* z, const float* alpha, const float* dy, int64_t n, float* dz, float* dalpha,
+                  void* stream);
 
 /* ---- VarLenSparseFeat pooled lookup (reference inputs.py:141-155, layers/sequence.py:49-77)
  * ids X[b, col .. col+T); mask = (id != 0) when len_col < 0, else t < (int)X[b,len_col].

@@ -244,7 +244,11 @@ def dnn(params, prefix, x, activation="relu"):
     while (prefix + "linears.%d.weight" % i) in params:
         w = params[prefix + "linears.%d.weight" % i]
         b = params[prefix + "linears.%d.bias" % i]
-        x = _activation(activation, F.linear(x, w, b))
+        z = F.linear(x, w, b)
+        if (activation or "").lower() == "prelu":        # nn.PReLU() per layer (reference activation.py:61-62)
+            x = F.prelu(z, params[prefix + "activation_layers.%d.weight" % i])
+        else:
+            x = _activation(activation, z)
         i += 1
     return x
 

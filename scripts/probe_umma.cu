@@ -102,6 +102,141 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* A, const flo
     }
 }
 
+// Timing: one thread issues `n_mma` back-to-back kind::tf32 MMAs (M = 128, N columns) and commits; cycles from the
+// first issue to the completion mbarrier.  variant bit0: A from TMEM (TS) instead of shared memory; bit1: alternate between two
+// accumulators; bit2: B (and A) described as SWIZZLE_128B K-major (timing only: the data is not laid out for it).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+__global__ void __launch_bounds__(128, 1) time_kernel(int N, int n_mma, int variant, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 32; i += 128) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 63);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 0) tmem_alloc_warp(&tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = tf32_idesc(N);
+        const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 128 * 128);
+        const bool ts = variant & 1, alt = variant & 2, sw = variant & 4;
+        const long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t k = (uint32_t)(i & 3);
+            const uint64_t da = sw ? make_desc_sw128(sa + k * 32u) : make_smem_desc(sa + k * 4096u, 2048, 128);
+            const uint64_t db = sw ? make_desc_sw128(sb + k * 32u) : make_smem_desc(sb + k * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128);
+            const uint32_t d = tbase + ((alt && (i & 1)) ? 256u : 0u);
+            if (ts) umma_tf32_ts(d, tbase + 480u + 8u * (k & 1), db, idesc, 1u);
+            else umma_tf32(d, da, db, idesc, 1u);
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        tc_fence_after();
+        tmem_dealloc_warp(tbase, 512);
+    }
+}
+
+// Interference: the TS N=256 MMA stream of time_kernel while the other warps of the CTA (a) spin on an mbarrier that never
+// completes, (b) stream LDS.128 over 32 KB, (c) stream STS.128, (d) one thread keeps 32 KB cp.async.bulk copies in flight.
+__global__ void __launch_bounds__(576, 1) interfere_kernel(int n_mma, int what, const float* gsrc, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar, never, tbar[4];
+    __shared__ uint32_t tmem_slot;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 48 * 1024 / 4; i += 576) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 63);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&never, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&tbar[i], 1);
+        stop = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 0) tmem_alloc_warp(&tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    if (wid == 0) {
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(256);
+            const uint32_t sb = smem_u32(smem);
+            const long long t0 = clock64();
+            for (int i = 0; i < n_mma; ++i) {
+                const uint32_t k = (uint32_t)(i & 3);
+                const uint64_t db = make_smem_desc(sb + k * 2u * 4096u, 4096u, 128);
+                umma_tf32_ts(tbase, tbase + 480u + 8u * (k & 1), db, idesc, 1u);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            out[what] = clock64() - t0;
+            stop = 1;
+        }
+    } else if (wid == 1 && what == 4) {
+        if (lane == 0) {      // keep 4 x 32 KB bulk copies global -> smem (region 48..176 KB) in flight
+            uint32_t ph[4] = {0, 0, 0, 0};
+            for (int q = 0; q < 4; ++q) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tbar[q])), "r"(32768u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(smem + 49152 + q * 32768)), "l"(gsrc + q * 8192), "r"(32768u), "r"(smem_u32(&tbar[q])) : "memory");
+            }
+            int q = 0;
+            while (!stop) {
+                mbar_wait(&tbar[q], ph[q]);
+                ph[q] ^= 1u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tbar[q])), "r"(32768u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(smem + 49152 + q * 32768)), "l"(gsrc + q * 8192), "r"(32768u), "r"(smem_u32(&tbar[q])) : "memory");
+                q = (q + 1) & 3;
+            }
+            for (int k = 0; k < 4; ++k) mbar_wait(&tbar[k], ph[k]);
+        }
+    } else if (wid >= 2) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* reg = reinterpret_cast<float4*>(smem + 49152 + (wid - 2) * 8192);     // 8 KB per warp
+        if (what == 1) {
+            while (!stop) (void)mbar_try_wait(&never, 0);
+        } else if (what == 2) {
+            while (!stop)
+                for (int j = 0; j < 16; ++j) {
+                    const float4 v = reg[j * 32 + lane];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+        } else if (what == 3) {
+            while (!stop)
+                for (int j = 0; j < 16; ++j) reg[j * 32 + lane] = acc;
+        }
+        if (acc.x == 123.456f) out[7] = 1;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        tc_fence_after();
+        tmem_dealloc_warp(tbase, 512);
+    }
+}
+
 float rn_tf32_h(float x) {
     uint32_t u;
     memcpy(&u, &x, 4);
@@ -178,5 +313,39 @@ int main() {
         }
     printf("mode 4 (fp32 inputs that are not tf32-exact): matches truncation %d, round-to-nearest %d, neither %d of %d\n",
            n_tr, n_rn, n_other, M * N);
+    long long* dt;
+    CK(cudaMalloc(&dt, 64));
+    CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const char* names[8] = {"SS", "TS", "SS 2 accumulators", "TS 2 accumulators", "SS sw128", "TS sw128", "SS sw128 2 acc", "TS sw128 2 acc"};
+    for (int Nn = 128; Nn <= 256; Nn += 128)
+        for (int v = 0; v < 8; ++v) {
+            long long h[2];
+            for (int rep = 0; rep < 2; ++rep) {
+                time_kernel<<<1, 128, 196 * 1024>>>(Nn, 96, v, dt);
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(h, dt, 16, cudaMemcpyDeviceToHost));
+            printf("timing N=%d %-22s: issue %5.1f clk/MMA, issue->complete %6.1f clk/MMA (ideal %d)\n", Nn, names[v], h[0] / 96.0,
+                   h[1] / 96.0, Nn / 2);
+        }
+    {
+        float* gsrc;
+        CK(cudaMalloc(&gsrc, 4 * 32768));
+        CK(cudaMemset(gsrc, 0, 4 * 32768));
+        CK(cudaFuncSetAttribute(interfere_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const char* wn[5] = {"alone", "16 warps spinning on an mbarrier", "16 warps LDS.128 streaming", "16 warps STS.128 streaming",
+                             "4 x 32 KB bulk copies in flight"};
+        for (int w = 0; w < 5; ++w) {
+            for (int rep = 0; rep < 2; ++rep) {
+                interfere_kernel<<<1, 576, 196 * 1024>>>(192, w, gsrc, dt);
+                CK(cudaDeviceSynchronize());
+            }
+            long long h[8];
+            CK(cudaMemcpy(h, dt, 16, cudaMemcpyDeviceToHost));
+            long long v;
+            CK(cudaMemcpy(&v, dt + w, 8, cudaMemcpyDeviceToHost));
+            printf("interference TS N=256, %-34s: %6.1f clk/MMA\n", wn[w], v / 192.0);
+        }
+    }
     return 0;
 }

@@ -18,6 +18,7 @@ def gemm(A, sam, sak, Bm, sbn, sbk, M, N, K, C=None):
     if C is None:
         C = torch.full((M, N), float("nan"), device="cuda")
     ops.ensure_gemm_scratch(DEV, M, K, N)
+    ops.ensure_scratch_bytes(DEV, int(os.environ.get("CTR_TS_BREP", "1")) * (2 << 20))
     _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), sam, sak, ops._ptr(Bm), sbn, sbk, ops._ptr(C), N, 0, ops._stream())
     return C
 

@@ -194,6 +194,8 @@ def extra_cases():
     cases.append(("deepfm_nolinear", O.make_cfg("DeepFM", [], c5, dnn_hidden_units=[16, 8], init_std=std), 20))
     cases.append(("deepfm_dropout_eval", O.make_cfg("DeepFM", c5, c5, dnn_hidden_units=[32, 32], dnn_dropout=0.5,
                                                     init_std=std), 24, None, 7, True))
+    cases.append(("deepfm_prelu", O.make_cfg("DeepFM", c5, c5, dnn_hidden_units=[32, 16], dnn_activation="prelu",
+                                             init_std=std), 32))
     cases.append(("dcnmix_cross0", O.make_cfg("DCNMix", c5, c5, cross_num=0, dnn_hidden_units=[16, 8],
                                               init_std=std), 20))
     cases.append(("dcn_cross0", O.make_cfg("DCN", c5, c5, cross_num=0, dnn_hidden_units=[16, 8], init_std=std), 20))
@@ -342,8 +344,12 @@ if __name__ == "__main__":
             run_model_case(*case)
         layer_cases()
         fit_case()
+    only = [a[7:] for a in sys.argv if a.startswith("--only=")]
     for case in extra_cases():
-        run_model_case(*case)
+        if not only or case[0] in only:
+            run_model_case(*case)
+    if only:
+        sys.exit(0)
     extra_layer_cases()
     # the fused row-wise optimizer equals the dense torch optimizer for sgd / adagrad at l2 = 0
     fit_case("sgd", 0.0, "fit_sgd_l2zero")

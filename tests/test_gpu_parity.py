@@ -20,6 +20,8 @@ def _run_case(c, table_grad):
     m = build_model(c["cfg"], DEV, table_grad=table_grad)
     m.load_state_dict(c["state"])
     m.train()
+    if c["cfg"]["kwargs"].get("dnn_dropout", 0) > 0:
+        m.eval()                    # dropout goldens are recorded in eval mode (deterministic)
     X = c["X"].to(DEV)
     y = c["y"].to(DEV)
     y_pred, logit = capture_logit(m, X)
