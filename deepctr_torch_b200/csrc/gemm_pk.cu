@@ -792,6 +792,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
 constexpr int TS_NG = 4;                          // converter groups
 constexpr int TS_RAW_PITCH = 20;                  // floats per row of a raw item (16 k + 4 padding: conflict-free LDS.128)
 constexpr uint32_t TS_RAW_TILE = PK_AR * TS_RAW_PITCH * 4;    // 10 240 bytes: 128 rows
+constexpr int TS_THREADS = PK_THREADS + 128;                  // + 4 warps that derive the lo half of raw weight stages
 
 struct TsParams {
     GemmArgs g;
@@ -800,10 +801,7 @@ struct TsParams {
     int BN, MT, SB, SLOTS, RAWD, tmem_cols, a_col0, has_mask;
     uint32_t off_raw, off_bar, raw_item_bytes;
     unsigned long long* dbg;         // optional clock64 timeline of CTA (0,0) (ctr_debug_set_buffer): [event][64 stages]
-    int b_rep; int64_t b_rep_bytes;  // experiment: b_rep replicas of the packed weights, CTA y uses replica y % b_rep
     int b_raw;                       // weight stages arrive as raw fp32 tiles (half the bytes): hi = the raw tile, lo derived in the CTA
-    int b_lsu;                       // fetch the second half of every weight stage with cp.async from the producer warp's 32 lanes
-    int tma_split, sleep_ns;         // experiments: weight stage fetched as tma_split bulk copies; back-off of the converters' waits
     int CL;                          // thread-block cluster size along the M tiles: every weight stage is read from L2 once
                                      // per cluster (each CTA fetches 1/CL of it and multicasts it to all of them)
 };
@@ -855,7 +853,7 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) 
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
+__global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[7 * 64 + 2] = clock64();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
@@ -877,8 +875,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
     if (tid == 0) {
         for (int s = 0; s < SB; ++s) {
             mbar_init(&b_rawfull[s], 1);
-            // TMA transaction (+ the 32 lanes' cp.async halves) — or, b_raw, the four warps that derived the lo half
-            mbar_init(&b_full[s], p.b_raw ? 4 : (p.b_lsu ? 33 : 1));
+            // TMA transaction — or, b_raw, the four warps that derived the lo half
+            mbar_init(&b_full[s], p.b_raw ? 4 : 1);
             mbar_init(&b_empty[s], p.CL);             // every CTA of the cluster has finished reading the stage
         }
         for (int s = 0; s < MT * SLOTS; ++s) {
@@ -897,37 +895,25 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
     const uint16_t cl_mask = (uint16_t)((1u << p.CL) - 1u);
 
     if (wid == 0) {
-        // ------------------------------ producer: weight stages -----------------------------------
-        // TMA bulk copies (one lane); with b_lsu the second half of a stage travels through the LSU path instead
-        // (cp.async by all 32 lanes, completion reported to the same mbarrier): the bulk-copy path alone delivered
-        // ~19-34 B/clk per SM from L2 (3 800 cycles per 32 KB copy, runs r2-5..7), below the 39 B/clk the MMAs consume
-        const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp) + (int64_t)(mblk % p.b_rep) * p.b_rep_bytes;
-        const uint32_t tma_bytes = (p.b_lsu || p.b_raw) ? b_stage / 2 : b_stage;
-        uint64_t* const tma_bar = p.b_raw ? b_rawfull : b_full;
-        const uint32_t slice = tma_bytes / (uint32_t)p.CL, my = (p.CL > 1) ? cluster_ctarank() * slice : 0u;
-        int sb = 0;
-        uint32_t phb = 1;
-        for (int i = 0; i < nkb; ++i) {
-            mbar_wait(&b_empty[sb], phb);
-            const unsigned char* stage_src = b_src + (nblk * p.nkb + i) * (int64_t)(p.b_raw ? b_stage / 2 : b_stage);
-            unsigned char* stage_dst = ringB + (size_t)sb * b_stage;
-            if (lane == 0) {
+        // ------------------------------ TMA producer: weight stages -------------------------------
+        if (lane == 0) {
+            const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
+            const uint32_t tma_bytes = p.b_raw ? b_stage / 2 : b_stage;
+            uint64_t* const tma_bar = p.b_raw ? b_rawfull : b_full;
+            const uint32_t slice = tma_bytes / (uint32_t)p.CL, my = (p.CL > 1) ? cluster_ctarank() * slice : 0u;
+            int sb = 0;
+            uint32_t phb = 1;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&b_empty[sb], phb);
                 TS_DBG(6, i);
                 mbar_expect_tx(&tma_bar[sb], tma_bytes);    // own slice + the peers' multicast slices
-                const uint32_t piece = slice / (uint32_t)p.tma_split;
-                for (int q = 0; q < p.tma_split; ++q) {
-                    if (p.CL > 1) bulk_g2s_mcast(stage_dst + my + q * piece, stage_src + my + q * piece, piece, &tma_bar[sb], cl_mask);
-                    else bulk_g2s(stage_dst + my + q * piece, stage_src + my + q * piece, piece, &tma_bar[sb]);
-                }
+                const unsigned char* src = b_src + (nblk * p.nkb + i) * (int64_t)tma_bytes + my;
+                unsigned char* dst = ringB + (size_t)sb * b_stage + my;
+                if (p.CL > 1) bulk_g2s_mcast(dst, src, slice, &tma_bar[sb], cl_mask);
+                else bulk_g2s(dst, src, slice, &tma_bar[sb]);
+                if (++sb == SB) { sb = 0; phb ^= 1u; }
             }
-            if (p.b_lsu) {
-                for (uint32_t off = tma_bytes + (uint32_t)lane * 16u; off < b_stage; off += 32u * 16u)
-                    cp_async16(stage_dst + off, stage_src + off, 16);
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&b_full[sb])) : "memory");
-            }
-            if (++sb == SB) { sb = 0; phb ^= 1u; }
         }
-        if (p.b_lsu) cp_async_wait<0>();
         __syncwarp();
     } else if (wid == 1) {
         // ------------------------------ MMA issuer ------------------------------------------------
@@ -942,7 +928,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             if (lane == 0) TS_DBG(0, i);
             for (int mt = 0; mt < MT; ++mt) mbar_wait(&a_full[mt * SLOTS + slot], pa);
             if (lane == 0) TS_DBG(1, i);
-            if (p.b_lsu) fence_async_smem();              // cp.async (generic proxy) half of the stage -> tcgen05.mma (async proxy)
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
@@ -968,6 +953,34 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; phb ^= 1u; }
+        }
+    } else if (wid >= 2 + PK_CONV_WARPS) {
+        // ------------------------------ weight-lo warps (b_raw) -----------------------------------
+        // The weight stage arrived as raw fp32 (= hi after the tensor core's truncation): lo = RN_tf32(w - trunc(w)),
+        // elementwise over the tile (the chunk layout does not matter).  Half the bytes cross L2 -> SM.
+        if (p.b_raw) {
+            const int t = tid - (2 + PK_CONV_WARPS) * 32;
+            const int n4 = (int)(b_stage / 32);               // float4 per half
+            int sb = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&b_rawfull[sb], ph);
+                float4* hi4 = reinterpret_cast<float4*>(ringB + (size_t)sb * b_stage);
+                float4* lo4 = reinterpret_cast<float4*>(ringB + (size_t)sb * b_stage + b_stage / 2);
+                for (int q = t; q < n4; q += 128) {
+                    const float4 w = hi4[q];
+                    float4 l;
+                    l.x = rn_tf32(w.x - __uint_as_float(__float_as_uint(w.x) & 0xFFFFE000u));
+                    l.y = rn_tf32(w.y - __uint_as_float(__float_as_uint(w.y) & 0xFFFFE000u));
+                    l.z = rn_tf32(w.z - __uint_as_float(__float_as_uint(w.z) & 0xFFFFE000u));
+                    l.w = rn_tf32(w.w - __uint_as_float(__float_as_uint(w.w) & 0xFFFFE000u));
+                    lo4[q] = l;
+                }
+                fence_async_smem();                           // generic-proxy stores -> async proxy (tcgen05.mma)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[sb]);
+                if (++sb == SB) { sb = 0; ph ^= 1u; }
+            }
         }
     } else {
         // ------------------------------ converters (4 groups x 4 warps), then epilogue ------------
@@ -1030,11 +1043,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             __syncwarp();                                  // every lane has read its row: the raw tile may be refilled
             issue();
-            if (p.sleep_ns > 0) {
-                while (!mbar_try_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1))) __nanosleep(p.sleep_ns);
-            } else {
-                mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
-            }
+            mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
             if (quad == 0 && lane == 0) TS_DBG(4, i);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + (mt * SLOTS + slot) * 32);
@@ -1045,27 +1054,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[mt * SLOTS + slot]);
             if (quad == 0 && lane == 0) TS_DBG(5, i);
-            if (p.b_raw && mt == 0) {
-                // the weight stage of this k block arrived as raw fp32 (= hi after the tensor core's truncation):
-                // lo = RN_tf32(w - trunc(w)), elementwise over the tile (the chunk layout does not matter)
-                const int sbi = i % SB;
-                mbar_wait(&b_rawfull[sbi], (uint32_t)((i / SB) & 1));
-                float4* hi4 = reinterpret_cast<float4*>(ringB + (size_t)sbi * b_stage);
-                float4* lo4 = reinterpret_cast<float4*>(ringB + (size_t)sbi * b_stage + b_stage / 2);
-                const int n4 = (int)(b_stage / 32);           // float4 per half
-                for (int q = (cw & 3) * 32 + lane; q < n4; q += 128) {
-                    const float4 w = hi4[q];
-                    float4 l;
-                    l.x = rn_tf32(w.x - __uint_as_float(__float_as_uint(w.x) & 0xFFFFE000u));
-                    l.y = rn_tf32(w.y - __uint_as_float(__float_as_uint(w.y) & 0xFFFFE000u));
-                    l.z = rn_tf32(w.z - __uint_as_float(__float_as_uint(w.z) & 0xFFFFE000u));
-                    l.w = rn_tf32(w.w - __uint_as_float(__float_as_uint(w.w) & 0xFFFFE000u));
-                    lo4[q] = l;
-                }
-                fence_async_smem();                           // generic-proxy stores -> async proxy (tcgen05.mma)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b_full[sbi]);
-            }
         }
         cp_async_wait<0>();
         // ------------------------------ epilogue (16 warps) ---------------------------------------
@@ -1078,6 +1066,229 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_ts_kernel(TsParams p) {
     }
     __syncthreads();
     if (p.CL > 1) cluster_sync_all();                 // nobody leaves while a peer may still multicast into / signal this CTA
+    if (wid == 1) {
+        tc_fence_after();
+        tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TSW engine (round 2): the weight-gradient GEMM   dW[n, k] (+)= sum_b dZ[b, n] * X[b, k]
+// (reference: autograd of nn.Linear inside DNN, layers/core.py:120-134) with BOTH operands streamed from
+// the batch-major activations and the contraction over the BATCH:
+//   * "A" = dZ^T goes through tensor memory: a converter thread owns ONE output feature n (= TMEM lane) and reads
+//     its COLUMN of the raw [16 samples x 128 features] tile (conflict-free LDS.32) — the transposition the SS
+//     engine does with 4x4 register shuffles and transposed shared-memory stores is free here; the same thread
+//     also accumulates db[n] = sum_b dZ[b, n] (the bias gradient: no separate column-sum kernel);
+//   * "B" = X^T is converted by two other warp groups into the K-major [hi | lo] tile the MMA reads from shared
+//     memory (4 LDS.32 down a column -> split -> two 128-bit stores, conflict-free);
+//   * K (the batch) is split across CTAs; partial tiles are reduced into dW with 128-bit fp32 reductions.
+// ---------------------------------------------------------------------------------------------
+constexpr int TW_A_PITCH = 132;                  // floats per row of a raw A tile (128 features + 4: conflict-free cp.async stores)
+constexpr uint32_t TW_A_TILE = 16 * TW_A_PITCH * 4;           // 8 448 bytes: 16 samples x 128 features
+
+struct TwParams {
+    GemmArgs g;                      // M = out features, N = in features, K = batch
+    int64_t nkb, kb_per_split;
+    int BN, SLOTS, SBW, RA, RB, tmem_cols, a_col0, has_mask;
+    uint32_t off_braw, off_araw, off_bar, b_raw_bytes, a_raw_bytes;
+    int b_pitch;                     // floats per row of a raw B tile (BN + 4)
+    float* db;                       // bias gradient [M] (NULL: not wanted), accumulated with atomics
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const GemmArgs& g = p.g;
+    const int BN = p.BN, SLOTS = p.SLOTS, SBW = p.SBW;
+    const uint32_t b_stage = (uint32_t)BN * 128u;
+    unsigned char* ringB = smem_raw;                                  // converted B stages
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw + p.off_bar);
+    uint64_t* b_empty = b_full + SBW;
+    uint64_t* a_full = b_empty + SBW;
+    uint64_t* a_empty = a_full + SLOTS;
+    uint64_t* accum_bar = a_empty + SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int64_t mblk = blockIdx.y, nblk = blockIdx.x;
+    const int64_t kb_beg = (int64_t)blockIdx.z * p.kb_per_split;
+    const int64_t kb_end = (kb_beg + p.kb_per_split < p.nkb) ? kb_beg + p.kb_per_split : p.nkb;
+    const int nkb = (int)(kb_end - kb_beg);
+    const int64_t m0 = mblk * PK_AR, n0 = nblk * BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < SBW; ++s) {
+            mbar_init(&b_full[s], 8);                 // the eight B-converter warps
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&a_full[s], 4);
+            mbar_init(&a_empty[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wid == 0) {
+        // idle: both operands are fetched by the converters themselves
+    } else if (wid == 1) {
+        // ------------------------------ MMA issuer ------------------------------------------------
+        const uint32_t idesc = tf32_idesc(BN);
+        const uint32_t b_lbo = (uint32_t)BN * 16u;
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int i = 0; i < nkb; ++i) {
+            const int slot = i % SLOTS;
+            mbar_wait(&b_full[sb], phb);
+            mbar_wait(&a_full[slot], (uint32_t)((i / SLOTS) & 1));
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
+#pragma unroll
+                for (int j = 0; j < PK_KB / 8; ++j) {
+                    const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + slot * 32 + 8 * j), a_lo = a_hi + 16u;
+                    umma_tf32_ts(tmem_base, a_lo, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base, a_hi, dbl, idesc, 1u);
+                    umma_tf32_ts(tmem_base, a_hi, dbh, idesc, 1u);
+                }
+                umma_commit(&b_empty[sb]);
+                umma_commit(&a_empty[slot]);
+                if (i == nkb - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++sb == SBW) { sb = 0; phb ^= 1u; }
+        }
+        if (nkb == 0 && lane == 0) mbar_arrive(accum_bar);
+    } else if (wid < 10) {
+        // ------------------------------ A converters: 2 groups x 4 warps (dZ^T through TMEM) ------
+        const int cw = wid - 2, grp = cw >> 2, quad = wid & 3;
+        const int t128 = (cw & 3) * 32 + lane;                  // thread inside the group (cp.async mapping)
+        const int feat = quad * 32 + lane;                      // the output feature this thread owns = its TMEM lane
+        unsigned char* araw = smem_raw + p.off_araw + (size_t)grp * p.RA * p.a_raw_bytes;
+        const float* Aptr = g.A;
+        const float* Mptr = g.amask;
+        const int64_t sak = g.sak, smk = g.smk;
+        const int mask_act = g.amask_act;
+        float dbacc = 0.f;
+        int issued = 0;
+        auto issue = [&]() {
+            const int i = grp + 2 * issued;
+            if (i < nkb) {
+                unsigned char* buf = araw + (size_t)(issued % p.RA) * p.a_raw_bytes;
+                // 16 rows x 32 pieces of 16 bytes: a warp copies one whole row (512 contiguous bytes)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pc = t128 + 128 * j, r = pc >> 5, c = pc & 31;
+                    const int64_t b = (kb_beg + i) * PK_KB + r;
+                    const int64_t m = m0 + 4 * c;
+                    int bytes = (b < g.K && m < g.M) ? (int)((g.M - m >= 4 ? 4 : g.M - m) * 4) : 0;
+                    float* dst = reinterpret_cast<float*>(buf) + r * TW_A_PITCH + 4 * c;
+                    cp_async16(dst, bytes ? Aptr + b * sak + m : Aptr, bytes);
+                    if (p.has_mask)
+                        cp_async16(reinterpret_cast<float*>(buf + TW_A_TILE) + r * TW_A_PITCH + 4 * c,
+                                   bytes ? Mptr + b * smk + m : Mptr, bytes);
+                }
+            }
+            cp_async_commit();
+            ++issued;
+        };
+        for (int d = 0; d < p.RA; ++d) issue();
+        int done = 0;
+        for (int i = grp; i < nkb; i += 2, ++done) {
+            const int slot = i % SLOTS;
+            if (p.RA == 3) cp_async_wait<2>();
+            else if (p.RA == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // the group's four warps copied each other's rows
+            const float* col = reinterpret_cast<const float*>(araw + (size_t)(done % p.RA) * p.a_raw_bytes) + feat;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                float v = col[r * TW_A_PITCH];
+                if (p.has_mask) v *= act_grad_from_y(mask_act, col[TW_A_TILE / 4 + r * TW_A_PITCH]);
+                dbacc += v;
+                split_tf32(v, hi[r], lo[r]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // every thread has read: the raw tile may be refilled
+            issue();
+            mbar_wait(&a_empty[slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + slot * 32);
+            tmem_st16(taddr, hi);
+            tmem_st16(taddr + 16u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[slot]);
+        }
+        cp_async_wait<0>();
+        if (p.db && nblk == 0 && m0 + feat < g.M) atomicAdd(p.db + m0 + feat, dbacc);
+    } else {
+        // ------------------------------ B converters: 8 warps (X^T into the K-major [hi | lo] tile) -
+        const int t256 = (wid - 10) * 32 + lane;
+        unsigned char* braw = smem_raw + p.off_braw;
+        const float* Bptr = g.B;
+        const int64_t sbk = g.sbk;
+        const int pitch = p.b_pitch;
+        const int pieces_per_row = BN / 4, n_pieces = 16 * pieces_per_row;
+        int issued = 0;
+        auto issue = [&]() {
+            const int i = issued;
+            if (i < nkb) {
+                unsigned char* buf = braw + (size_t)(issued % p.RB) * p.b_raw_bytes;
+                for (int pc = t256; pc < n_pieces; pc += 256) {
+                    const int r = pc / pieces_per_row, c = pc - r * pieces_per_row;
+                    const int64_t b = (kb_beg + i) * PK_KB + r;
+                    const int64_t n = n0 + 4 * c;
+                    int bytes = (b < g.K && n < g.N) ? (int)((g.N - n >= 4 ? 4 : g.N - n) * 4) : 0;
+                    cp_async16(reinterpret_cast<float*>(buf) + r * pitch + 4 * c, bytes ? Bptr + b * sbk + n : Bptr, bytes);
+                }
+            }
+            cp_async_commit();
+            ++issued;
+        };
+        for (int d = 0; d < p.RB; ++d) issue();
+        int sb = 0;
+        uint32_t phb = 1;
+        for (int i = 0; i < nkb; ++i) {
+            if (p.RB == 3) cp_async_wait<2>();
+            else if (p.RB == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            const float* raw = reinterpret_cast<const float*>(braw + (size_t)(i % p.RB) * p.b_raw_bytes);
+            mbar_wait(&b_empty[sb], phb);
+            float* tile = reinterpret_cast<float*>(ringB + (size_t)sb * b_stage);
+            // (n, chunk c): 4 samples of column n -> one 16-byte chunk of row n; lanes = consecutive n
+            for (int q = t256; q < 4 * BN; q += 256) {
+                const int c = q / BN, n = q - c * BN;
+                const float4 v = make_float4(raw[(4 * c + 0) * pitch + n], raw[(4 * c + 1) * pitch + n],
+                                             raw[(4 * c + 2) * pitch + n], raw[(4 * c + 3) * pitch + n]);
+                split_store(tile, (c * BN + n) * 4, BN * 16, v);
+            }
+            fence_async_smem();
+            asm volatile("bar.sync 3, 256;" ::: "memory");           // every thread has read the raw tile and written its chunks
+            if (lane == 0) mbar_arrive(&b_full[sb]);
+            issue();
+            if (++sb == SBW) { sb = 0; phb ^= 1u; }
+        }
+        cp_async_wait<0>();
+    }
+    if (wid >= 2) {
+        // ------------------------------ epilogue (16 warps): reduce the partial tile into dW ------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        if (nkb > 0) tile_epilogue<EPI_STORE>(g, tmem_base, smem_raw, wid, lane, m0, 1, BN, n0, true);
+        tc_fence_before();
+    }
+    __syncthreads();
     if (wid == 1) {
         tc_fence_after();
         tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
@@ -1264,8 +1475,10 @@ int gemm_pack_operand(const float* P, int64_t s_row, int64_t s_k, int64_t n_rows
 // TS engine: eligible when A is a big K-contiguous fp32 matrix (activations) and B is small enough to be packed
 // (weights), no split-K.  Returns -3 when the shape does not qualify (the caller continues with the SS engine).
 static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
+    // opt-in (CTR_GEMM_TS=1): measured within 10 % of the SS engine on the tower shapes (profiles/r02_gemm_engines.md:
+    // both are paced by the weight-stage ring, not by shared memory or the MMA rate), so the proven engine stays default
     const char* e = getenv("CTR_GEMM_TS");
-    if (e && e[0] == '0') return -3;
+    if (!(e && e[0] == '1')) return -3;
     if (g.M < 4 * PK_AR || g.K < 16 || g.N < 16 || g.accumulate) return -3;
     if (stream_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk) != OP_KVEC) return -3;
     if (g.bmask) return -3;
@@ -1317,35 +1530,16 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     }
     // the weight ring wants depth (the copies' latency is ~4 stages of MMA time), the raw tiles need little: the
     // converters run far ahead of the MMAs anyway
-    static int sb_env = -1, rawd_env = -1, split_env = 1, sleep_env = 0;
+    static int sb_env = -1, rawd_env = -1, raw_env = -1;
     if (sb_env < 0) {
         const char* e1 = getenv("CTR_TS_SB");
         const char* e2 = getenv("CTR_TS_RAWD");
-        const char* e3 = getenv("CTR_TS_TMA_SPLIT");
-        const char* e4 = getenv("CTR_TS_SLEEP");
+        const char* e6 = getenv("CTR_TS_BRAW");
         sb_env = e1 ? atoi(e1) : 0;
         rawd_env = e2 ? atoi(e2) : 0;
-        split_env = e3 ? atoi(e3) : 1;
-        sleep_env = e4 ? atoi(e4) : 0;
-        if (split_env != 1 && split_env != 2 && split_env != 4 && split_env != 8) split_env = 1;
+        raw_env = (e6 && e6[0] == '1') ? 1 : 0;
     }
-    p.tma_split = split_env;
-    p.sleep_ns = sleep_env;
-    {
-        static int lsu_env = -1;
-        if (lsu_env < 0) {
-            const char* e5 = getenv("CTR_TS_BLSU");
-            lsu_env = (e5 && e5[0] == '1') ? 1 : 0;
-        }
-        p.b_lsu = (lsu_env && p.CL == 1) ? 1 : 0;
-        static int raw_env = -1;
-        if (raw_env < 0) {
-            const char* e6 = getenv("CTR_TS_BRAW");
-            raw_env = (e6 && e6[0] == '0') ? 0 : 1;
-        }
-        p.b_raw = raw_env;
-        if (p.b_raw) p.b_lsu = 0;
-    }
+    p.b_raw = raw_env;       // weight stages as raw fp32 (half the L2 -> SM bytes), lo derived by four extra warps
     p.SB = 0;
     for (int rawd = (rawd_env ? rawd_env : 2); rawd >= 1 && !p.SB; --rawd)
         for (int sbn = (sb_env ? sb_env : 6); sbn >= 3 && !p.SB; --sbn) {
@@ -1376,21 +1570,6 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     } else if ((rc = launch_pack(pb, st)) != 0) {
         return rc;
     }
-    {
-        static int rep_env = -1;
-        if (rep_env < 0) {
-            const char* e7 = getenv("CTR_TS_BREP");
-            rep_env = e7 ? atoi(e7) : 1;
-            if (rep_env < 1) rep_env = 1;
-        }
-        const int64_t one = (p.b_raw ? b_bytes / 2 : b_bytes);
-        p.b_rep_bytes = (one + 255) / 256 * 256;
-        p.b_rep = rep_env;
-        while (p.b_rep > 1 && p.b_rep * p.b_rep_bytes > g_scratch_bytes[dev]) p.b_rep >>= 1;
-        for (int r = 1; r < p.b_rep; ++r)
-            CTR_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(scratch) + r * p.b_rep_bytes, scratch, (size_t)one,
-                                     cudaMemcpyDeviceToDevice, st));
-    }
     static bool configured = false;
     if (!configured) {
         const int max_smem = 232448;
@@ -1403,7 +1582,7 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)gn, (unsigned)gm, 1);
-    cfg.blockDim = dim3(PK_THREADS, 1, 1);
+    cfg.blockDim = dim3(TS_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1424,10 +1603,84 @@ static int launch_gemm_ts(const GemmArgs& g, cudaStream_t st) {
     return 0;
 }
 
+static bool row_vec_ok_host(const float* base, int64_t ld) { return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (ld % 4 == 0); }
+
+// TSW: weight-gradient form  C[M,N] = A^T B  with A(m,k) = A[k*sak + m] (sam == 1), B(n,k) = B[k*sbk + n] (sbn == 1),
+// K = batch large, C row-major.  db (may be NULL): column sums of the (masked) A operand, i.e. the bias gradient.
+// Returns -3 when the shape does not qualify.
+int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
+    const char* e = getenv("CTR_GEMM_TSW");
+    if (!e || e[0] != '1') return -3;              // opt-in until validated on hardware
+    if (g.sam != 1 || g.sbn != 1 || g.K < 4096 || g.M < 16 || g.N < 16 || g.epilogue != EPI_STORE || g.bmask) return -3;
+    if (g.sak % 4 != 0 || g.sbk % 4 != 0 || !pk_al16(g.A) || !pk_al16(g.B)) return -3;
+    if (g.amask && (g.smm != 1 || g.smk % 4 != 0 || !pk_al16(g.amask))) return -3;
+    if (!row_vec_ok_host(g.C, g.ldc)) return -3;
+    TwParams p{};
+    p.g = g;
+    p.db = db;
+    const int64_t gn = ceil_div64(g.N, 256);
+    p.BN = (int)(ceil_div64(ceil_div64(g.N, gn), 16) * 16);
+    const int64_t gm = ceil_div64(g.M, PK_AR);
+    p.nkb = ceil_div64(g.K, PK_KB);
+    const int64_t tiles = gm * gn, sms = ctr_sm_count();
+    int64_t splits = tiles >= sms ? 1 : sms / tiles;
+    if (splits > p.nkb / 8) splits = p.nkb / 8;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = ceil_div64(p.nkb, splits);
+    splits = ceil_div64(p.nkb, p.kb_per_split);
+    if (splits > 65535 || gm > 65535) return -3;
+    p.has_mask = g.amask ? 1 : 0;
+    p.a_col0 = p.BN;
+    p.SLOTS = (512 - p.a_col0) / 32;
+    if (p.SLOTS > 8) p.SLOTS = 8;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.a_col0 + p.SLOTS * 32) p.tmem_cols <<= 1;
+    p.b_pitch = p.BN + 4;
+    p.b_raw_bytes = (uint32_t)(16 * p.b_pitch * 4);
+    p.a_raw_bytes = TW_A_TILE * (p.has_mask ? 2u : 1u);
+    const int64_t budget = 232448 - 1024, b_stage = (int64_t)p.BN * 128;
+    const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;
+    p.SBW = 0;
+    for (int ra = 3; ra >= 2 && !p.SBW; --ra)
+        for (int sbw = 3; sbw >= 2 && !p.SBW; --sbw) {
+            const int64_t need = sbw * b_stage + 3 * (int64_t)p.b_raw_bytes + 2 * ra * (int64_t)p.a_raw_bytes;
+            if (need <= budget) {
+                p.SBW = sbw;
+                p.RA = ra;
+                p.RB = 3;
+            }
+        }
+    if (!p.SBW) return -3;
+    int64_t off = p.SBW * b_stage;
+    p.off_braw = (uint32_t)off;
+    off += (int64_t)p.RB * p.b_raw_bytes;
+    p.off_araw = (uint32_t)((off + 15) / 16 * 16);
+    off = p.off_araw + 2 * (int64_t)p.RA * p.a_raw_bytes;
+    if (off < stg) off = stg;
+    p.off_bar = (uint32_t)((off + 15) / 16 * 16);
+    const size_t smem = p.off_bar + (size_t)(2 * p.SBW + 2 * p.SLOTS + 1) * sizeof(uint64_t) + 16;
+    if (smem > 232448) return -3;
+    if (!g.accumulate) CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
+    if (db) CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * g.M, st));
+    static bool configured = false;
+    if (!configured) {
+        CTR_CUDA(cudaFuncSetAttribute(gemm_tsw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)splits);
+    gemm_tsw_kernel<0><<<grid, PK_THREADS, smem, st>>>(p);
+    CTR_LAUNCH_OK("gemm_tsw_kernel");
+    return 0;
+}
+
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     {
         const int rc_ts = launch_gemm_ts(g, st);
         if (rc_ts != -3) return rc_ts;
+    }
+    if (g.allow_split_k) {
+        const int rc_tw = launch_gemm_tsw(g, nullptr, st);
+        if (rc_tw != -3) return rc_tw;
     }
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);

@@ -1,6 +1,7 @@
 mkdir -p gpurun_out; rm -rf gpurun_out/*
-for cfg in "1 0" "16 0" "64 0" "16 1"; do
-  set -- $cfg
-  echo "== ts bench BREP=$1 BRAW=$2"
-  CTR_TS_BREP=$1 CTR_TS_BRAW=$2 timeout -s KILL 120 python scripts/ts_probe.py bench 2>&1 | grep -E "fwd|dgrad" | sed 's/(.*ceiling)  TS=0.*//' | cut -c1-110
+echo "== check BRAW(dedicated warps)"; timeout -s KILL 240 python scripts/ts_probe.py check 2>&1 | grep -E "TS=1 rel|y rel" | cut -c1-100
+for cfg in "1" "0"; do
+  echo "== ts bench BRAW=$cfg"
+  CTR_TS_BRAW=$cfg timeout -s KILL 120 python scripts/ts_probe.py bench 2>&1 | grep -E "fwd|dgrad" | cut -c1-200
 done
+timeout -s KILL 120 python scripts/ts_timeline.py fwd1 2>&1 | sed -n 1,3p\;12,20p | cut -c1-120

@@ -137,3 +137,34 @@ def test_dnn_tower_large_batch_streaming(hidden):
         assert rel_err(W.grad.cpu(), Wr.grad.cpu()) <= 5e-5      # K = 40 000 truncating accumulations
     for b, br in zip(bs, bd):
         assert rel_err(b.grad.cpu(), br.grad.cpu()) <= 5e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 256, 432), (65536, 128, 256), (5000, 432, 256), (66000, 256, 128)])
+@pytest.mark.parametrize("variant", ["", "raw", "cluster2"])
+def test_ts_engine_matches_fp64(M, N, K, variant, monkeypatch):
+    """The opt-in TS engine (A operand through tensor memory, csrc/gemm_pk.cu): plain, with raw fp32 weight stages
+    (lo derived in the CTA) and with the weight stages multicast across a 2-CTA cluster.  Run in a subprocess: the
+    engine reads its switches once per process."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+from deepctr_torch_b200 import _lib, ops
+M, N, K = %d, %d, %d
+g = torch.Generator(device="cuda").manual_seed(1)
+A = torch.randn(M, K, device="cuda", generator=g); Bm = torch.randn(N, K, device="cuda", generator=g)
+C = torch.full((M, N), float("nan"), device="cuda")
+ops.ensure_gemm_scratch(torch.device("cuda:0"), M, K, N)
+n0 = _lib.launch_count()
+_lib.call("ctr_sgemm", M, N, K, ops._ptr(A), K, 1, ops._ptr(Bm), K, 1, ops._ptr(C), N, 0, ops._stream())
+torch.cuda.synchronize()
+ref = A.double() @ Bm.double().t()
+print("ERR", float((C.double() - ref).abs().max() / ref.abs().max()))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), M, N, K)
+    env = dict(os.environ, CTR_GEMM_TS="1", CTR_TS_BRAW="1" if variant == "raw" else "0",
+               CTR_TS_CLUSTER="2" if variant == "cluster2" else "1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    err = float([l for l in r.stdout.splitlines() if l.startswith("ERR")][-1].split()[1])
+    assert err <= 5e-6, (variant, err)
