@@ -590,8 +590,11 @@ def rooflines(workload, m, steps):
     ld = (blk_w + 3) // 4 * 4
     gather_bytes = 4 * (39 + 26 * D + 26 + blk_w + 2)                 # X row + rows + linear w + blk + lin/fm
     scatter_bytes = 4 * (2 * ld + 26 * 2 + 26 * D + 26 + 2)             # d_blk + blk + inv/cnt + row grads out
+    # duplicate-free plan: id read + hash slot (key CAS + value) + inv written twice + cnt/uniq, per id column —
+    # a chain of dependent L2 atomics, reported against HBM bandwidth for lack of a better ceiling
+    plan_bytes = 26 * (4 + 8 + 8 + 8)
     hbm_entries = {"ctr_gather_fwd": gather_bytes, "ctr_gather_fwd_exchanged": gather_bytes,
-                   "ctr_scatter_bwd_rowwise": scatter_bytes,
+                   "ctr_scatter_bwd_rowwise": scatter_bytes, "ctr_unique_plan": plan_bytes,
                    "ctr_cross_vector_fwd": 4 * (2 * ld + 2), "ctr_cross_vector_bwd": 4 * (4 * ld)}
     roofs = {}
     for name, bps in hbm_entries.items():

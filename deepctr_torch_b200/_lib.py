@@ -39,7 +39,7 @@ SIGNATURES = {
     "ctr_shard_serve": [c_int, c_int, c_int, _P, _P, c_i64, _P, _P, _P, _P, _P],
     "ctr_gather_fwd_exchanged": [_P, c_i64, c_i64, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P,
                                  c_int, _P, _P, _P, c_i64, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P],
-    "ctr_rowgrad_push": [c_i64, c_int, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
+    "ctr_rowgrad_push": [c_i64, c_int, c_int, _P, _P, c_int, c_int, _P, c_i64, _P, c_int, _P, c_i64, _P,
                          _P, _P, _P, _P, c_i64, _P, _P],
     "ctr_lin_dense_wgrad": [_P, c_i64, c_i64, c_int, _P, _P, _P, _P],
     "ctr_dnn_layer_fwd": [_P, c_i64, _P, c_i64, c_i64, _P, _P, c_i64, c_i64, c_int, c_int, c_int, _P],
@@ -100,6 +100,7 @@ SPECIAL = {
     "ctr_unique_plan_hash_slots": ([c_i64], c_i64),
     "ctr_launch_count": ([], c_i64),
     "ctr_gemm_scratch_bytes": ([c_i64, c_i64, c_i64], c_i64),
+    "ctr_dnn_wgrad_is_scratch_free": ([_P, c_i64, _P, c_i64, _P, c_i64, _P, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int], c_int),
 }
 
 

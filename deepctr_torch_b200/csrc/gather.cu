@@ -542,6 +542,32 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 // (id -> CAS -> next probe ...), so each thread keeps PLAN_ILP independent keys in flight and the
 // first probe is the CAS itself (no read-before-CAS): measured 140 us -> see profiles/.
 constexpr int PLAN_ILP = 4;
+
+// Ragged plans (receive lists of the sharded backward) size each column's hash table from the number of entries the
+// column really holds: the storage stride stays H, but only the first plan_hash_slots(count) slots are cleared and
+// probed — the clears no longer scale with the worst-case list capacity (world x batch).
+__device__ __forceinline__ uint32_t plan_hash_slots(int64_t count, int64_t H) {
+    uint32_t h = 64;
+    while ((int64_t)h < 2 * count && (int64_t)h < H) h <<= 1;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) plan_clear_kernel(int64_t B, int64_t H, const int32_t* __restrict__ col_count,
+                                                         int32_t* keys, int32_t* n_uniq, int32_t* uniq, int32_t* cnt) {
+    const int c = blockIdx.y;
+    int64_t n = __ldg(col_count + c);
+    if (n > B) n = B;
+    if (n < 0) n = 0;
+    const int64_t hs = plan_hash_slots(n, H);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    if (t == 0) n_uniq[c] = 0;
+    int4* k4 = reinterpret_cast<int4*>(keys + (int64_t)c * H);          // H is a power of two >= 64
+    for (int64_t i = t; i < hs / 4; i += nt) k4[i] = make_int4(-1, -1, -1, -1);
+    for (int64_t i = t; i < n; i += nt) {
+        uniq[(int64_t)c * B + i] = 0;
+        cnt[(int64_t)c * B + i] = 0;
+    }
+}
 __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restrict__ X, int64_t ldx,
                                                           int64_t B, int n_cols,
                                                           const int32_t* __restrict__ cols,
@@ -550,8 +576,15 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
                                                           int32_t* n_uniq, int32_t* uniq,
                                                           int32_t* inv, int32_t* err_flag, int id_mode,
                                                           const int32_t* __restrict__ col_count) {
-    const int64_t total = B * n_cols;
-    const uint32_t mask = (uint32_t)(H - 1);
+    // ragged plan: blockIdx.y is the column and only its col_count[c] entries are visited
+    const int col_fixed = col_count ? (int)blockIdx.y : -1;
+    int64_t total = B * n_cols;
+    uint32_t col_mask = (uint32_t)(H - 1);
+    if (col_count) {
+        total = __ldg(col_count + col_fixed);
+        if (total > B) total = B;
+        col_mask = plan_hash_slots(total, H) - 1u;
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -559,7 +592,7 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
         int c[PLAN_ILP];
         int64_t b[PLAN_ILP];
         bool valid[PLAN_ILP], won[PLAN_ILP];
-        uint32_t slot[PLAN_ILP];
+        uint32_t slot[PLAN_ILP], mask[PLAN_ILP];
         int32_t key[PLAN_ILP], old[PLAN_ILP];
         float xv[PLAN_ILP];
 #pragma unroll
@@ -567,16 +600,15 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
             const int64_t i = base + t * 32 + lane;
             valid[t] = i < total;
             const int64_t ic = valid[t] ? i : 0;
-            c[t] = (int)(ic / B);
-            b[t] = ic - (int64_t)c[t] * B;
-            // ragged columns (receive lists of the sharded backward): only the first col_count[c] entries exist
-            if (col_count && b[t] >= __ldg(col_count + c[t])) valid[t] = false;
+            c[t] = col_fixed >= 0 ? col_fixed : (int)(ic / B);
+            b[t] = col_fixed >= 0 ? ic : ic - (int64_t)c[t] * B;
+            mask[t] = col_mask;
             xv[t] = __ldg(X + (valid[t] ? b[t] : 0) * ldx + cols[c[t]]);
         }
 #pragma unroll
         for (int t = 0; t < PLAN_ILP; ++t) {                 // all first probes (CAS) in flight
             key[t] = (int32_t)decode_id(xv[t], vocab[c[t]], valid[t] ? err_flag : nullptr, id_mode);
-            slot[t] = mix32((uint32_t)key[t]) & mask;
+            slot[t] = mix32((uint32_t)key[t]) & mask[t];
             old[t] = valid[t] ? atomicCAS(keys + (int64_t)c[t] * H + slot[t], -1, key[t]) : key[t];
         }
 #pragma unroll
@@ -591,7 +623,7 @@ __global__ void __launch_bounds__(256) plan_insert_kernel(const float* __restric
                         break;
                     }
                     if (o == key[t]) break;
-                    slot[t] = (slot[t] + 1) & mask;            // linear probing (rare at load factor <= 0.5)
+                    slot[t] = (slot[t] + 1) & mask[t];         // linear probing (rare at load factor <= 0.5)
                     o = atomicCAS(kc + slot[t], -1, key[t]);
                 }
                 inv[b[t] * n_cols + c[t]] = (int32_t)slot[t];  // replaced by the unique index in plan_finalize_kernel
@@ -620,11 +652,22 @@ __global__ void __launch_bounds__(256) plan_finalize_kernel(int64_t B, int n_col
                                                             const int32_t* __restrict__ vals,
                                                             int64_t H, int32_t* inv, int32_t* cnt,
                                                             const int32_t* __restrict__ col_count) {
+    if (col_count) {                                   // ragged plan: blockIdx.y is the column
+        const int c = blockIdx.y;
+        int64_t n = __ldg(col_count + c);
+        if (n > B) n = B;
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i = b * n_cols + c;
+            const int32_t u = __ldcg(vals + (int64_t)c * H + inv[i]);
+            inv[i] = u;
+            atomicAdd(cnt + (int64_t)c * B + u, 1);
+        }
+        return;
+    }
     const int64_t total = B * n_cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % n_cols);
-        if (col_count && i / n_cols >= __ldg(col_count + c)) continue;
         const int32_t u = __ldcg(vals + (int64_t)c * H + inv[i]);
         inv[i] = u;
         atomicAdd(cnt + (int64_t)c * B + u, 1);
@@ -905,18 +948,32 @@ extern "C" int ctr_unique_plan(const float* X, int64_t ldx, int64_t B, int n_col
     CTR_ARG(H >= 2 * B && (H & (H - 1)) == 0, "ctr_unique_plan: H must be a power of two >= 2B");
     if (B == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    CTR_CUDA(cudaMemsetAsync(hash_keys, 0xFF, sizeof(int32_t) * H * n_cols, st));
-    CTR_CUDA(cudaMemsetAsync(n_uniq, 0, sizeof(int32_t) * n_cols, st));
-    CTR_CUDA(cudaMemsetAsync(uniq, 0, sizeof(int32_t) * B * n_cols, st));
-    CTR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * B * n_cols, st));
     int64_t blocks = ceil_div64(B * n_cols, 256);
     const int64_t cap = (int64_t)ctr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    plan_insert_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, B, n_cols, cols, vocab, hash_keys,
-                                                         hash_vals, H, n_uniq, uniq, inv, err_flag, id_mode,
-                                                         col_count);
+    if (col_count) {
+        int64_t bx = ceil_div64(blocks, n_cols);
+        if (bx < 1) bx = 1;
+        plan_clear_kernel<<<dim3((unsigned)bx, (unsigned)n_cols), 256, 0, st>>>(B, H, col_count, hash_keys, n_uniq, uniq, cnt);
+        CTR_LAUNCH_OK("plan_clear_kernel");
+    } else {
+        CTR_CUDA(cudaMemsetAsync(hash_keys, 0xFF, sizeof(int32_t) * H * n_cols, st));
+        CTR_CUDA(cudaMemsetAsync(n_uniq, 0, sizeof(int32_t) * n_cols, st));
+        CTR_CUDA(cudaMemsetAsync(uniq, 0, sizeof(int32_t) * B * n_cols, st));
+        CTR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * B * n_cols, st));
+    }
+    dim3 grid((unsigned)blocks, 1);
+    if (col_count) {
+        // expected list length is about B / n_shards: a few blocks per column keep every SM busy without
+        // launching the worst-case grid
+        int64_t bx = ceil_div64(cap, n_cols);
+        if (bx < 1) bx = 1;
+        grid = dim3((unsigned)bx, (unsigned)n_cols);
+    }
+    plan_insert_kernel<<<grid, 256, 0, st>>>(X, ldx, B, n_cols, cols, vocab, hash_keys, hash_vals, H, n_uniq, uniq, inv,
+                                            err_flag, id_mode, col_count);
     CTR_LAUNCH_OK("plan_insert_kernel");
-    plan_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, n_cols, hash_vals, H, inv, cnt, col_count);
+    plan_finalize_kernel<<<grid, 256, 0, st>>>(B, n_cols, hash_vals, H, inv, cnt, col_count);
     CTR_LAUNCH_OK("plan_finalize_kernel");
     return 0;
 }

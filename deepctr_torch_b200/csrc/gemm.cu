@@ -456,6 +456,20 @@ extern "C" int ctr_dnn_layer_fwd(const float* X, int64_t ldx, const float* W, in
     return launch_sgemm(g, as_stream(stream));
 }
 
+// dW[n, k] = sum_b dZ[b, n] X[b, k], dW row-major [N, K] (nn.Linear layout)
+static GemmArgs wgrad_args(const float* X, int64_t ldx, const float* mask, int64_t ldy, const float* dY, int64_t lddy,
+                           float* dW, int64_t sdwn, int64_t B, int K, int N, int act) {
+    GemmArgs g = gemm_args_default();
+    g.K = B;
+    g.allow_split_k = 1;
+    g.M = N; g.N = K;
+    g.A = dY; g.sam = 1; g.sak = lddy;
+    g.amask = mask; g.smm = 1; g.smk = ldy; g.amask_act = act;
+    g.B = X; g.sbn = 1; g.sbk = ldx;
+    g.C = dW; g.ldc = sdwn;
+    return g;
+}
+
 static int dnn_layer_bwd_impl(const float* X, int64_t ldx, const float* W, int64_t swn, int64_t swk,
                               const float* Y, int64_t ldy, const float* dY, int64_t lddy, float* dX,
                               int64_t lddx, int accumulate_dx, float* dW, int64_t sdwn, int64_t sdwk,
@@ -483,11 +497,11 @@ static int dnn_layer_bwd_impl(const float* X, int64_t ldx, const float* W, int64
         g.K = B;
         g.allow_split_k = 1;
         if (sdwk == 1) {  // rows = n, cols = k
-            g.M = N; g.N = K;
-            g.A = dY; g.sam = 1; g.sak = lddy;
-            g.amask = mask; g.smm = 1; g.smk = ldy; g.amask_act = act;
-            g.B = X; g.sbn = 1; g.sbk = ldx;
-            g.C = dW; g.ldc = sdwn;
+            g = wgrad_args(X, ldx, mask, ldy, dY, lddy, dW, sdwn, B, K, N, act);
+            // TSW engine: dZ^T through tensor memory, bias gradient fused (no colsum launch)
+            rc = launch_gemm_tsw(g, db, st);
+            if (rc == 0) return 0;
+            if (rc != -3) return rc;
         } else {          // transposed storage: rows = k, cols = n
             g.M = K; g.N = N;
             g.A = X; g.sam = 1; g.sak = ldx;
@@ -514,6 +528,14 @@ extern "C" int ctr_dnn_layer_bwd(const float* X, int64_t ldx, const float* W, in
     CTR_ARG(!dW || sdwn == 1 || sdwk == 1, "ctr_dnn_layer_bwd: dW must be contiguous along n or k");
     return dnn_layer_bwd_impl(X, ldx, W, swn, swk, Y, ldy, dY, lddy, dX, lddx, accumulate_dx, dW, sdwn, sdwk, db, B,
                               K, N, act, 0, CTR_ACT_LINEAR, as_stream(stream));
+}
+
+extern "C" int ctr_dnn_wgrad_is_scratch_free(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* dY,
+                                             int64_t lddy, const float* dW, int64_t sdwn, int64_t sdwk, int64_t B, int K,
+                                             int N, int act, int dy_is_dz) {
+    if (!X || !dY || !dW || sdwk != 1 || B <= 0 || K <= 0 || N <= 0) return 0;
+    const float* mask = (act == CTR_ACT_LINEAR || dy_is_dz) ? nullptr : Y;
+    return gemm_tsw_eligible(wgrad_args(X, ldx, mask, ldy, dY, lddy, const_cast<float*>(dW), sdwn, B, K, N, act)) ? 1 : 0;
 }
 
 extern "C" int ctr_dnn_layer_bwd_chain(const float* X, int64_t ldx, const float* W, int64_t swn,

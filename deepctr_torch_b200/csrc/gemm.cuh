@@ -44,6 +44,10 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 unsigned long long* ctr_debug_buffer();          // buffer registered with ctr_debug_set_buffer (or NULL)
 // packed-operand engine (gemm_pk.cu): needs the scratch registered with ctr_set_scratch
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st);
+// weight-gradient engine (gemm_pk.cu): C[M,N] = A^T B over a long K (the batch); db (may be NULL) = column sums of the
+// masked A operand.  Returns -3 when the shape does not qualify (caller falls back to launch_sgemm + launch_colsum).
+int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st);
+bool gemm_tsw_eligible(const GemmArgs& g);
 int64_t gemm_pk_scratch_bytes(int64_t M, int64_t N, int64_t K);
 bool gemm_pk_has_scratch(int64_t M, int64_t N, int64_t K);
 void* gemm_scratch_ptr(int64_t need_bytes);      // registered scratch if it holds need_bytes, else NULL

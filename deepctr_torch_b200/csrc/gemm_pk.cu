@@ -921,9 +921,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
         const uint32_t b_lbo = (uint32_t)BN * 16u;
         int sb = 0;
         uint32_t phb = 0;
+        int slot = 0;                                      // i % SLOTS and (i / SLOTS) & 1 kept as counters: a runtime
+        uint32_t pa = 0;                                   // integer division costs this single thread ~200 cycles per stage
         for (int i = 0; i < nkb; ++i) {
-            const int slot = i % SLOTS;
-            const uint32_t pa = (uint32_t)((i / SLOTS) & 1);
             mbar_wait(&b_full[sb], phb);
             if (lane == 0) TS_DBG(0, i);
             for (int mt = 0; mt < MT; ++mt) mbar_wait(&a_full[mt * SLOTS + slot], pa);
@@ -953,6 +953,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; phb ^= 1u; }
+            if (++slot == SLOTS) { slot = 0; pa ^= 1u; }
         }
     } else if (wid >= 2 + PK_CONV_WARPS) {
         // ------------------------------ weight-lo warps (b_raw) -----------------------------------
@@ -995,12 +996,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
         const int mask_act = g.amask_act;
         // cp.async mapping: instruction j moves rows 8j + lane/4 of the warp's 32, chunk lane%4 (64 contiguous bytes per row)
         const int cp_row = lane >> 2, cp_chunk = lane & 3;
-        int issued = 0;                                    // items of this group issued so far
+        int issued = 0, raw_issue = 0;                     // items of this group issued so far / their raw buffer
         auto issue = [&]() {
             const int it = grp + issued * TS_NG;
             if (it < n_items) {
-                const int i = it / MT, mt = it - i * MT;
-                unsigned char* buf = raw_grp + (size_t)(issued % p.RAWD) * p.raw_item_bytes;
+                const int i = MT == 2 ? it >> 1 : it, mt = MT == 2 ? it & 1 : 0;        // MT is 1 or 2
+                unsigned char* buf = raw_grp + (size_t)raw_issue * p.raw_item_bytes;
                 const int64_t k0 = (int64_t)i * PK_KB + cp_chunk * 4;
                 int kbytes = (int)(g.K - k0) * 4;
                 kbytes = kbytes > 16 ? 16 : (kbytes < 0 ? 0 : kbytes);
@@ -1018,18 +1019,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             cp_async_commit();
             ++issued;
+            if (++raw_issue == p.RAWD) raw_issue = 0;
         };
         for (int d = 0; d < p.RAWD; ++d) issue();
-        int done = 0;
-        for (int it = grp; it < n_items; it += TS_NG, ++done) {
-            const int i = it / MT, mt = it - i * MT;
-            const int slot = i % SLOTS;
+        // stage i = it / MT advances by TS_NG / MT per item: slot = i % SLOTS and the slot's use parity are counters
+        const int i_step = MT == 2 ? TS_NG / 2 : TS_NG;
+        int raw_conv = 0, slot = (MT == 2 ? grp >> 1 : grp);
+        uint32_t slot_par = 0;
+        while (slot >= SLOTS) { slot -= SLOTS; slot_par ^= 1u; }
+        for (int it = grp; it < n_items; it += TS_NG) {
+            const int i = MT == 2 ? it >> 1 : it, mt = MT == 2 ? it & 1 : 0;
             if (p.RAWD == 3) cp_async_wait<2>();
             else if (p.RAWD == 2) cp_async_wait<1>();
             else cp_async_wait<0>();
             __syncwarp();                                  // the warp's lanes copied each other's rows
             if (quad == 0 && lane == 0) TS_DBG(3, i);
-            const unsigned char* buf = raw_grp + (size_t)(done % p.RAWD) * p.raw_item_bytes;
+            const unsigned char* buf = raw_grp + (size_t)raw_conv * p.raw_item_bytes;
             const float* myrow = reinterpret_cast<const float*>(buf) + (quad * 32 + lane) * TS_RAW_PITCH;
             float hi[16], lo[16];
 #pragma unroll
@@ -1043,7 +1048,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
             }
             __syncwarp();                                  // every lane has read its row: the raw tile may be refilled
             issue();
-            mbar_wait(&a_empty[mt * SLOTS + slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            mbar_wait(&a_empty[mt * SLOTS + slot], slot_par ^ 1u);
             if (quad == 0 && lane == 0) TS_DBG(4, i);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + (mt * SLOTS + slot) * 32);
@@ -1054,6 +1059,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[mt * SLOTS + slot]);
             if (quad == 0 && lane == 0) TS_DBG(5, i);
+            if (++raw_conv == p.RAWD) raw_conv = 0;
+            slot += i_step;
+            while (slot >= SLOTS) { slot -= SLOTS; slot_par ^= 1u; }
         }
         cp_async_wait<0>();
         // ------------------------------ epilogue (16 warps) ---------------------------------------
@@ -1094,7 +1102,12 @@ struct TwParams {
     uint32_t off_braw, off_araw, off_bar, b_raw_bytes, a_raw_bytes;
     int b_pitch;                     // floats per row of a raw B tile (BN + 4)
     float* db;                       // bias gradient [M] (NULL: not wanted), accumulated with atomics
+    unsigned long long* dbg;         // optional clock64 timeline of CTA (0,0,0) (ctr_debug_set_buffer): [10 events][64 stages]
 };
+#define TW_DBG(ev, idx)                                                                                   \
+    do {                                                                                                  \
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64) p.dbg[(ev) * 64 + (idx)] = clock64(); \
+    } while (0)
 
 template <int DUMMY>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
@@ -1134,6 +1147,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) TW_DBG(7, 2);
 
     if (wid == 0) {
         // idle: both operands are fetched by the converters themselves
@@ -1143,10 +1157,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
         const uint32_t b_lbo = (uint32_t)BN * 16u;
         int sb = 0;
         uint32_t phb = 0;
+        int slot = 0;                                      // counters instead of i % SLOTS, (i / SLOTS) & 1: the divisions
+        uint32_t pa = 0;                                   // cost this single thread ~400 cycles of a 1 750-cycle stage
         for (int i = 0; i < nkb; ++i) {
-            const int slot = i % SLOTS;
             mbar_wait(&b_full[sb], phb);
-            mbar_wait(&a_full[slot], (uint32_t)((i / SLOTS) & 1));
+            if (lane == 0) TW_DBG(0, i);
+            mbar_wait(&a_full[slot], pa);
+            if (lane == 0) TW_DBG(1, i);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
@@ -1162,9 +1179,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
                 umma_commit(&b_empty[sb]);
                 umma_commit(&a_empty[slot]);
                 if (i == nkb - 1) umma_commit(accum_bar);
+                TW_DBG(2, i);
             }
             __syncwarp();
             if (++sb == SBW) { sb = 0; phb ^= 1u; }
+            if (++slot == SLOTS) { slot = 0; pa ^= 1u; }
         }
         if (nkb == 0 && lane == 0) mbar_arrive(accum_bar);
     } else if (wid < 10) {
@@ -1178,11 +1197,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
         const int64_t sak = g.sak, smk = g.smk;
         const int mask_act = g.amask_act;
         float dbacc = 0.f;
-        int issued = 0;
+        int issued = 0, ra_issue = 0;
         auto issue = [&]() {
             const int i = grp + 2 * issued;
             if (i < nkb) {
-                unsigned char* buf = araw + (size_t)(issued % p.RA) * p.a_raw_bytes;
+                unsigned char* buf = araw + (size_t)ra_issue * p.a_raw_bytes;
                 // 16 rows x 32 pieces of 16 bytes: a warp copies one whole row (512 contiguous bytes)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -1199,16 +1218,18 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
             }
             cp_async_commit();
             ++issued;
+            if (++ra_issue == p.RA) ra_issue = 0;
         };
         for (int d = 0; d < p.RA; ++d) issue();
-        int done = 0;
-        for (int i = grp; i < nkb; i += 2, ++done) {
-            const int slot = i % SLOTS;
+        int ra_conv = 0, slot = grp % SLOTS;
+        uint32_t slot_par = 0;                                  // parity of the slot's current use (stage / SLOTS)
+        for (int i = grp; i < nkb; i += 2) {
             if (p.RA == 3) cp_async_wait<2>();
             else if (p.RA == 2) cp_async_wait<1>();
             else cp_async_wait<0>();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // the group's four warps copied each other's rows
-            const float* col = reinterpret_cast<const float*>(araw + (size_t)(done % p.RA) * p.a_raw_bytes) + feat;
+            if (t128 == 0) TW_DBG(3, i);
+            const float* col = reinterpret_cast<const float*>(araw + (size_t)ra_conv * p.a_raw_bytes) + feat;
             float hi[16], lo[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -1219,7 +1240,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // every thread has read: the raw tile may be refilled
             issue();
-            mbar_wait(&a_empty[slot], (uint32_t)(((i / SLOTS) & 1) ^ 1));
+            mbar_wait(&a_empty[slot], slot_par ^ 1u);
+            if (t128 == 0) TW_DBG(4, i);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.a_col0 + slot * 32);
             tmem_st16(taddr, hi);
@@ -1228,55 +1250,84 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[slot]);
+            if (t128 == 0) TW_DBG(5, i);
+            if (++ra_conv == p.RA) ra_conv = 0;
+            slot += 2;                                          // next stage of this group: i + 2
+            if (slot >= SLOTS) { slot -= SLOTS; slot_par ^= 1u; }
         }
         cp_async_wait<0>();
         if (p.db && nblk == 0 && m0 + feat < g.M) atomicAdd(p.db + m0 + feat, dbacc);
     } else {
         // ------------------------------ B converters: 8 warps (X^T into the K-major [hi | lo] tile) -
+        // Thread t (< BN) owns COLUMN t of the tile: its four cells (k chunk c, column t) and its four 16-byte pieces
+        // of the raw tile (rows 4k + t / (BN/4)) sit at constant strides, so the stage loop has no index arithmetic
+        // (the first version recomputed everything with integer divisions in rolled loops: 3 400 cycles per stage;
+        // precomputed offsets with validity predicates: 2 060, still 400 warp-instructions per stage — ncu: the
+        // kernel is issue-bound at 4 700 warp-instructions per stage).
         const int t256 = (wid - 10) * 32 + lane;
-        unsigned char* braw = smem_raw + p.off_braw;
-        const float* Bptr = g.B;
+        const bool act = t256 < BN;
+        float* braw_f = reinterpret_cast<float*>(smem_raw + p.off_braw);
+        const int raw_floats = (int)(p.b_raw_bytes >> 2);
         const int64_t sbk = g.sbk;
-        const int pitch = p.b_pitch;
-        const int pieces_per_row = BN / 4, n_pieces = 16 * pieces_per_row;
-        int issued = 0;
+        const int pitch = p.b_pitch, RB = p.RB;
+        const int ppr = BN >> 2;                                     // 16-byte pieces per row of the raw tile
+        const int rq = act ? t256 / ppr : 0, pcq = act ? t256 - rq * ppr : 0;
+        const int64_t ncol = n0 + 4 * pcq;
+        const int nbytes = (act && ncol < g.N) ? (int)((g.N - ncol >= 4 ? 4 : g.N - ncol) * 4) : 0;
+        const float* src = g.B + (kb_beg * PK_KB + rq) * sbk + (nbytes ? ncol : 0);
+        const int dst0 = rq * pitch + 4 * pcq;
+        int issued = 0, rb_issue = 0;
         auto issue = [&]() {
-            const int i = issued;
-            if (i < nkb) {
-                unsigned char* buf = braw + (size_t)(issued % p.RB) * p.b_raw_bytes;
-                for (int pc = t256; pc < n_pieces; pc += 256) {
-                    const int r = pc / pieces_per_row, c = pc - r * pieces_per_row;
-                    const int64_t b = (kb_beg + i) * PK_KB + r;
-                    const int64_t n = n0 + 4 * c;
-                    int bytes = (b < g.K && n < g.N) ? (int)((g.N - n >= 4 ? 4 : g.N - n) * 4) : 0;
-                    cp_async16(reinterpret_cast<float*>(buf) + r * pitch + 4 * c, bytes ? Bptr + b * sbk + n : Bptr, bytes);
+            if (issued < nkb && act) {
+                float* buf = braw_f + rb_issue * raw_floats + dst0;
+                const int64_t b0 = (kb_beg + issued) * PK_KB + rq;
+                if (b0 - rq + PK_KB <= g.K) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cp_async16(buf + 4 * k * pitch, src + 4 * k * sbk, nbytes);
+                } else {                                               // K tail: rows beyond the batch are zero-filled
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int bytes = (b0 + 4 * k < g.K) ? nbytes : 0;
+                        cp_async16(buf + 4 * k * pitch, bytes ? src + 4 * k * sbk : g.B, bytes);
+                    }
                 }
+                src += PK_KB * sbk;
             }
             cp_async_commit();
             ++issued;
+            if (++rb_issue == RB) rb_issue = 0;
         };
-        for (int d = 0; d < p.RB; ++d) issue();
-        int sb = 0;
+        for (int d = 0; d < RB; ++d) issue();
+        int sb = 0, rb_conv = 0;
         uint32_t phb = 1;
         for (int i = 0; i < nkb; ++i) {
-            if (p.RB == 3) cp_async_wait<2>();
-            else if (p.RB == 2) cp_async_wait<1>();
+            if (RB == 3) cp_async_wait<2>();
+            else if (RB == 2) cp_async_wait<1>();
             else cp_async_wait<0>();
             asm volatile("bar.sync 3, 256;" ::: "memory");
-            const float* raw = reinterpret_cast<const float*>(braw + (size_t)(i % p.RB) * p.b_raw_bytes);
+            if (t256 == 0) TW_DBG(6, i);
+            const float* raw = braw_f + rb_conv * raw_floats + t256;
+            float4 v[4];
+            if (act) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float* cell = raw + 4 * c * pitch;           // 4 samples of column t -> one 16-byte chunk of row t
+                    v[c] = make_float4(cell[0], cell[pitch], cell[2 * pitch], cell[3 * pitch]);
+                }
+            }
             mbar_wait(&b_empty[sb], phb);
-            float* tile = reinterpret_cast<float*>(ringB + (size_t)sb * b_stage);
-            // (n, chunk c): 4 samples of column n -> one 16-byte chunk of row n; lanes = consecutive n
-            for (int q = t256; q < 4 * BN; q += 256) {
-                const int c = q / BN, n = q - c * BN;
-                const float4 v = make_float4(raw[(4 * c + 0) * pitch + n], raw[(4 * c + 1) * pitch + n],
-                                             raw[(4 * c + 2) * pitch + n], raw[(4 * c + 3) * pitch + n]);
-                split_store(tile, (c * BN + n) * 4, BN * 16, v);
+            if (t256 == 0) TW_DBG(8, i);
+            if (act) {
+                float* tile = reinterpret_cast<float*>(ringB + (size_t)sb * b_stage) + t256 * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) split_store(tile, c * BN * 4, BN * 16, v[c]);
             }
             fence_async_smem();
             asm volatile("bar.sync 3, 256;" ::: "memory");           // every thread has read the raw tile and written its chunks
             if (lane == 0) mbar_arrive(&b_full[sb]);
+            if (t256 == 0) TW_DBG(9, i);
             issue();
+            if (++rb_conv == RB) rb_conv = 0;
             if (++sb == SBW) { sb = 0; phb ^= 1u; }
         }
         cp_async_wait<0>();
@@ -1284,9 +1335,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
     if (wid >= 2) {
         // ------------------------------ epilogue (16 warps): reduce the partial tile into dW ------
         mbar_wait(accum_bar, 0);
+        if (wid == 2 && lane == 0) TW_DBG(7, 0);
         tc_fence_after();
         if (nkb > 0) tile_epilogue<EPI_STORE>(g, tmem_base, smem_raw, wid, lane, m0, 1, BN, n0, true);
         tc_fence_before();
+        if (wid == 2 && lane == 0) TW_DBG(7, 1);
     }
     __syncthreads();
     if (wid == 1) {
@@ -1608,16 +1661,22 @@ static bool row_vec_ok_host(const float* base, int64_t ld) { return ((reinterpre
 // TSW: weight-gradient form  C[M,N] = A^T B  with A(m,k) = A[k*sak + m] (sam == 1), B(n,k) = B[k*sbk + n] (sbn == 1),
 // K = batch large, C row-major.  db (may be NULL): column sums of the (masked) A operand, i.e. the bias gradient.
 // Returns -3 when the shape does not qualify.
-int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
+bool gemm_tsw_eligible(const GemmArgs& g) {
     const char* e = getenv("CTR_GEMM_TSW");
-    if (!e || e[0] != '1') return -3;              // opt-in until validated on hardware
-    if (g.sam != 1 || g.sbn != 1 || g.K < 4096 || g.M < 16 || g.N < 16 || g.epilogue != EPI_STORE || g.bmask) return -3;
-    if (g.sak % 4 != 0 || g.sbk % 4 != 0 || !pk_al16(g.A) || !pk_al16(g.B)) return -3;
-    if (g.amask && (g.smm != 1 || g.smk % 4 != 0 || !pk_al16(g.amask))) return -3;
-    if (!row_vec_ok_host(g.C, g.ldc)) return -3;
+    if (e && e[0] == '0') return false;            // CTR_GEMM_TSW=0: SS engine + column-sum kernel (A/B baseline)
+    if (g.sam != 1 || g.sbn != 1 || g.K < 4096 || g.M < 16 || g.N < 16 || g.epilogue != EPI_STORE || g.bmask) return false;
+    if (g.sak % 4 != 0 || g.sbk % 4 != 0 || !pk_al16(g.A) || !pk_al16(g.B)) return false;
+    if (g.amask && (g.smm != 1 || g.smk % 4 != 0 || !pk_al16(g.amask))) return false;
+    if (!row_vec_ok_host(g.C, g.ldc)) return false;
+    return ceil_div64(g.M, PK_AR) <= 65535;
+}
+
+int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
+    if (!gemm_tsw_eligible(g)) return -3;
     TwParams p{};
     p.g = g;
     p.db = db;
+    p.dbg = ctr_debug_buffer();
     const int64_t gn = ceil_div64(g.N, 256);
     p.BN = (int)(ceil_div64(ceil_div64(g.N, gn), 16) * 16);
     const int64_t gm = ceil_div64(g.M, PK_AR);
@@ -1678,10 +1737,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         const int rc_ts = launch_gemm_ts(g, st);
         if (rc_ts != -3) return rc_ts;
     }
-    if (g.allow_split_k) {
-        const int rc_tw = launch_gemm_tsw(g, nullptr, st);
-        if (rc_tw != -3) return rc_tw;
-    }
+
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);
     if (!c.ok) return -3;     // no shared-memory plan for this shape: the caller uses the first-generation engine

@@ -36,20 +36,22 @@ struct PushArgs {
     int32_t* err_flag;
 };
 
-// One block = one field x a chunk of PUSH_CHUNK unique rows.  The slot claim in the owner's receive
-// list is aggregated per block: positions inside the block come from shared-memory atomics, and ONE
-// remote atomicAdd per (block, owner) reserves the range — a remote atomic that returns a value is a
-// full NVLink round trip, and the first version issued one per row (3.4 M per step: 4.5 ms at G = 2).
+// One block = one id column of the plan x a chunk of PUSH_CHUNK unique rows.  A receive list belongs to an id
+// COLUMN, not to a field: every field that reads the column (DeepFM: one embedding table + one linear table)
+// delivers its row into the same slot, so the owner builds ONE duplicate-free plan per column (round 1 kept a list
+// per field: twice the ids, twice the slot claims and twice the owner-side plan).
+// The slot claim in the owner's receive list is aggregated per block: positions inside the block come from
+// shared-memory atomics, and ONE remote atomicAdd per (block, owner) reserves the range — a remote atomic that
+// returns a value is a full NVLink round trip, and the first version issued one per row (3.4 M per step: 4.5 ms at G = 2).
 constexpr int PUSH_CHUNK = 1024;
 constexpr int PUSH_MAX_G = 16;
 __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
     __shared__ int s_cnt[PUSH_MAX_G];
     __shared__ int s_base[PUSH_MAX_G];
     __shared__ int s_dst[PUSH_CHUNK];
-    const int f = blockIdx.y;
-    const bool is_emb = f < a.n_emb;
-    const int pc = is_emb ? a.emb_plan_col[f] : a.lin_plan_col[f - a.n_emb];
+    const int pc = blockIdx.y;
     const int64_t nu = a.n_uniq[pc];
+    const bool vec_rows = (a.D & 3) == 0 && a.D <= 128 && 256 % (a.D >> 2) == 0;
     for (int64_t u0 = (int64_t)blockIdx.x * PUSH_CHUNK; u0 < nu; u0 += (int64_t)gridDim.x * PUSH_CHUNK) {
         if (threadIdx.x < PUSH_MAX_G) s_cnt[threadIdx.x] = 0;
         __syncthreads();
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
         }
         __syncthreads();
         if (threadIdx.x < a.G && s_cnt[threadIdx.x] > 0)
-            s_base[threadIdx.x] = atomicAdd(a.recv_count[threadIdx.x] + f, s_cnt[threadIdx.x]);   // remote, once per owner
+            s_base[threadIdx.x] = atomicAdd(a.recv_count[threadIdx.x] + pc, s_cnt[threadIdx.x]);   // remote, once per owner
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < PUSH_CHUNK / 256; ++j) {     // destinations into shared memory ...
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
                 if (slot >= a.cap) atomicOr(a.err_flag, 2);
                 else {
                     dst = (owner[j] << 26) | (int)slot;
-                    a.recv_ids[owner[j]][(int64_t)f * a.cap + slot] = local[j];
+                    a.recv_ids[owner[j]][(int64_t)pc * a.cap + slot] = local[j];
                 }
             }
             s_dst[threadIdx.x + 256 * j] = dst;
@@ -86,30 +88,33 @@ __global__ void __launch_bounds__(256) rowgrad_push_kernel(PushArgs a) {
         __syncthreads();
         // ... so that D/4 lanes move one row: a warp writes 8 consecutive source rows with 128-bit
         // stores (the first version let one thread write its whole 64-byte row: 0.40 ms per step)
-        if (is_emb && (a.D & 3) == 0 && a.D <= 128 && 256 % (a.D >> 2) == 0) {
-            const int lpr = a.D >> 2, sub = threadIdx.x % lpr;
-            for (int it = threadIdx.x / lpr; it < PUSH_CHUNK; it += 256 / lpr) {
-                const int dst = s_dst[it];
-                if (dst < 0) continue;
-                const int64_t u = u0 + it;
-                const float4 v = *reinterpret_cast<const float4*>(a.emb_rowgrad + f * a.emb_rg_stride + u * a.D + sub * 4);
-                *reinterpret_cast<float4*>(a.recv_emb_rows[dst >> 26] + ((int64_t)f * a.cap + (dst & ((1 << 26) - 1))) * a.D + sub * 4) = v;
+        for (int f = 0; f < a.n_emb; ++f) {
+            if (a.emb_plan_col[f] != pc) continue;       // block-uniform
+            if (vec_rows) {
+                const int lpr = a.D >> 2, sub = threadIdx.x % lpr;
+                for (int it = threadIdx.x / lpr; it < PUSH_CHUNK; it += 256 / lpr) {
+                    const int dst = s_dst[it];
+                    if (dst < 0) continue;
+                    const int64_t u = u0 + it;
+                    const float4 v = *reinterpret_cast<const float4*>(a.emb_rowgrad + f * a.emb_rg_stride + u * a.D + sub * 4);
+                    *reinterpret_cast<float4*>(a.recv_emb_rows[dst >> 26] + ((int64_t)f * a.cap + (dst & ((1 << 26) - 1))) * a.D + sub * 4) = v;
+                }
+            } else {
+                for (int it = threadIdx.x; it < PUSH_CHUNK; it += 256) {
+                    const int dst = s_dst[it];
+                    if (dst < 0) continue;
+                    const float* src = a.emb_rowgrad + f * a.emb_rg_stride + (u0 + it) * a.D;
+                    float* d2 = a.recv_emb_rows[dst >> 26] + ((int64_t)f * a.cap + (dst & ((1 << 26) - 1))) * a.D;
+                    for (int d = 0; d < a.D; ++d) d2[d] = src[d];
+                }
             }
-        } else {
+        }
+        for (int fl = 0; fl < a.n_lin; ++fl) {
+            if (a.lin_plan_col[fl] != pc) continue;      // block-uniform
             for (int it = threadIdx.x; it < PUSH_CHUNK; it += 256) {
                 const int dst = s_dst[it];
                 if (dst < 0) continue;
-                const int64_t u = u0 + it;
-                const int o = dst >> 26;
-                const int64_t slot = dst & ((1 << 26) - 1);
-                if (is_emb) {
-                    const float* src = a.emb_rowgrad + f * a.emb_rg_stride + u * a.D;
-                    float* d2 = a.recv_emb_rows[o] + ((int64_t)f * a.cap + slot) * a.D;
-                    for (int d = 0; d < a.D; ++d) d2[d] = src[d];
-                } else {
-                    const int fl = f - a.n_emb;
-                    a.recv_lin_rows[o][(int64_t)fl * a.cap + slot] = a.lin_rowgrad[fl * a.lin_rg_stride + u];
-                }
+                a.recv_lin_rows[dst >> 26][(int64_t)fl * a.cap + (dst & ((1 << 26) - 1))] = a.lin_rowgrad[fl * a.lin_rg_stride + u0 + it];
             }
         }
         __syncthreads();
@@ -317,7 +322,7 @@ extern "C" int ctr_p2p_close(void* peer_ptr) {
     return 0;
 }
 
-extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
+extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, int n_plan_cols, const int32_t* n_uniq, const int32_t* uniq,
                                 int n_emb, int D, const float* emb_rowgrad, int64_t emb_rowgrad_stride,
                                 const int32_t* emb_plan_col, int n_lin, const float* lin_rowgrad,
                                 int64_t lin_rowgrad_stride, const int32_t* lin_plan_col,
@@ -328,16 +333,17 @@ extern "C" int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, 
             "ctr_rowgrad_push: bad arguments");
     CTR_ARG(n_emb == 0 || (D > 0 && emb_rowgrad && emb_plan_col && recv_emb_rows), "ctr_rowgrad_push: embedding arrays missing");
     CTR_ARG(n_lin == 0 || (lin_rowgrad && lin_plan_col && recv_lin_rows), "ctr_rowgrad_push: linear arrays missing");
+    CTR_ARG(n_plan_cols > 0 && n_plan_cols <= 65535, "ctr_rowgrad_push: bad number of plan columns");
     if (B == 0 || n_emb + n_lin == 0) return 0;
     PushArgs a{B, n_shards, n_uniq, uniq, n_emb, D, emb_rowgrad, emb_rowgrad_stride, emb_plan_col, n_lin,
                lin_rowgrad, lin_rowgrad_stride, lin_plan_col, recv_count, recv_ids, recv_emb_rows, recv_lin_rows, cap, err_flag};
     CTR_ARG(n_shards <= PUSH_MAX_G, "ctr_rowgrad_push: at most %d shards", PUSH_MAX_G);
     CTR_ARG(cap < (1 << 26), "ctr_rowgrad_push: receive-list capacity must be below 2^26 rows");
     int64_t bx = ceil_div64(B, PUSH_CHUNK);
-    const int64_t limit = ceil_div64((int64_t)ctr_sm_count() * 8, n_emb + n_lin);
+    const int64_t limit = ceil_div64((int64_t)ctr_sm_count() * 8, n_plan_cols);
     if (bx > limit) bx = limit;
     if (bx < 1) bx = 1;
-    dim3 grid((unsigned)bx, (unsigned)(n_emb + n_lin));
+    dim3 grid((unsigned)bx, (unsigned)n_plan_cols);
     rowgrad_push_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
     CTR_LAUNCH_OK("rowgrad_push_kernel");
     return 0;

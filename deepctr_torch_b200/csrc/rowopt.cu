@@ -100,7 +100,8 @@ __global__ void rowopt_tick_kernel(float* hp) {
     hp[6] = 1.f - powf(hp[3], step);
 }
 
-// out[f][inv[b, pc(f)]] += recv[f][b], b < count[f]: rows of the same id meet in one output row
+// out[f][inv[b, pc(f)]] += recv[f][b], b < count[pc(f)]: rows of the same id meet in one output row
+// (receive lists belong to the id columns of the plan; every field of a column shares the slots)
 template <bool VEC>
 __global__ void __launch_bounds__(256) combine_kernel(int64_t cap, int D, const int32_t* __restrict__ count,
                                                       const int32_t* __restrict__ inv, int n_plan,
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) combine_kernel(int64_t cap, int D, const 
                                                       float* out, int64_t out_stride) {
     const int f = blockIdx.y;
     const int pc = plan_col[f];
-    const int64_t n = count[f] < cap ? count[f] : cap;
+    const int64_t n = count[pc] < cap ? count[pc] : cap;
     const int per_row = VEC ? (D >> 2) : D;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * per_row; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / per_row;

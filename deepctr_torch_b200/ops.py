@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import functools
+import os
 
 import torch
 
@@ -489,6 +490,30 @@ def dnn_layer(x, W, bias, act="relu", w_kn=False):
     return _DnnLayer.apply(x, W, bias, act_code(act) if isinstance(act, str) else int(act), w_kn)
 
 
+# ---- deferred first-layer weight gradient -------------------------------------------------------------------
+# The first layer's (dW, db) is the last GEMM of the tower backward and nothing in the backward pass consumes it,
+# while its input gradient heads the longest remaining chain (embedding scatter, and on several GPUs the row-gradient
+# push over NVLink).  When the weight-gradient engine needs no shared scratch it is therefore issued on a second
+# stream; the calling stream joins it in an autograd-engine callback at the end of the backward pass (before an
+# optimizer or the dense all-reduce can look at the gradients).  CTR_DEFER_WGRAD=0 keeps everything on one stream.
+_DEFER_WGRAD = os.environ.get("CTR_DEFER_WGRAD", "1") != "0"
+_wgrad_streams = {}
+_wgrad_joins = []
+
+
+def _wgrad_stream(dev):
+    s = _wgrad_streams.get(dev)
+    if s is None:
+        s = _wgrad_streams[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _join_deferred_wgrads():
+    while _wgrad_joins:
+        dev, ev = _wgrad_joins.pop()
+        torch.cuda.current_stream(dev).wait_event(ev)
+
+
 class _DnnTower(torch.autograd.Function):
     """A stack of Linear(+bias) -> activation layers as ONE autograd node (reference core.py:120-134
     without batch-norm / dropout).  Forward = one fused GEMM+bias+activation launch per layer; the
@@ -523,6 +548,7 @@ class _DnnTower(torch.autograd.Function):
             kws.append(Kw)
             cur = y
         ctx.act, ctx.L, ctx.kws = act, L, kws
+        ctx.w0 = params[0]                 # the leaf itself: a pending .grad forbids the deferred weight gradient
         ctx.wshapes = [tuple(params[2 * l].shape) for l in range(L)]
         ctx.save_for_backward(*xs, *Ws, *ys)
         return cur
@@ -547,12 +573,37 @@ class _DnnTower(torch.autograd.Function):
             dx_full = torch.empty(B, ldx, device=dev, dtype=torch.float32) if need_dx else None
             dW = torch.empty(N, Kc, device=dev, dtype=torch.float32)
             db = torch.empty(N, device=dev, dtype=torch.float32)
-            _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
-                      _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, _ptr(dW), Kc, 1, _ptr(db),
-                      B, K, N, ctx.act, 1 if l < L - 1 else 0,
-                      ctx.act if l > 0 else 0, _stream())
-            grads[2 * l] = dW[:, :ctx.kws[l]].contiguous() if Kc != ctx.kws[l] else dW
-            grads[2 * l + 1] = db
+            dy_is_dz = 1 if l < L - 1 else 0
+            defer = (l == 0 and need_dx and _DEFER_WGRAD and B > 0 and getattr(ctx.w0, "grad", None) is None
+                     and _lib.load().ctr_dnn_wgrad_is_scratch_free(
+                         _ptr(x), x.stride(0), _ptr(y), N, _ptr(cur), cur.stride(0), _ptr(dW), Kc, 1, B, K, N,
+                         ctx.act, dy_is_dz) == 1)
+            if defer:
+                main = torch.cuda.current_stream(dev)
+                _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
+                          _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, None, Kc, 1, None,
+                          B, K, N, ctx.act, dy_is_dz, 0, _stream())
+                side = _wgrad_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
+                              _ptr(cur), cur.stride(0), None, 0, _ptr(dW), Kc, 1, _ptr(db),
+                              B, K, N, ctx.act, dy_is_dz, 0, _stream())
+                    grads[0] = dW[:, :ctx.kws[0]].contiguous() if Kc != ctx.kws[0] else dW
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                for t in (x, y, cur, dW, db, grads[0]):
+                    t.record_stream(side)
+                _wgrad_joins.append((dev, ev))
+                torch.autograd.Variable._execution_engine.queue_callback(_join_deferred_wgrads)
+                grads[1] = db
+            else:
+                _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
+                          _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, _ptr(dW), Kc, 1, _ptr(db),
+                          B, K, N, ctx.act, dy_is_dz,
+                          ctx.act if l > 0 else 0, _stream())
+                grads[2 * l] = dW[:, :ctx.kws[l]].contiguous() if Kc != ctx.kws[l] else dW
+                grads[2 * l + 1] = db
             if need_dx:
                 cur = dx_full[:, :K] if ldx != K else dx_full
                 dx_out = cur

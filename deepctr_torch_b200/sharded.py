@@ -269,7 +269,9 @@ class ShardedPlan(ops.GatherPlan):
         return self._emb_ptrs, self._lin_ptrs
 
     def recv_views(self, parity):
-        """This rank's receive lists: (count [n_fields], ids [n_fields, cap], emb [n_emb, cap, D], lin [n_lin, cap])."""
+        """This rank's receive lists: (count [n_fields], ids [n_fields, cap], emb [n_emb, cap, D], lin [n_lin, cap]).
+        A list belongs to an id COLUMN of the plan (``plan_cols_host``): only the first ``len(plan_cols_host)``
+        entries of count / ids are used, and every field reading column pc finds its rows in the slots of list pc."""
         L, r = self.layout, self.layout.recv[parity]
         nf = max(L.n_emb + L.n_lin, 1)
         return (self.arena.view(r["count"], (nf,), torch.int32),
@@ -282,7 +284,7 @@ def push_row_grads(plan, ws, rg_emb, rg_lin, B, n_emb):
     """Called from the fused-input backward in sharded mode."""
     par = plan.step_parity
     rp = plan.recv_ptrs[par]
-    _lib.call("ctr_rowgrad_push", B, plan.world, ops._ptr(ws["n_uniq"]), ops._ptr(ws["uniq"]),
+    _lib.call("ctr_rowgrad_push", B, plan.world, len(plan.plan_cols_host), ops._ptr(ws["n_uniq"]), ops._ptr(ws["uniq"]),
               n_emb, plan.D, ops._ptr(rg_emb), B * max(plan.D, 1), ops._ptr(plan.emb_plan_col),
               plan.n_lin, ops._ptr(rg_lin), B, ops._ptr(plan.lin_plan_col),
               ops._ptr(rp["count"]), ops._ptr(rp["ids"]), ops._ptr(rp["emb"]), ops._ptr(rp["lin"]),
@@ -331,14 +333,21 @@ class ShardedRuntime:
     def _combine_workspace(self):
         if self._cws is None:
             plan, L = self.plan, self.plan.layout
-            nf = L.n_emb + L.n_lin
+            n_plan = max(len(plan.plan_cols_host), 1)
             dev = plan.device
-            ws = plan.alloc_workspace(L.cap, n_cols=max(nf, 1))
+            ws = plan.alloc_workspace(L.cap, n_cols=n_plan)
             i32 = dict(dtype=torch.int32, device=dev)
-            ws["cols"] = torch.arange(max(nf, 1), **i32) * L.cap           # field f's ids start at f * cap
-            ws["vocab"] = torch.tensor((L.emb_rows + L.lin_rows) or [1], **i32)
-            ws["emb_pc"] = torch.arange(max(L.n_emb, 1), **i32)
-            ws["lin_pc"] = torch.arange(max(L.n_lin, 1), **i32) + L.n_emb
+            ws["cols"] = torch.arange(n_plan, **i32) * L.cap               # list pc's ids start at pc * cap
+            # rows this rank holds of the table(s) fed by plan column pc
+            rows_of = [1] * n_plan
+            for f, pc in enumerate(plan.emb_plan_col_host):
+                rows_of[pc] = max(rows_of[pc], L.emb_rows[f])
+            for f, pc in enumerate(plan.lin_plan_col_host):
+                rows_of[pc] = max(rows_of[pc], L.lin_rows[f])
+            ws["vocab"] = torch.tensor(rows_of, **i32)
+            ws["n_plan"] = n_plan
+            ws["emb_pc"] = plan.emb_plan_col if L.n_emb else torch.zeros(1, **i32)
+            ws["lin_pc"] = plan.lin_plan_col if L.n_lin else torch.zeros(1, **i32)
             ws["comb_emb"] = torch.empty(max(L.n_emb, 1), L.cap, max(L.D, 1), device=dev)
             ws["comb_lin"] = torch.empty(max(L.n_lin, 1), L.cap, device=dev)
             self._cws = ws
@@ -352,8 +361,8 @@ class ShardedRuntime:
         plan, L = self.plan, self.plan.layout
         ws = self._combine_workspace()
         counts, ids, emb, lin = plan.recv_views(parity)
-        nf = L.n_emb + L.n_lin
-        if nf == 0:
+        nf = ws["n_plan"]
+        if L.n_emb + L.n_lin == 0:
             return ws
         _lib.call("ctr_unique_plan", ops._ptr(ids.view(torch.float32)), 1, L.cap, nf, ops._ptr(ws["cols"]),
                   ops._ptr(ws["vocab"]), ops._ptr(ws["keys"]), ops._ptr(ws["vals"]), ws["H"], ops._ptr(ws["n_uniq"]),
@@ -364,7 +373,7 @@ class ShardedRuntime:
                       ops._ptr(ws["inv"]), nf, ops._ptr(ws["emb_pc"]), ops._ptr(emb), L.cap * L.D,
                       ops._ptr(ws["comb_emb"]), L.cap * L.D, ops._stream())
         if L.n_lin:
-            _lib.call("ctr_rowgrad_combine", L.cap, L.n_lin, 1, ops._ptr(counts[L.n_emb:]), ops._ptr(ws["n_uniq"]),
+            _lib.call("ctr_rowgrad_combine", L.cap, L.n_lin, 1, ops._ptr(counts), ops._ptr(ws["n_uniq"]),
                       ops._ptr(ws["inv"]), nf, ops._ptr(ws["lin_pc"]), ops._ptr(lin), L.cap,
                       ops._ptr(ws["comb_lin"]), L.cap, ops._stream())
         return ws

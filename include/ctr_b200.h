@@ -131,13 +131,16 @@ int ctr_scatter_bwd_rowwise(int64_t B, int n_plan_cols, const int32_t* inv, cons
  * ctr_p2p_alloc/free : cudaMalloc'ed (zero-filled) buffer that can be exported to peers — the
  *                      only entry points that allocate; ctr_p2p_export writes the 64-byte CUDA
  *                      IPC handle, ctr_p2p_open maps a peer's buffer (peer access enabled lazily).
- * ctr_rowgrad_push   : after ctr_scatter_bwd_rowwise, appends every unique (local row id / G,
- *                      gradient row) of field f to the receive list of its owner GPU id % G:
- *                      slot = atomicAdd(recv_count[owner][f], 1) (remote atomic), then
- *                      recv_ids[owner][f*cap + slot], recv_emb_rows[owner][(f*cap+slot)*D ..]
- *                      (fields n_emb.. are the linear tables, rows in recv_lin_rows[owner]).
- *                      recv_* are DEVICE arrays of n_shards peer pointers.  A full list sets
- *                      bit 1 of *err_flag.
+ * ctr_rowgrad_push   : after ctr_scatter_bwd_rowwise, appends every unique row id of plan column pc
+ *                      (local row = id / G) to the receive list pc of its owner GPU id % G:
+ *                      slot = remote atomicAdd on recv_count[owner][pc] (one claim per block and owner),
+ *                      recv_ids[owner][pc*cap + slot] = local row, and EVERY field reading column pc
+ *                      delivers its gradient into that slot: recv_emb_rows[owner][(f*cap+slot)*D ..]
+ *                      for embedding field f (emb_plan_col[f] == pc), recv_lin_rows[owner][fl*cap+slot]
+ *                      for linear field fl.  One list per id column means one owner-side plan per
+ *                      column (ctr_unique_plan with col_count = recv_count) whatever the number of
+ *                      tables fed by it.  recv_* are DEVICE arrays of n_shards peer pointers.  A full
+ *                      list sets bit 1 of *err_flag.
  */
 int ctr_p2p_alloc(int64_t bytes, void** ptr);
 int ctr_p2p_free(void* ptr);
@@ -150,7 +153,7 @@ int ctr_p2p_close(void* peer_ptr);
  * A peer that never arrives sets bit 2 of *err_flag after a bounded spin. */
 int ctr_p2p_barrier(int32_t* const* peer_flags, int32_t* epoch_ctr, int n_shards, int rank, int32_t* err_flag,
                     void* stream);
-int ctr_rowgrad_push(int64_t B, int n_shards, const int32_t* n_uniq, const int32_t* uniq,
+int ctr_rowgrad_push(int64_t B, int n_shards, int n_plan_cols, const int32_t* n_uniq, const int32_t* uniq,
                      int n_emb, int D, const float* emb_rowgrad, int64_t emb_rowgrad_stride,
                      const int32_t* emb_plan_col,
                      int n_lin, const float* lin_rowgrad, int64_t lin_rowgrad_stride,
@@ -227,6 +230,12 @@ int ctr_dnn_layer_bwd_chain(const float* X, int64_t ldx, const float* W, int64_t
                             const float* Y, int64_t ldy, const float* dY, int64_t lddy,
                             float* dX, int64_t lddx, float* dW, int64_t sdwn, int64_t sdwk, float* db,
                             int64_t B, int K, int N, int act, int dy_is_dz, int dx_act, void* stream);
+/* 1 when ctr_dnn_layer_bwd_chain(..., dX = NULL, dW, db) with these operands runs on the engine that streams both
+ * operands from the batch-major activations (no caller scratch from ctr_set_scratch is touched): such a call may be
+ * issued on a second stream while the first one continues with the input gradient's consumers.  0 otherwise. */
+int ctr_dnn_wgrad_is_scratch_free(const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* dY,
+                                  int64_t lddy, const float* dW, int64_t sdwn, int64_t sdwk, int64_t B, int K,
+                                  int N, int act, int dy_is_dz);
 
 /* Scratch for the tensor-core GEMM engine (csrc/gemm_pk.cu): every GEMM-shaped entry point
  * (ctr_dnn_layer_*, ctr_sgemm, ctr_cross_matrix_*, CrossNetMix projections) first re-tiles its two
@@ -395,8 +404,9 @@ int ctr_varlen_pool_bwd(const float* X, int64_t ldx, int64_t B, int col, int T, 
  *      the kind may be NULL).  row_div > 1: the tables are row shards, row = id (ids are already local).
  *   ctr_rowgrad_combine : owner side of the sharded backward: sums the received
  *        (row, gradient) pairs of field f that share a row, using a unique plan built over the receive
- *        list (ctr_unique_plan with col_count): out[f][inv[b, f]] += recv[f][b] for b < count[f].
- *        The rows u < n_uniq[plan_col[f]] of out are zeroed inside (n_uniq: the plan's distinct-row counts).
+ *        lists (ctr_unique_plan with col_count; one list per id column pc, see ctr_rowgrad_push):
+ *        out[f][inv[b, pc]] += recv[f][b] for b < count[pc], pc = plan_col[f]; count: int32 [n_plan_cols].
+ *        The rows u < n_uniq[pc] of out are zeroed inside (n_uniq: the plan's distinct-row counts).
  */
 enum { CTR_OPT_SGD = 0, CTR_OPT_ADAGRAD = 1, CTR_OPT_ADAM = 2, CTR_OPT_RMSPROP = 3 };
 int ctr_rowopt_tick(float* hp, void* stream);

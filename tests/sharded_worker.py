@@ -119,8 +119,11 @@ def run_check(dev, rank, world, B=2048, V=1003, D=16, optimizer="adagrad", verbo
         torch.cuda.synchronize()
         nf = len(sparse)
         for f, c in enumerate(sparse):
-            for key, buf, pc in (("embedding_dict.%s.weight", ws["comb_emb"][f], f),
-                                 ("linear_model.embedding_dict.%s.weight", ws["comb_lin"][f].unsqueeze(1), nf + f)):
+            # receive lists (and the owner-side plan) belong to the id columns of the plan, shared by the
+            # embedding and the linear table of a feature
+            for key, buf, pc in (("embedding_dict.%s.weight", ws["comb_emb"][f], sh._plan.emb_plan_col_host[f]),
+                                 ("linear_model.embedding_dict.%s.weight", ws["comb_lin"][f].unsqueeze(1),
+                                  sh._plan.lin_plan_col_host[f])):
                 expect = sharded.shard_rows(tot[key % c["name"]], rank, world)
                 n = int(ws["n_uniq"][pc])
                 got = torch.zeros_like(expect)
