@@ -78,14 +78,14 @@ __device__ __forceinline__ float act_apply(int act, float z) {
 }
 
 // derivative of the activation expressed through its OUTPUT y
+// (an if chain on purpose: the switch became a jump table — one indirect branch per ELEMENT inside the GEMM
+// converters' unrolled loops, ~150 cycles each: profiles/r02_raw/tsw_tl_dw2.log before / after)
 __device__ __forceinline__ float act_grad_from_y(int act, float y) {
-    switch (act) {
-        case CTR_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-        case CTR_ACT_SIGMOID: return y * (1.f - y);
-        case CTR_ACT_TANH: return 1.f - y * y;
-        case 100: return y;            // internal: plain multiply by the "mask" operand (GEMM prologue A(m,k) *= aux(m,k))
-        default: return 1.f;
-    }
+    if (act == CTR_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == CTR_ACT_TANH) return 1.f - y * y;
+    if (act == CTR_ACT_SIGMOID) return y * (1.f - y);
+    if (act == 100) return y;          // internal: plain multiply by the "mask" operand (GEMM prologue A(m,k) *= aux(m,k))
+    return 1.f;
 }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -29,6 +29,7 @@
 // weights; measured 34 TFLOP/s effective on the DeepFM tower.  Here the split costs one streaming
 // pass per operand and the GEMM runs at the tensor pipe's pace.
 #include <stdlib.h>
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 #include "gemm.cuh"
 #include "tc_common.cuh"
@@ -1092,8 +1093,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
 //     memory (4 LDS.32 down a column -> split -> two 128-bit stores, conflict-free);
 //   * K (the batch) is split across CTAs; partial tiles are reduced into dW with 128-bit fp32 reductions.
 // ---------------------------------------------------------------------------------------------
-constexpr int TW_A_PITCH = 132;                  // floats per row of a raw A tile (128 features + 4: conflict-free cp.async stores)
-constexpr uint32_t TW_A_TILE = 16 * TW_A_PITCH * 4;           // 8 448 bytes: 16 samples x 128 features
+constexpr int TW_A_PITCH = 128;                  // floats per row of a raw A tile (dense TMA box: 16 samples x 128 features)
+constexpr uint32_t TW_A_TILE = 16 * TW_A_PITCH * 4;           // 8 192 bytes
 
 struct TwParams {
     GemmArgs g;                      // M = out features, N = in features, K = batch
@@ -1109,18 +1110,34 @@ struct TwParams {
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64) p.dbg[(ev) * 64 + (idx)] = clock64(); \
     } while (0)
 
+// one 2-D tiled TMA load: box (x = first column, y = first row) of a row-major fp32 matrix; elements outside the
+// matrix arrive as zeros (batch tail, feature tails) and still count towards the mbarrier's transaction bytes
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
 template <int DUMMY>
-__global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
+__global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p, const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_m,
+                                                                 const __grid_constant__ CUtensorMap map_b) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
-    const int BN = p.BN, SLOTS = p.SLOTS, SBW = p.SBW;
+    const int BN = p.BN, SLOTS = p.SLOTS, SBW = p.SBW, RA = p.RA, RB = p.RB;
     const uint32_t b_stage = (uint32_t)BN * 128u;
     unsigned char* ringB = smem_raw;                                  // converted B stages
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw + p.off_bar);
     uint64_t* b_empty = b_full + SBW;
     uint64_t* a_full = b_empty + SBW;
     uint64_t* a_empty = a_full + SLOTS;
-    uint64_t* accum_bar = a_empty + SLOTS;
+    uint64_t* braw_full = a_empty + SLOTS;                            // raw fp32 tiles delivered by the TMA producer
+    uint64_t* braw_empty = braw_full + RB;
+    uint64_t* araw_full = braw_empty + RB;                            // [2 groups][RA]
+    uint64_t* araw_empty = araw_full + 2 * RA;
+    uint64_t* accum_bar = araw_empty + 2 * RA;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -1139,6 +1156,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
             mbar_init(&a_full[s], 4);
             mbar_init(&a_empty[s], 1);
         }
+        for (int s = 0; s < RB; ++s) {
+            mbar_init(&braw_full[s], 1);              // the producer's arrive.expect_tx
+            mbar_init(&braw_empty[s], 8);
+        }
+        for (int s = 0; s < 2 * RA; ++s) {
+            mbar_init(&araw_full[s], 1);
+            mbar_init(&araw_empty[s], 4);
+        }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1150,7 +1175,32 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
     if (tid == 0) TW_DBG(7, 2);
 
     if (wid == 0) {
-        // idle: both operands are fetched by the converters themselves
+        // ------------------------------ TMA producer: raw fp32 tiles by 2-D tiled loads ----------------------------
+        // One instruction per operand and stage: a [16 samples x BN] box of X, a [16 x 128] box of dZ (and of the
+        // activation mask).  The converters never touch global memory; tails are zero-filled by the TMA unit.
+        // (One bulk copy per sample ROW — 32 to 48 copies of 0.5-0.9 KB per stage — was tried first: ~55 cycles per
+        // copy in the TMA unit, 2 700 cycles per stage.)
+        if (lane == 0) {
+            int rb = 0, ra[2] = {0, 0};
+            uint32_t phb = 1, pha[2] = {1, 1};
+            for (int i = 0; i < nkb; ++i) {
+                const int grp = i & 1;
+                const int y = (int)((kb_beg + i) * PK_KB);
+                uint64_t* bfull = &braw_full[rb];
+                uint64_t* afull = &araw_full[grp * RA + ra[grp]];
+                mbar_wait(&braw_empty[rb], phb);
+                mbar_expect_tx(bfull, (uint32_t)(PK_KB * BN * 4));
+                tma_load_2d(smem_raw + p.off_braw + (size_t)rb * p.b_raw_bytes, &map_b, (int)n0, y, bfull);
+                mbar_wait(&araw_empty[grp * RA + ra[grp]], pha[grp]);
+                mbar_expect_tx(afull, TW_A_TILE * (p.has_mask ? 2u : 1u));
+                unsigned char* dst = smem_raw + p.off_araw + (size_t)(grp * RA + ra[grp]) * p.a_raw_bytes;
+                tma_load_2d(dst, &map_a, (int)m0, y, afull);
+                if (p.has_mask) tma_load_2d(dst + TW_A_TILE, &map_m, (int)m0, y, afull);
+                if (++rb == RB) { rb = 0; phb ^= 1u; }
+                if (++ra[grp] == RA) { ra[grp] = 0; pha[grp] ^= 1u; }
+            }
+        }
+        __syncwarp();
     } else if (wid == 1) {
         // ------------------------------ MMA issuer ------------------------------------------------
         const uint32_t idesc = tf32_idesc(BN);
@@ -1159,13 +1209,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
         uint32_t phb = 0;
         int slot = 0;                                      // counters instead of i % SLOTS, (i / SLOTS) & 1: the divisions
         uint32_t pa = 0;                                   // cost this single thread ~400 cycles of a 1 750-cycle stage
+        // one lane runs the whole loop (waits included): no warp-level reconvergence between stages
+        if (lane == 0)
         for (int i = 0; i < nkb; ++i) {
             mbar_wait(&b_full[sb], phb);
-            if (lane == 0) TW_DBG(0, i);
+            TW_DBG(0, i);
             mbar_wait(&a_full[slot], pa);
-            if (lane == 0) TW_DBG(1, i);
+            TW_DBG(1, i);
             tc_fence_after();
-            if (lane == 0) {
+            {
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
 #pragma unroll
                 for (int j = 0; j < PK_KB / 8; ++j) {
@@ -1181,65 +1233,52 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
                 if (i == nkb - 1) umma_commit(accum_bar);
                 TW_DBG(2, i);
             }
-            __syncwarp();
             if (++sb == SBW) { sb = 0; phb ^= 1u; }
             if (++slot == SLOTS) { slot = 0; pa ^= 1u; }
         }
+        __syncwarp();
         if (nkb == 0 && lane == 0) mbar_arrive(accum_bar);
     } else if (wid < 10) {
         // ------------------------------ A converters: 2 groups x 4 warps (dZ^T through TMEM) ------
         const int cw = wid - 2, grp = cw >> 2, quad = wid & 3;
-        const int t128 = (cw & 3) * 32 + lane;                  // thread inside the group (cp.async mapping)
+        const int t128 = (cw & 3) * 32 + lane;
         const int feat = quad * 32 + lane;                      // the output feature this thread owns = its TMEM lane
-        unsigned char* araw = smem_raw + p.off_araw + (size_t)grp * p.RA * p.a_raw_bytes;
-        const float* Aptr = g.A;
-        const float* Mptr = g.amask;
-        const int64_t sak = g.sak, smk = g.smk;
+        const unsigned char* araw = smem_raw + p.off_araw + (size_t)grp * RA * p.a_raw_bytes;
         const int mask_act = g.amask_act;
         float dbacc = 0.f;
-        int issued = 0, ra_issue = 0;
-        auto issue = [&]() {
-            const int i = grp + 2 * issued;
-            if (i < nkb) {
-                unsigned char* buf = araw + (size_t)ra_issue * p.a_raw_bytes;
-                // 16 rows x 32 pieces of 16 bytes: a warp copies one whole row (512 contiguous bytes)
+        int ra = 0, slot = grp % SLOTS;
+        uint32_t ph_raw = 0, slot_par = 0;                      // parity of the slot's current use (stage / SLOTS)
+        for (int i = grp; i < nkb; i += 2) {
+            mbar_wait(&araw_full[grp * RA + ra], ph_raw);
+            if (t128 == 0) TW_DBG(3, i);
+            const float* col = reinterpret_cast<const float*>(araw + (size_t)ra * p.a_raw_bytes) + feat;
+            float hi[16], lo[16];
+            // samples beyond the batch were zero-filled by the TMA unit; the activation kind is hoisted out of the
+            // element loop (three straight-line variants)
+            if (!p.has_mask) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pc = t128 + 128 * j, r = pc >> 5, c = pc & 31;
-                    const int64_t b = (kb_beg + i) * PK_KB + r;
-                    const int64_t m = m0 + 4 * c;
-                    int bytes = (b < g.K && m < g.M) ? (int)((g.M - m >= 4 ? 4 : g.M - m) * 4) : 0;
-                    float* dst = reinterpret_cast<float*>(buf) + r * TW_A_PITCH + 4 * c;
-                    cp_async16(dst, bytes ? Aptr + b * sak + m : Aptr, bytes);
-                    if (p.has_mask)
-                        cp_async16(reinterpret_cast<float*>(buf + TW_A_TILE) + r * TW_A_PITCH + 4 * c,
-                                   bytes ? Mptr + b * smk + m : Mptr, bytes);
+                for (int r = 0; r < 16; ++r) {
+                    const float v = col[r * TW_A_PITCH];
+                    dbacc += v;
+                    split_tf32(v, hi[r], lo[r]);
+                }
+            } else if (mask_act == CTR_ACT_RELU) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float v = col[TW_A_TILE / 4 + r * TW_A_PITCH] > 0.f ? col[r * TW_A_PITCH] : 0.f;
+                    dbacc += v;
+                    split_tf32(v, hi[r], lo[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float v = col[r * TW_A_PITCH] * act_grad_from_y(mask_act, col[TW_A_TILE / 4 + r * TW_A_PITCH]);
+                    dbacc += v;
+                    split_tf32(v, hi[r], lo[r]);
                 }
             }
-            cp_async_commit();
-            ++issued;
-            if (++ra_issue == p.RA) ra_issue = 0;
-        };
-        for (int d = 0; d < p.RA; ++d) issue();
-        int ra_conv = 0, slot = grp % SLOTS;
-        uint32_t slot_par = 0;                                  // parity of the slot's current use (stage / SLOTS)
-        for (int i = grp; i < nkb; i += 2) {
-            if (p.RA == 3) cp_async_wait<2>();
-            else if (p.RA == 2) cp_async_wait<1>();
-            else cp_async_wait<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // the group's four warps copied each other's rows
-            if (t128 == 0) TW_DBG(3, i);
-            const float* col = reinterpret_cast<const float*>(araw + (size_t)ra_conv * p.a_raw_bytes) + feat;
-            float hi[16], lo[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                float v = col[r * TW_A_PITCH];
-                if (p.has_mask) v *= act_grad_from_y(mask_act, col[TW_A_TILE / 4 + r * TW_A_PITCH]);
-                dbacc += v;
-                split_tf32(v, hi[r], lo[r]);
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");     // every thread has read: the raw tile may be refilled
-            issue();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&araw_empty[grp * RA + ra]);      // the raw tile may be refilled
             mbar_wait(&a_empty[slot], slot_par ^ 1u);
             if (t128 == 0) TW_DBG(4, i);
             tc_fence_after();
@@ -1251,62 +1290,30 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[slot]);
             if (t128 == 0) TW_DBG(5, i);
-            if (++ra_conv == p.RA) ra_conv = 0;
+            if (++ra == RA) { ra = 0; ph_raw ^= 1u; }
             slot += 2;                                          // next stage of this group: i + 2
             if (slot >= SLOTS) { slot -= SLOTS; slot_par ^= 1u; }
         }
-        cp_async_wait<0>();
         if (p.db && nblk == 0 && m0 + feat < g.M) atomicAdd(p.db + m0 + feat, dbacc);
     } else {
         // ------------------------------ B converters: 8 warps (X^T into the K-major [hi | lo] tile) -
-        // Thread t (< BN) owns COLUMN t of the tile: its four cells (k chunk c, column t) and its four 16-byte pieces
-        // of the raw tile (rows 4k + t / (BN/4)) sit at constant strides, so the stage loop has no index arithmetic
-        // (the first version recomputed everything with integer divisions in rolled loops: 3 400 cycles per stage;
-        // precomputed offsets with validity predicates: 2 060, still 400 warp-instructions per stage — ncu: the
-        // kernel is issue-bound at 4 700 warp-instructions per stage).
+        // Thread t (< BN) owns COLUMN t of the tile: it reads the 16 samples of its column from the raw tile
+        // (conflict-free LDS.32) and writes the four 16-byte chunks (k chunk c, column t) of the MMA tile.  History of
+        // this warp group (cycles per 16-sample stage, dW1 of the DeepFM tower): rolled loops with integer divisions
+        // 3 400; precomputed offsets, cp.async by the converters themselves 2 060 -> 1 750 (column ownership): ncu showed
+        // 4 700 warp-instructions per stage and every phase between two named barriers taking ~550 cycles; with the
+        // raw tiles delivered by bulk copies the loop has no global-memory instruction and no CTA-level barrier left.
         const int t256 = (wid - 10) * 32 + lane;
         const bool act = t256 < BN;
-        float* braw_f = reinterpret_cast<float*>(smem_raw + p.off_braw);
+        const float* braw_f = reinterpret_cast<const float*>(smem_raw + p.off_braw);
         const int raw_floats = (int)(p.b_raw_bytes >> 2);
-        const int64_t sbk = g.sbk;
-        const int pitch = p.b_pitch, RB = p.RB;
-        const int ppr = BN >> 2;                                     // 16-byte pieces per row of the raw tile
-        const int rq = act ? t256 / ppr : 0, pcq = act ? t256 - rq * ppr : 0;
-        const int64_t ncol = n0 + 4 * pcq;
-        const int nbytes = (act && ncol < g.N) ? (int)((g.N - ncol >= 4 ? 4 : g.N - ncol) * 4) : 0;
-        const float* src = g.B + (kb_beg * PK_KB + rq) * sbk + (nbytes ? ncol : 0);
-        const int dst0 = rq * pitch + 4 * pcq;
-        int issued = 0, rb_issue = 0;
-        auto issue = [&]() {
-            if (issued < nkb && act) {
-                float* buf = braw_f + rb_issue * raw_floats + dst0;
-                const int64_t b0 = (kb_beg + issued) * PK_KB + rq;
-                if (b0 - rq + PK_KB <= g.K) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cp_async16(buf + 4 * k * pitch, src + 4 * k * sbk, nbytes);
-                } else {                                               // K tail: rows beyond the batch are zero-filled
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int bytes = (b0 + 4 * k < g.K) ? nbytes : 0;
-                        cp_async16(buf + 4 * k * pitch, bytes ? src + 4 * k * sbk : g.B, bytes);
-                    }
-                }
-                src += PK_KB * sbk;
-            }
-            cp_async_commit();
-            ++issued;
-            if (++rb_issue == RB) rb_issue = 0;
-        };
-        for (int d = 0; d < RB; ++d) issue();
-        int sb = 0, rb_conv = 0;
-        uint32_t phb = 1;
+        const int pitch = p.b_pitch;
+        int sb = 0, rb = 0;
+        uint32_t phb = 1, ph_raw = 0;
         for (int i = 0; i < nkb; ++i) {
-            if (RB == 3) cp_async_wait<2>();
-            else if (RB == 2) cp_async_wait<1>();
-            else cp_async_wait<0>();
-            asm volatile("bar.sync 3, 256;" ::: "memory");
+            mbar_wait(&braw_full[rb], ph_raw);
             if (t256 == 0) TW_DBG(6, i);
-            const float* raw = braw_f + rb_conv * raw_floats + t256;
+            const float* raw = braw_f + rb * raw_floats + t256;
             float4 v[4];
             if (act) {
 #pragma unroll
@@ -1315,6 +1322,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
                     v[c] = make_float4(cell[0], cell[pitch], cell[2 * pitch], cell[3 * pitch]);
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&braw_empty[rb]);             // the raw tile may be refilled
             mbar_wait(&b_empty[sb], phb);
             if (t256 == 0) TW_DBG(8, i);
             if (act) {
@@ -1323,14 +1332,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p) {
                 for (int c = 0; c < 4; ++c) split_store(tile, c * BN * 4, BN * 16, v[c]);
             }
             fence_async_smem();
-            asm volatile("bar.sync 3, 256;" ::: "memory");           // every thread has read the raw tile and written its chunks
+            __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[sb]);
             if (t256 == 0) TW_DBG(9, i);
-            issue();
-            if (++rb_conv == RB) rb_conv = 0;
+            if (++rb == RB) { rb = 0; ph_raw ^= 1u; }
             if (++sb == SBW) { sb = 0; phb ^= 1u; }
         }
-        cp_async_wait<0>();
     }
     if (wid >= 2) {
         // ------------------------------ epilogue (16 warps): reduce the partial tile into dW ------
@@ -1661,6 +1668,37 @@ static bool row_vec_ok_host(const float* base, int64_t ld) { return ((reinterpre
 // TSW: weight-gradient form  C[M,N] = A^T B  with A(m,k) = A[k*sak + m] (sam == 1), B(n,k) = B[k*sbk + n] (sbn == 1),
 // K = batch large, C row-major.  db (may be NULL): column sums of the (masked) A operand, i.e. the bias gradient.
 // Returns -3 when the shape does not qualify.
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeFn>(ptr);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// row-major fp32 matrix [rows, cols] with a row stride of ld floats, loaded in boxes of [16 rows x box_cols]
+static bool make_tile_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)PK_KB};
+    const cuuint32_t estr[2] = {1, 1};
+    return tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool gemm_tsw_eligible(const GemmArgs& g) {
     const char* e = getenv("CTR_GEMM_TSW");
     if (e && e[0] == '0') return false;            // CTR_GEMM_TSW=0: SS engine + column-sum kernel (A/B baseline)
@@ -1668,7 +1706,8 @@ bool gemm_tsw_eligible(const GemmArgs& g) {
     if (g.sak % 4 != 0 || g.sbk % 4 != 0 || !pk_al16(g.A) || !pk_al16(g.B)) return false;
     if (g.amask && (g.smm != 1 || g.smk % 4 != 0 || !pk_al16(g.amask))) return false;
     if (!row_vec_ok_host(g.C, g.ldc)) return false;
-    return ceil_div64(g.M, PK_AR) <= 65535;
+    if (g.K > 0x7fffffff || g.M > 0x7fffffff || g.N > 0x7fffffff) return false;      // tensor-map coordinates are int32
+    return ceil_div64(g.M, PK_AR) <= 65535 && tensor_map_encoder() != nullptr;
 }
 
 int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
@@ -1694,31 +1733,36 @@ int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
     if (p.SLOTS > 8) p.SLOTS = 8;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.a_col0 + p.SLOTS * 32) p.tmem_cols <<= 1;
-    p.b_pitch = p.BN + 4;
+    p.b_pitch = p.BN;                                   // dense TMA box
     p.b_raw_bytes = (uint32_t)(16 * p.b_pitch * 4);
     p.a_raw_bytes = TW_A_TILE * (p.has_mask ? 2u : 1u);
     const int64_t budget = 232448 - 1024, b_stage = (int64_t)p.BN * 128;
     const int64_t stg = (int64_t)PK_CONV_WARPS * 32 * PK_STG_PITCH * 4;
     p.SBW = 0;
     for (int ra = 3; ra >= 2 && !p.SBW; --ra)
-        for (int sbw = 3; sbw >= 2 && !p.SBW; --sbw) {
-            const int64_t need = sbw * b_stage + 3 * (int64_t)p.b_raw_bytes + 2 * ra * (int64_t)p.a_raw_bytes;
-            if (need <= budget) {
-                p.SBW = sbw;
-                p.RA = ra;
-                p.RB = 3;
+        for (int sbw = 3; sbw >= 2 && !p.SBW; --sbw)
+            for (int rb = 4; rb >= 3 && !p.SBW; --rb) {
+                const int64_t need = sbw * b_stage + rb * (int64_t)p.b_raw_bytes + 2 * ra * (int64_t)p.a_raw_bytes;
+                if (need <= budget) {
+                    p.SBW = sbw;
+                    p.RA = ra;
+                    p.RB = rb;
+                }
             }
-        }
     if (!p.SBW) return -3;
     int64_t off = p.SBW * b_stage;
     p.off_braw = (uint32_t)off;
     off += (int64_t)p.RB * p.b_raw_bytes;
-    p.off_araw = (uint32_t)((off + 15) / 16 * 16);
+    p.off_araw = (uint32_t)((off + 127) / 128 * 128);
     off = p.off_araw + 2 * (int64_t)p.RA * p.a_raw_bytes;
     if (off < stg) off = stg;
     p.off_bar = (uint32_t)((off + 15) / 16 * 16);
-    const size_t smem = p.off_bar + (size_t)(2 * p.SBW + 2 * p.SLOTS + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = p.off_bar + (size_t)(2 * p.SBW + 2 * p.SLOTS + 2 * p.RB + 4 * p.RA + 1) * sizeof(uint64_t) + 16;
     if (smem > 232448) return -3;
+    CUtensorMap map_a, map_m, map_b;
+    bool ok = make_tile_map(&map_a, g.A, g.K, g.M, g.sak, PK_AR) && make_tile_map(&map_b, g.B, g.K, g.N, g.sbk, p.BN);
+    ok = ok && make_tile_map(&map_m, g.amask ? g.amask : g.A, g.K, g.M, g.amask ? g.smk : g.sak, PK_AR);
+    if (!ok) return -3;
     if (!g.accumulate) CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
     if (db) CTR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * g.M, st));
     static bool configured = false;
@@ -1727,7 +1771,7 @@ int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)splits);
-    gemm_tsw_kernel<0><<<grid, PK_THREADS, smem, st>>>(p);
+    gemm_tsw_kernel<0><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_m, map_b);
     CTR_LAUNCH_OK("gemm_tsw_kernel");
     return 0;
 }

@@ -54,16 +54,16 @@ if what == "check":
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).requires_grad_(True)
     b = (torch.randn(N, device="cuda", generator=g) * 0.05).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
-    y = ops.dnn_layer(xr, W, b, "relu")
+    y = ops.dnn_layer(xr, W, b, "tanh")
     w = torch.randn(B, N, device="cuda", generator=g)
     (y * w).sum().backward()
     x64 = x.double().requires_grad_(True)
     W64, b64 = W.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
-    y64 = torch.relu(x64 @ W64.t() + b64)
+    y64 = torch.tanh(x64 @ W64.t() + b64)
     (y64 * w.double()).sum().backward()
     for name, got, ref in (("y", y, y64), ("dx", xr.grad, x64.grad), ("dW", W.grad, W64.grad), ("db", b.grad, b64.grad)):
         e = float((got.double() - ref).abs().max() / ref.abs().max())
-        print("dnn_layer relu B=%d K=%d N=%d  %s rel err %.3e" % (B, K, N, name, e), flush=True)
+        print("dnn_layer tanh B=%d K=%d N=%d  %s rel err %.3e" % (B, K, N, name, e), flush=True)
         worst = max(worst, e if name == "y" else e * 0.1)
     sys.exit(0 if worst < 5e-6 else 1)
 

@@ -168,3 +168,32 @@ print("ERR", float((C.double() - ref).abs().max() / ref.abs().max()))
     assert r.returncode == 0, r.stderr[-2000:]
     err = float([l for l in r.stdout.splitlines() if l.startswith("ERR")][-1].split()[1])
     assert err <= 5e-6, (variant, err)
+
+
+@pytest.mark.parametrize("B,K,N,masked", [(65536, 432, 256, True), (65536, 256, 128, False), (5000, 432, 256, True),
+                                          (4099, 100, 132, True), (4099, 101, 130, True), (70001, 24, 40, False), (8192, 600, 20, True),
+                                          (16384, 256, 384, False), (4097, 432, 256, False)])
+def test_wgrad_engine_matches_fp64(B, K, N, masked):
+    """The weight-gradient engine (csrc/gemm_pk.cu gemm_tsw_kernel: dZ^T through tensor memory, raw row segments by
+    bulk copies, fused bias gradient) through ctr_dnn_layer_bwd_chain: dW and db against fp64, with and without the
+    act'(Y) mask, with M / N tails inside a tile and a batch tail inside the last 16-sample stage.  Reference:
+    autograd of nn.Linear inside DNN (layers/core.py:120-134).  Tolerance: the batch is the contraction, 65 536 samples
+    are accumulated by truncating fp32 adds in chains of ~100 stages: 2e-5 of max|dW|."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    K4, N4 = (K + 3) // 4 * 4, (N + 3) // 4 * 4
+    X = torch.randn(B, K4, device="cuda", generator=g)
+    Y = torch.relu(torch.randn(B, N4, device="cuda", generator=g))
+    dY = torch.randn(B, N4, device="cuda", generator=g)
+    W = torch.randn(N, K4, device="cuda", generator=g)
+    dW = torch.full((N, K4), float("nan"), device="cuda")
+    db = torch.full((N,), float("nan"), device="cuda")
+    ops.ensure_gemm_scratch(torch.device("cuda:0"), B, K, N)
+    _lib.call("ctr_dnn_layer_bwd_chain", ops._ptr(X), K4, ops._ptr(W), K4, 1, ops._ptr(Y) if masked else None,
+              N4 if masked else 0, ops._ptr(dY), N4, None, 0, ops._ptr(dW), K4, 1, ops._ptr(db), B, K, N,
+              1 if masked else 0, 0 if masked else 1, 0, ops._stream())
+    torch.cuda.synchronize()
+    dz = dY[:, :N].double() * ((Y[:, :N] > 0).double() if masked else 1.0)
+    ref_w = dz.t() @ X[:, :K].double()
+    ref_b = dz.sum(0)
+    assert float((dW[:, :K].double() - ref_w).abs().max() / ref_w.abs().max()) <= 2e-5
+    assert float((db.double() - ref_b).abs().max() / ref_b.abs().max()) <= 5e-6
