@@ -274,7 +274,14 @@ struct PkParams {
     uint32_t off_b, off_raw, off_bar;     // shared-memory layout (bytes): A ring at 0
     uint32_t raw_a_bytes, raw_b_bytes;    // raw cp.async region of each streamed operand, per depth
     int t0_b;                             // first converter thread of B's OP_TRANS groups
+    unsigned long long* dbg;              // optional clock64 timeline of CTA (0,0,0) (ctr_debug_set_buffer): [8 events][64 stages]
+    int a_tma;                            // K-contiguous streamed A: raw [MT*128 x 16] fp32 tiles arrive by 2-D tiled TMA loads
+                                          // (64-byte swizzle) instead of the converters' own cp.async pieces
 };
+#define PK_DBG(ev, idx)                                                                                   \
+    do {                                                                                                  \
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64) p.dbg[(ev) * 64 + (idx)] = clock64(); \
+    } while (0)
 
 constexpr int PK_CONV_THREADS = PK_CONV_WARPS * 32;
 
@@ -441,6 +448,15 @@ __device__ __forceinline__ void stream_convert(const StreamOp& o, const PieceSet
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// one 2-D tiled TMA load: box (x = first column, y = first row) of a row-major fp32 matrix; elements outside the
+// matrix arrive as zeros (batch tail, feature tails) and still count towards the mbarrier's transaction bytes
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -592,7 +608,8 @@ __device__ __forceinline__ void tile_epilogue(const GemmArgs& g, uint32_t tmem_b
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
+__global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p, const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_am) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const GemmArgs& g = p.g;
     const int BN = p.BN, MT = p.MT, SA = p.SA, SB = p.SB;
@@ -606,7 +623,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     uint64_t* b_full = a_empty + SA;
     uint64_t* b_empty = b_full + SB;
     uint64_t* accum_bar = b_empty + SB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* raw_full = accum_bar + 1;                   // [depth] raw A tiles delivered by TMA (a_tma)
+    uint64_t* raw_empty = raw_full + p.depth;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + p.depth);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int64_t mblk = blockIdx.y, nblk = blockIdx.x;
@@ -615,6 +634,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     const int nkb = (int)(kb_end - kb_beg);
     const bool split = gridDim.z > 1;
     const bool a_stream = p.sa.mode != OP_PACKED, b_stream = p.sb.mode != OP_PACKED;
+    const bool a_tma = p.a_tma != 0;
 
     if (tid == 0) {
         // a stage is full after all converter warps arrived (streamed operand) or after the TMA
@@ -628,6 +648,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             mbar_init(&b_empty[s], 1);
         }
         mbar_init(accum_bar, 1);
+        for (int s = 0; s < p.depth; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], PK_CONV_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (wid == 1) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
@@ -635,16 +659,27 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) PK_DBG(7, 2);
 
     if (wid == 0) {
-        // ------------------------------ TMA producer (one lane): packed operands ------------
-        if (lane == 0 && (!a_stream || !b_stream)) {
+        // ------------------------------ TMA producer (one lane): packed operands, raw A tiles ------------
+        if (lane == 0 && (!a_stream || !b_stream || a_tma)) {
             const unsigned char* a_src = reinterpret_cast<const unsigned char*>(p.Ap);
             const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
-            int sa = 0, sb = 0;
-            uint32_t pha = 1, phb = 1;                    // parity of the "empty" phase to wait for
+            int sa = 0, sb = 0, dr = 0;
+            uint32_t pha = 1, phb = 1, phr = 1;           // parity of the "empty" phase to wait for
+            const uint32_t raw_tile = (uint32_t)MT * PK_AR * 64u;          // [MT*128 rows x 16 k] fp32
+            const uint32_t raw_depth_bytes = p.raw_a_bytes + p.raw_b_bytes;
             for (int i = 0; i < nkb; ++i) {
                 const int64_t kb = kb_beg + i;
+                if (a_tma) {
+                    mbar_wait(&raw_empty[dr], phr);
+                    mbar_expect_tx(&raw_full[dr], raw_tile * (p.sa.mask ? 2u : 1u));
+                    unsigned char* dst = smem_raw + p.off_raw + (size_t)dr * raw_depth_bytes;
+                    tma_load_2d(dst, &map_a, (int)(kb * PK_KB), (int)(mblk * MT * PK_AR), &raw_full[dr]);
+                    if (p.sa.mask) tma_load_2d(dst + 16384, &map_am, (int)(kb * PK_KB), (int)(mblk * MT * PK_AR), &raw_full[dr]);
+                    if (++dr == p.depth) { dr = 0; phr ^= 1u; }
+                }
                 if (!a_stream) {
                     mbar_wait(&a_empty[sa], pha);
                     mbar_expect_tx(&a_full[sa], a_stage);
@@ -670,7 +705,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
         uint32_t pha = 0, phb = 0;
         for (int i = 0; i < nkb; ++i) {
             mbar_wait(&a_full[sa], pha);
+            if (lane == 0) PK_DBG(0, i);
             mbar_wait(&b_full[sb], phb);
+            if (lane == 0) PK_DBG(1, i);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(ringA + (size_t)sa * a_stage);
@@ -692,6 +729,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                 umma_commit(&a_empty[sa]);                // frees the stages when these MMAs retire
                 umma_commit(&b_empty[sb]);
                 if (i == nkb - 1) umma_commit(accum_bar);
+                PK_DBG(2, i);
             }
             __syncwarp();
             if (++sa == SA) { sa = 0; pha ^= 1u; }
@@ -712,13 +750,25 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             PieceSet pa, pb;
             if (a_stream) piece_setup(p.sa, MT * PK_AR, PK_AR, a_row0, kb_beg * PK_KB, ct, 0, pa);
             if (b_stream) piece_setup(p.sb, BN, BN, b_row0, kb_beg * PK_KB, ct, p.t0_b, pb);
+            // a_tma: piece q of this thread = (row r, 16-byte chunk c) of the raw tile the TMA unit wrote with the
+            // 64-byte swizzle: chunk c of row r sits at r*64 + ((c ^ ((r >> 1) & 3)) * 16) — a quarter warp (8 consecutive
+            // rows, same c) then reads 8 different 16-byte bank groups
+            int raw_off[2] = {0, 0};
+            if (a_tma) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = ct + PK_CONV_THREADS * q, R = MT * PK_AR;
+                    const int c = idx / R, r = idx - c * R;
+                    raw_off[q] = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+                }
+            }
             int64_t krem_issue = g.K - kb_beg * PK_KB;    // K left at the stage being issued
             int issued = 0, d_issue = 0;
             auto issue = [&]() {
                 if (issued < nkb) {
                     const int kr = krem_issue > 64 ? 64 : (int)krem_issue;
                     unsigned char* base = raw + (size_t)d_issue * raw_depth;
-                    if (a_stream) stream_issue(oa, pa, kr, reinterpret_cast<float4*>(base) + pa.tloc);
+                    if (a_stream && !a_tma) stream_issue(oa, pa, kr, reinterpret_cast<float4*>(base) + pa.tloc);
                     if (b_stream) stream_issue(ob, pb, kr, reinterpret_cast<float4*>(base + p.raw_a_bytes) + pb.tloc);
                 }
                 cp_async_commit();
@@ -728,13 +778,35 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
             };
             for (int i = 0; i < p.depth; ++i) issue();
             int sa = 0, sb = 0, d = 0;
-            uint32_t pha = 1, phb = 1;
+            uint32_t pha = 1, phb = 1, phr = 0;
             for (int i = 0; i < nkb; ++i) {
-                if (p.depth == 3) cp_async_wait<2>();
-                else cp_async_wait<1>();
+                if (b_stream || !a_tma) {
+                    if (p.depth == 3) cp_async_wait<2>();
+                    else cp_async_wait<1>();
+                }
                 const unsigned char* base = raw + (size_t)d * raw_depth;
-                if (a_stream) {
+                if (a_tma) {
+                    mbar_wait(&raw_full[d], phr);
+                    if (ct == 0) PK_DBG(3, i);
+                    float4 v[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (pa.toff[q] < 0) continue;
+                        v[q] = *reinterpret_cast<const float4*>(base + raw_off[q]);
+                        if (oa.mask) v[q] = pk_mask4(v[q], *reinterpret_cast<const float4*>(base + 16384 + raw_off[q]), oa.mask_act);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_empty[d]);        // the raw tile may be refilled
                     mbar_wait(&a_empty[sa], pha);
+                    if (ct == 0) PK_DBG(4, i);
+                    float* tile = reinterpret_cast<float*>(ringA + (size_t)sa * a_stage);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (pa.toff[q] >= 0) split_store(tile, pa.toff[q], PK_AR * 16, v[q]);
+                } else if (a_stream) {
+                    if (ct == 0) PK_DBG(3, i);
+                    mbar_wait(&a_empty[sa], pha);
+                    if (ct == 0) PK_DBG(4, i);
                     stream_convert(oa, pa, PK_AR, reinterpret_cast<float*>(ringA + (size_t)sa * a_stage),
                                    reinterpret_cast<const float4*>(base) + pa.tloc);
                 }
@@ -749,18 +821,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p) {
                     if (a_stream) mbar_arrive(&a_full[sa]);
                     if (b_stream) mbar_arrive(&b_full[sb]);
                 }
+                if (ct == 0) PK_DBG(5, i);
                 if (++sa == SA) { sa = 0; pha ^= 1u; }
                 if (++sb == SB) { sb = 0; phb ^= 1u; }
-                if (++d == p.depth) d = 0;
+                if (++d == p.depth) { d = 0; phr ^= 1u; }
                 issue();
             }
             cp_async_wait<0>();
         }
         // ------------------------------ epilogue (16 warps) ---------------------------------
         mbar_wait(accum_bar, 0);
+        if (wid == 2 && lane == 0) PK_DBG(7, 0);
         tc_fence_after();
         tile_epilogue<EPI>(g, tmem_base, smem_raw, wid, lane, mblk * MT * PK_AR, MT, BN, nblk * BN, split);
         tc_fence_before();
+        if (wid == 2 && lane == 0) PK_DBG(7, 1);
     }
     __syncthreads();
     if (wid == 1) {
@@ -1110,16 +1185,6 @@ struct TwParams {
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 64) p.dbg[(ev) * 64 + (idx)] = clock64(); \
     } while (0)
 
-// one 2-D tiled TMA load: box (x = first column, y = first row) of a row-major fp32 matrix; elements outside the
-// matrix arrive as zeros (batch tail, feature tails) and still count towards the mbarrier's transaction bytes
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
-
 template <int DUMMY>
 __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p, const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_m,
@@ -1460,7 +1525,7 @@ PkConfig pk_config(const GemmArgs& g, bool allow_split, bool force_mt1 = false) 
         if (rings < stg) rings = stg;
         c.off_raw = (uint32_t)rings;
         c.off_bar = (uint32_t)(rings + c.depth * raw_per_depth);
-        c.smem = c.off_bar + (uint32_t)((2 * c.SA + 2 * c.SB + 1) * sizeof(uint64_t) + 16);
+        c.smem = c.off_bar + (uint32_t)((2 * c.SA + 2 * c.SB + 1 + 2 * c.depth) * sizeof(uint64_t) + 16);
         if (c.smem > 232448) c.ok = false;
     }
     // nothing fits with two accumulators (e.g. both operands streamed, one of them masked): one accumulator
@@ -1689,14 +1754,15 @@ static TensorMapEncodeFn tensor_map_encoder() {
 }
 
 // row-major fp32 matrix [rows, cols] with a row stride of ld floats, loaded in boxes of [16 rows x box_cols]
-static bool make_tile_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols) {
+static bool make_tile_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                          int box_rows = PK_KB, bool swizzle64 = false) {
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)PK_KB};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool gemm_tsw_eligible(const GemmArgs& g) {
@@ -1813,6 +1879,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
     PkParams p{};
     p.g = g;
+    p.dbg = ctr_debug_buffer();
     p.Ap = Ap;
     p.Bp = Bp;
     p.sa = StreamOp{g.A, g.sam, g.sak, g.amask, g.smm, g.smk, g.amask_act, g.M, c.a_mode};
@@ -1831,6 +1898,17 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     p.raw_a_bytes = c.raw_a_bytes;
     p.raw_b_bytes = c.raw_b_bytes;
     p.t0_b = c.t0_b;
+    // K-contiguous streamed A: raw tiles by 2-D tiled TMA loads (CTR_PK_ATMA=0: the converters' own cp.async pieces)
+    CUtensorMap map_a{}, map_am{};
+    {
+        const char* e = getenv("CTR_PK_ATMA");
+        if (c.a_mode == OP_KVEC && !(e && e[0] == '0') && tensor_map_encoder() && g.M <= 0x7fffffff && g.K <= 0x7fffffff &&
+            c.off_raw % 1024 == 0 && (c.raw_a_bytes + c.raw_b_bytes) % 1024 == 0) {
+            bool ok = make_tile_map(&map_a, g.A, g.M, g.K, g.sam, PK_KB, c.MT * PK_AR, true);
+            if (ok && g.amask) ok = make_tile_map(&map_am, g.amask, g.M, g.K, g.smm, PK_KB, c.MT * PK_AR, true);
+            p.a_tma = ok ? 1 : 0;
+        }
+    }
     const size_t smem = c.smem;
     static bool configured = false;
     if (!configured) {
@@ -1844,11 +1922,11 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
     }
     dim3 grid((unsigned)c.gn, (unsigned)c.gm, (unsigned)c.splits);
     switch (g.epilogue) {
-        case EPI_BIAS_ACT: gemm_pk_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_MUL_ACTGRAD: gemm_pk_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_CROSS: gemm_pk_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p); break;
-        case EPI_MUL: gemm_pk_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p); break;
-        default: gemm_pk_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p); break;
+        case EPI_BIAS_ACT: gemm_pk_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_MUL_ACTGRAD: gemm_pk_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_CROSS: gemm_pk_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_MUL: gemm_pk_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        default: gemm_pk_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
     }
     CTR_LAUNCH_OK("gemm_pk_kernel");
     return 0;

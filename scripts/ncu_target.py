@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from oracle import ctr_oracle as O
 from helpers import build_model
+from deepctr_torch_b200 import ops
 
 model = sys.argv[1] if len(sys.argv) > 1 else "DeepFM"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
@@ -25,7 +26,7 @@ X = torch.cat([torch.randint(0, V, (B, 26), device="cuda", generator=g).float(),
 y = (torch.rand(B, device="cuda", generator=g) < 0.25).float()
 for _ in range(steps):
     m.zero_grad(set_to_none=True)
-    loss = torch.nn.functional.binary_cross_entropy(m(X).squeeze(1), y, reduction="sum")
+    loss = ops.binary_cross_entropy(m(X).squeeze(1), y, reduction="sum")
     loss.backward()
 torch.cuda.synchronize()
 print("done", float(loss))
