@@ -1847,6 +1847,10 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         const int rc_ts = launch_gemm_ts(g, st);
         if (rc_ts != -3) return rc_ts;
     }
+    if (g.allow_split_k) {          // long-K products of two batch-major operands (bilinear dW, ...): the TSW engine
+        const int rc_tw = launch_gemm_tsw(g, nullptr, st);
+        if (rc_tw != -3) return rc_tw;
+    }
 
     const bool allow_split = g.allow_split_k && g.epilogue == EPI_STORE;
     const PkConfig c = pk_config(g, allow_split);

@@ -534,7 +534,9 @@ class _DnnTower(torch.autograd.Function):
             B, K = cur.shape
             Wc = W if W.is_contiguous() else W.contiguous()
             N, Kw = Wc.shape
-            if Kw % 4 != 0:
+            if Kw % 4 != 0 and K != Kw:
+                # the input carries zero columns up to a multiple of 4: the weight rows must match.  (K == Kw: the
+                # unpadded weight is used as it is — the pack kernels take any row stride — no pad kernels per step.)
                 Wc = torch.nn.functional.pad(Wc, (0, _round4(Kw) - Kw))
             if K != Kw and K != _round4(Kw):
                 raise ValueError("dnn_tower: input width %d does not match weight width %d" % (K, Kw))
@@ -571,12 +573,13 @@ class _DnnTower(torch.autograd.Function):
             need_dx = l > 0 or ctx.needs_input_grad[0]
             ldx = _round4(K)
             dx_full = torch.empty(B, ldx, device=dev, dtype=torch.float32) if need_dx else None
-            dW = torch.empty(N, Kc, device=dev, dtype=torch.float32)
+            Kd = _round4(Kc)                       # dW rows padded to 16 bytes (vector reductions of the split-K partials)
+            dW = torch.empty(N, Kd, device=dev, dtype=torch.float32)
             db = torch.empty(N, device=dev, dtype=torch.float32)
             dy_is_dz = 1 if l < L - 1 else 0
             defer = (l == 0 and need_dx and _DEFER_WGRAD and B > 0 and getattr(ctx.w0, "grad", None) is None
                      and _lib.load().ctr_dnn_wgrad_is_scratch_free(
-                         _ptr(x), x.stride(0), _ptr(y), N, _ptr(cur), cur.stride(0), _ptr(dW), Kc, 1, B, K, N,
+                         _ptr(x), x.stride(0), _ptr(y), N, _ptr(cur), cur.stride(0), _ptr(dW), Kd, 1, B, K, N,
                          ctx.act, dy_is_dz) == 1)
             if defer:
                 main = torch.cuda.current_stream(dev)
@@ -587,9 +590,9 @@ class _DnnTower(torch.autograd.Function):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
-                              _ptr(cur), cur.stride(0), None, 0, _ptr(dW), Kc, 1, _ptr(db),
+                              _ptr(cur), cur.stride(0), None, 0, _ptr(dW), Kd, 1, _ptr(db),
                               B, K, N, ctx.act, dy_is_dz, 0, _stream())
-                    grads[0] = dW[:, :ctx.kws[0]].contiguous() if Kc != ctx.kws[0] else dW
+                    grads[0] = dW[:, :ctx.kws[0]].contiguous() if Kd != ctx.kws[0] else dW
                     ev = torch.cuda.Event()
                     ev.record(side)
                 for t in (x, y, cur, dW, db, grads[0]):
@@ -599,10 +602,10 @@ class _DnnTower(torch.autograd.Function):
                 grads[1] = db
             else:
                 _lib.call("ctr_dnn_layer_bwd_chain", _ptr(x), x.stride(0), _ptr(Wc), Kc, 1, _ptr(y), N,
-                          _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, _ptr(dW), Kc, 1, _ptr(db),
+                          _ptr(cur), cur.stride(0), _ptr(dx_full), ldx, _ptr(dW), Kd, 1, _ptr(db),
                           B, K, N, ctx.act, dy_is_dz,
                           ctx.act if l > 0 else 0, _stream())
-                grads[2 * l] = dW[:, :ctx.kws[l]].contiguous() if Kc != ctx.kws[l] else dW
+                grads[2 * l] = dW[:, :ctx.kws[l]].contiguous() if Kd != ctx.kws[l] else dW
                 grads[2 * l + 1] = db
             if need_dx:
                 cur = dx_full[:, :K] if ldx != K else dx_full
