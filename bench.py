@@ -673,6 +673,26 @@ def run_gpu_arm(args):
                 secondary[wl] = {"error": str(ex)[:300]}
                 torch.cuda.synchronize()
 
+        # labelled NON-PARITY fast mode: the same DeepFM step with single-pass TF32 tower GEMMs
+        # (ctr_set_gemm_passes(1)).  A secondary figure only: the headline above is the 3xTF32 parity mode.
+        from deepctr_torch_b200 import _lib
+        prev = _lib.load().ctr_set_gemm_passes(1)
+        try:
+            mf = measure_workload("deepfm", args, world, rank, dev, 10, 3, full=False)
+            pf = quick_parity_check(dev)
+            secondary["deepfm_fast_tf32"] = {
+                "workload": WORKLOADS["deepfm"]["desc"] + " — NON-PARITY fast mode: single-pass TF32 on the tensor cores",
+                "value": WORKLOADS["deepfm"]["B"] * 10 / (mf["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": mf["ms"] / 10,
+                "steps": 10, "cuda_graph": mf["cuda_graph"],
+                "logit_rel_err_vs_oracle": pf["max_rel_err"], "grad_rel_err_vs_oracle": pf["max_grad_rel_err"],
+                "meets_parity_bar": bool(pf["ok"]),
+                "per_entry_ms": {k: round(v["ms_per_step"], 4) for k, v in mf["per_entry"].items()}}
+        except Exception as ex:          # noqa: BLE001
+            secondary["deepfm_fast_tf32"] = {"error": str(ex)[:300]}
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().ctr_set_gemm_passes(prev)
+
     if rank != 0:
         if world > 1:
             _finish_multi_gpu()

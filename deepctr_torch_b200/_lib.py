@@ -99,6 +99,7 @@ SPECIAL = {
     "ctr_last_error": ([], ctypes.c_char_p),
     "ctr_unique_plan_hash_slots": ([c_i64], c_i64),
     "ctr_launch_count": ([], c_i64),
+    "ctr_set_gemm_passes": ([c_int], c_int),
     "ctr_gemm_scratch_bytes": ([c_i64, c_i64, c_i64], c_i64),
     "ctr_dnn_wgrad_is_scratch_free": ([_P, c_i64, _P, c_i64, _P, c_i64, _P, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int], c_int),
 }

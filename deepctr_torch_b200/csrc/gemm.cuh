@@ -41,6 +41,7 @@ inline GemmArgs gemm_args_default() {
 // 3xTF32 kernel (gemm_tc.cu) and the FP32 FFMA tiles (gemm.cu)
 int launch_sgemm(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+int ctr_gemm_passes();                           // 3 = 3xTF32 (parity), 1 = single-pass TF32 (fast, non-parity)
 unsigned long long* ctr_debug_buffer();          // buffer registered with ctr_debug_set_buffer (or NULL)
 // packed-operand engine (gemm_pk.cu): needs the scratch registered with ctr_set_scratch
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st);

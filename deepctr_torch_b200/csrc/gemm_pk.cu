@@ -275,6 +275,7 @@ struct PkParams {
     uint32_t raw_a_bytes, raw_b_bytes;    // raw cp.async region of each streamed operand, per depth
     int t0_b;                             // first converter thread of B's OP_TRANS groups
     unsigned long long* dbg;              // optional clock64 timeline of CTA (0,0,0) (ctr_debug_set_buffer): [8 events][64 stages]
+    int fast;                             // single-pass TF32 (non-parity fast mode): only the hi*hi MMA is issued
     int a_tma;                            // K-contiguous streamed A: raw [MT*128 x 16] fp32 tiles arrive by 2-D tiled TMA loads
                                           // (64-byte swizzle) instead of the converters' own cp.async pieces
 };
@@ -721,9 +722,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p, cons
                         const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
                         const uint64_t dal = make_smem_desc(a_hi + a_tile / 2, a_lbo, 128);
                         const uint32_t d = tmem_base + (uint32_t)(mt * BN);
-                        umma_tf32(d, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
-                        umma_tf32(d, dah, dbl, idesc, 1u);
-                        umma_tf32(d, dah, dbh, idesc, 1u);
+                        if (p.fast) {
+                            umma_tf32(d, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                        } else {
+                            umma_tf32(d, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(&a_empty[sa]);                // frees the stages when these MMAs retire
@@ -1177,6 +1182,7 @@ struct TwParams {
     int BN, SLOTS, SBW, RA, RB, tmem_cols, a_col0, has_mask;
     uint32_t off_braw, off_araw, off_bar, b_raw_bytes, a_raw_bytes;
     int b_pitch;                     // floats per row of a raw B tile (BN + 4)
+    int fast;                        // single-pass TF32 (non-parity fast mode)
     float* db;                       // bias gradient [M] (NULL: not wanted), accumulated with atomics
     unsigned long long* dbg;         // optional clock64 timeline of CTA (0,0,0) (ctr_debug_set_buffer): [10 events][64 stages]
 };
@@ -1289,9 +1295,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p, con
                     const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
                     const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
                     const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + slot * 32 + 8 * j), a_lo = a_hi + 16u;
-                    umma_tf32_ts(tmem_base, a_lo, dbh, idesc, (i | j) != 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_base, a_hi, dbl, idesc, 1u);
-                    umma_tf32_ts(tmem_base, a_hi, dbh, idesc, 1u);
+                    if (p.fast) {
+                        umma_tf32_ts(tmem_base, a_hi, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                    } else {
+                        umma_tf32_ts(tmem_base, a_lo, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, a_hi, dbl, idesc, 1u);
+                        umma_tf32_ts(tmem_base, a_hi, dbh, idesc, 1u);
+                    }
                 }
                 umma_commit(&b_empty[sb]);
                 umma_commit(&a_empty[slot]);
@@ -1781,6 +1791,7 @@ int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
     TwParams p{};
     p.g = g;
     p.db = db;
+    p.fast = ctr_gemm_passes() == 1 ? 1 : 0;
     p.dbg = ctr_debug_buffer();
     const int64_t gn = ceil_div64(g.N, 256);
     p.BN = (int)(ceil_div64(ceil_div64(g.N, gn), 16) * 16);
@@ -1883,6 +1894,7 @@ int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
         CTR_CUDA(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
     PkParams p{};
     p.g = g;
+    p.fast = ctr_gemm_passes() == 1 ? 1 : 0;
     p.dbg = ctr_debug_buffer();
     p.Ap = Ap;
     p.Bp = Bp;

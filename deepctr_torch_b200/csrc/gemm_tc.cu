@@ -430,6 +430,14 @@ int pick_mode(const float* P, int64_t s_row, int64_t s_k, const float* mask, int
 
 }  // namespace
 
+static int g_gemm_passes = 3;
+int ctr_gemm_passes() { return g_gemm_passes; }
+extern "C" int ctr_set_gemm_passes(int passes) {
+    const int prev = g_gemm_passes;
+    g_gemm_passes = passes == 1 ? 1 : 3;
+    return prev;
+}
+
 static unsigned long long* g_dbg_buf = nullptr;
 unsigned long long* ctr_debug_buffer() { return g_dbg_buf; }
 extern "C" int ctr_debug_set_buffer(void* ptr) {

@@ -35,6 +35,10 @@ int         ctr_version(void);            /* ABI version, currently 2 */
 const char* ctr_last_error(void);
 int         ctr_debug_set_buffer(void* dev_u64_buffer);   /* optional: per-stage clock64 timeline of the tensor-core GEMM (>= 256 u64), NULL = off */
 int64_t     ctr_launch_count(void);       /* kernels launched by this library so far (process-wide) */
+/* Tensor-core passes of the fp32 GEMMs: 3 (default, PARITY mode: 3xTF32, fp32-grade accuracy) or 1 (FAST mode,
+ * NOT parity: single-pass TF32, ~1e-3 relative error like torch.backends.cuda.matmul.allow_tf32).  Process-wide,
+ * read at launch time (a CUDA graph keeps the mode it was captured in).  Returns the previous value. */
+int         ctr_set_gemm_passes(int passes);
 
 /* activation codes shared by the dense ops (reference layers/activation.py:57-84) */
 enum { CTR_ACT_LINEAR = 0, CTR_ACT_RELU = 1, CTR_ACT_SIGMOID = 2, CTR_ACT_TANH = 3 };

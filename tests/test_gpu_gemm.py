@@ -197,3 +197,34 @@ def test_wgrad_engine_matches_fp64(B, K, N, masked):
     ref_b = dz.sum(0)
     assert float((dW[:, :K].double() - ref_w).abs().max() / ref_w.abs().max()) <= 2e-5
     assert float((db.double() - ref_b).abs().max() / ref_b.abs().max()) <= 5e-6
+
+
+def test_fast_mode_is_single_pass_and_restorable():
+    """ctr_set_gemm_passes(1) = the labelled NON-PARITY mode (single-pass TF32): ~1e-3 relative error, and the default
+    3xTF32 mode comes back bit-for-bit when the switch is restored (bench.py reports the fast mode as a secondary line)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 32768, 256, 432
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bm = torch.randn(N, K, device="cuda", generator=g)
+    ref = A.double() @ Bm.double().t()
+    ops.ensure_gemm_scratch(torch.device("cuda:0"), M, K, N)
+
+    def run():
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), K, 1, ops._ptr(Bm), K, 1, ops._ptr(C), N, 0, ops._stream())
+        torch.cuda.synchronize()
+        return C
+
+    exact = run()
+    prev = _lib.load().ctr_set_gemm_passes(1)
+    try:
+        assert prev == 3
+        fast = run()
+    finally:
+        assert _lib.load().ctr_set_gemm_passes(prev) == 1
+    again = run()
+    e_exact = float((exact.double() - ref).abs().max() / ref.abs().max())
+    e_fast = float((fast.double() - ref).abs().max() / ref.abs().max())
+    assert e_exact <= 5e-6
+    assert 1e-5 < e_fast < 5e-3, e_fast
+    assert torch.equal(exact, again)
