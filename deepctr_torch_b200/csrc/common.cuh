@@ -68,13 +68,13 @@ __device__ __forceinline__ void red_add4(float* p, float4 v) {
                  : "memory");
 }
 
+// (if chains, not switches, in both helpers: see act_grad_from_y)
 __device__ __forceinline__ float act_apply(int act, float z) {
-    switch (act) {
-        case CTR_ACT_RELU: return z > 0.f ? z : 0.f;
-        case CTR_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
-        case CTR_ACT_TANH: return tanhf(z);
-        default: return z;
-    }
+    if (act == CTR_ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == CTR_ACT_LINEAR) return z;
+    if (act == CTR_ACT_TANH) return tanhf(z);
+    if (act == CTR_ACT_SIGMOID) return 1.f / (1.f + expf(-z));
+    return z;
 }
 
 // derivative of the activation expressed through its OUTPUT y

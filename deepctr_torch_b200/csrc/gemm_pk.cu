@@ -713,21 +713,28 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_pk_kernel(PkParams p, cons
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(ringA + (size_t)sa * a_stage);
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
+                if (!p.fast) {
 #pragma unroll
-                for (int j = 0; j < PK_KB / 8; ++j) {
-                    const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
-                    const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t a_hi = a_base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo;
-                        const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
-                        const uint64_t dal = make_smem_desc(a_hi + a_tile / 2, a_lbo, 128);
-                        const uint32_t d = tmem_base + (uint32_t)(mt * BN);
-                        if (p.fast) {
-                            umma_tf32(d, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
-                        } else {
+                    for (int j = 0; j < PK_KB / 8; ++j) {
+                        const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t a_hi = a_base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo;
+                            const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
+                            const uint64_t dal = make_smem_desc(a_hi + a_tile / 2, a_lbo, 128);
+                            const uint32_t d = tmem_base + (uint32_t)(mt * BN);
                             umma_tf32(d, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
                             umma_tf32(d, dah, dbl, idesc, 1u);
                             umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
+                    }
+                } else {                                  // labelled non-parity mode: single-pass TF32
+#pragma unroll
+                    for (int j = 0; j < PK_KB / 8; ++j) {
+                        const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t dah = make_smem_desc(a_base + (uint32_t)mt * a_tile + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
+                            umma_tf32(tmem_base + (uint32_t)(mt * BN), dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
                         }
                     }
                 }
@@ -1290,17 +1297,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) gemm_tsw_kernel(TwParams p, con
             tc_fence_after();
             {
                 const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
+                if (!p.fast) {
 #pragma unroll
-                for (int j = 0; j < PK_KB / 8; ++j) {
-                    const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
-                    const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + slot * 32 + 8 * j), a_lo = a_hi + 16u;
-                    if (p.fast) {
-                        umma_tf32_ts(tmem_base, a_hi, dbh, idesc, (i | j) != 0 ? 1u : 0u);
-                    } else {
+                    for (int j = 0; j < PK_KB / 8; ++j) {
+                        const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + slot * 32 + 8 * j), a_lo = a_hi + 16u;
                         umma_tf32_ts(tmem_base, a_lo, dbh, idesc, (i | j) != 0 ? 1u : 0u);
                         umma_tf32_ts(tmem_base, a_hi, dbl, idesc, 1u);
                         umma_tf32_ts(tmem_base, a_hi, dbh, idesc, 1u);
+                    }
+                } else {                                  // labelled non-parity mode: single-pass TF32
+#pragma unroll
+                    for (int j = 0; j < PK_KB / 8; ++j) {
+                        const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                        umma_tf32_ts(tmem_base, tmem_base + (uint32_t)(p.a_col0 + slot * 32 + 8 * j), dbh, idesc, (i | j) != 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&b_empty[sb]);

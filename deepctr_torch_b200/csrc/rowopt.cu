@@ -30,22 +30,21 @@ struct OptArgs {
 
 __device__ __forceinline__ float opt_update(int kind, float w, float g, float& a, float& b, float lr, float b1, float b2,
                                             float eps, float bc1, float bc2_sqrt) {
-    switch (kind) {
-        case CTR_OPT_ADAGRAD:
-            a += g * g;
-            return w - lr * g / (sqrtf(a) + eps);
-        case CTR_OPT_ADAM: {
-            a = b1 * a + (1.f - b1) * g;
-            b = b2 * b + (1.f - b2) * g * g;
-            const float denom = sqrtf(b) / bc2_sqrt + eps;
-            return w - (lr / bc1) * (a / denom);
-        }
-        case CTR_OPT_RMSPROP:
-            a = b1 * a + (1.f - b1) * g * g;
-            return w - lr * g / (sqrtf(a) + eps);
-        default:
-            return w - lr * g;
+    if (kind == CTR_OPT_ADAGRAD) {
+        a += g * g;
+        return w - lr * g / (sqrtf(a) + eps);
     }
+    if (kind == CTR_OPT_ADAM) {
+        a = b1 * a + (1.f - b1) * g;
+        b = b2 * b + (1.f - b2) * g * g;
+        const float denom = sqrtf(b) / bc2_sqrt + eps;
+        return w - (lr / bc1) * (a / denom);
+    }
+    if (kind == CTR_OPT_RMSPROP) {
+        a = b1 * a + (1.f - b1) * g * g;
+        return w - lr * g / (sqrtf(a) + eps);
+    }
+    return w - lr * g;
 }
 
 // VEC: D % 4 == 0 — D/4 lanes per row, float4 accesses; otherwise one thread per element
