@@ -1169,6 +1169,250 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_ts_kernel(TsParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// PP engine (round 2): the SS engine as a PERSISTENT, tile-pipelined kernel for the tall GEMMs of the tower
+// (M = batch, K-contiguous streamed A by TMA, packed weights, no split-K).  One CTA per SM loops over 128 x BN
+// tiles; the accumulator is double-buffered in tensor memory (2 x BN <= 512 columns) and the roles are split:
+//   warp 0      TMA producer (raw A tiles + packed weight stages, rings run across tile boundaries)
+//   warp 1      MMA issuer (one lane)
+//   warps 2-9   converters (raw fp32 -> hi/lo MMA tile): two groups of 4 warps on alternating stages
+//   warps 10-17 epilogue of tile t while the main loop of tile t+1 runs
+// Why: in the one-tile-per-CTA kernel the prologue (4.5 k cycles) and the epilogue (10 k) of every tile are exposed
+// and 256-512 tiles leave a partial last wave on 148 SMs; with K = 256..432 that is a third of a tile's time
+// (profiles/r02_gemm_engines.md section 5).
+// ---------------------------------------------------------------------------------------------
+struct PpParams {
+    GemmArgs g;
+    const float* Bp;                 // packed B (row blocks of BN)
+    int64_t nkb, gm, gn;
+    int BN, SA, SB, RD, tmem_cols, has_mask, fast;
+    uint32_t off_b, off_raw, off_stg, off_bar;
+};
+constexpr int PP_CONV_WARPS = 8, PP_EPI_WARPS = 8;
+
+template <int EPI>
+__device__ __forceinline__ void pp_tile_epilogue(const GemmArgs& g, uint32_t tmem_acc, float* stg_base, int ew, int lane,
+                                                 int64_t m_tile0, int BN, int64_t n0) {
+    const int quad = ew & 3;                          // TMEM lane quadrant of this warp (= CTA warp index & 3, hardware rule)
+    const int cgrp = ew >> 2;                         // which half of the 32-column chunks
+    float* stg = stg_base + (size_t)(ew & 7) * (32 * PK_STG_PITCH);
+    const int nchunks = (BN + 31) / 32;
+    const int64_t m_base = m_tile0 + quad * 32;
+    if (m_base >= g.M) return;
+    for (int ci = cgrp; ci < nchunks; ci += PP_EPI_WARPS / 4) {
+        const int c0 = ci * 32;
+        if (n0 + c0 >= g.N) break;
+        uint32_t raw[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * PK_STG_PITCH + 4 * j) =
+                make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        __syncwarp();
+        const int colq = lane & 7;
+        const int col = c0 + 4 * colq;
+        const int64_t n = n0 + col;
+        int nvalid = 0;
+        if (col < BN && n < g.N) {
+            nvalid = BN - col < 4 ? BN - col : 4;
+            if (g.N - n < nvalid) nvalid = (int)(g.N - n);
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((EPI == EPI_BIAS_ACT || EPI == EPI_CROSS) && g.bias && nvalid > 0)
+            b4 = ld4_or_scalar(g.bias + n, nvalid, row_vec_ok(g.bias, 4, n));
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const int64_t m = m_base + r;
+            const float4 v = *reinterpret_cast<const float4*>(stg + r * PK_STG_PITCH + 4 * colq);
+            if (m < g.M && nvalid > 0) epi_store<EPI>(g, v, b4, m, n, nvalid, false);
+        }
+        __syncwarp();
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(PK_THREADS, 1) gemm_pp_kernel(PpParams p, const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_am) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const GemmArgs& g = p.g;
+    const int BN = p.BN, SA = p.SA, SB = p.SB, RD = p.RD;
+    const uint32_t a_stage = PK_AR * 128u;                // hi+lo of a 128 x 16 tile
+    const uint32_t b_stage = (uint32_t)BN * 128u;
+    const uint32_t raw_item = PK_AR * 64u * (p.has_mask ? 2u : 1u);
+    unsigned char* ringA = smem_raw;
+    unsigned char* ringB = smem_raw + p.off_b;
+    unsigned char* ringR = smem_raw + p.off_raw;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw + p.off_bar);
+    uint64_t* a_empty = a_full + SA;
+    uint64_t* b_full = a_empty + SA;
+    uint64_t* b_empty = b_full + SB;
+    uint64_t* raw_full = b_empty + SB;
+    uint64_t* raw_empty = raw_full + RD;
+    uint64_t* acc_full = raw_empty + RD;                  // [2]
+    uint64_t* acc_empty = acc_full + 2;                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int nkb = (int)p.nkb;
+    const int64_t n_tiles = p.gm * p.gn;
+
+    if (tid == 0) {
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], PP_CONV_WARPS / 2); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < RD; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], PP_CONV_WARPS / 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PP_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) tmem_alloc_warp(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wid == 0) {
+        // ------------------------------ TMA producer ---------------------------------------------
+        if (lane == 0) {
+            const unsigned char* b_src = reinterpret_cast<const unsigned char*>(p.Bp);
+            int sb = 0, dr = 0;
+            uint32_t phb = 1, phr = 1;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int64_t mblk = t / p.gn, nblk = t - mblk * p.gn;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&raw_empty[dr], phr);
+                    mbar_expect_tx(&raw_full[dr], raw_item);
+                    unsigned char* dst = ringR + (size_t)dr * raw_item;
+                    tma_load_2d(dst, &map_a, i * PK_KB, (int)(mblk * PK_AR), &raw_full[dr]);
+                    if (p.has_mask) tma_load_2d(dst + PK_AR * 64u, &map_am, i * PK_KB, (int)(mblk * PK_AR), &raw_full[dr]);
+                    if (++dr == RD) { dr = 0; phr ^= 1u; }
+                    mbar_wait(&b_empty[sb], phb);
+                    mbar_expect_tx(&b_full[sb], b_stage);
+                    bulk_g2s(ringB + (size_t)sb * b_stage, b_src + (nblk * p.nkb + i) * (int64_t)b_stage, b_stage, &b_full[sb]);
+                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (wid == 1) {
+        // ------------------------------ MMA issuer -----------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(BN);
+            const uint32_t a_lbo = PK_AR * 16u, b_lbo = (uint32_t)BN * 16u;
+            int sa = 0, sb = 0, buf = 0;
+            uint32_t pha = 0, phb = 0, phe[2] = {1, 1};
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[buf], phe[buf]);         // the epilogue drained this accumulator
+                phe[buf] ^= 1u;
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&a_full[sa], pha);
+                    mbar_wait(&b_full[sb], phb);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(ringA + (size_t)sa * a_stage);
+                    const uint32_t b_hi = smem_u32(ringB + (size_t)sb * b_stage), b_lo = b_hi + b_stage / 2;
+                    if (!p.fast) {
+#pragma unroll
+                        for (int j = 0; j < PK_KB / 8; ++j) {
+                            const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                            const uint64_t dbl = make_smem_desc(b_lo + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                            const uint32_t a_hi = a_base + (uint32_t)j * 2u * a_lbo;
+                            const uint64_t dah = make_smem_desc(a_hi, a_lbo, 128);
+                            const uint64_t dal = make_smem_desc(a_hi + a_stage / 2, a_lbo, 128);
+                            umma_tf32(d, dal, dbh, idesc, (i | j) != 0 ? 1u : 0u);      // small terms first
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PK_KB / 8; ++j) {
+                            const uint64_t dbh = make_smem_desc(b_hi + (uint32_t)j * 2u * b_lbo, b_lbo, 128);
+                            const uint64_t dah = make_smem_desc(a_base + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
+                            umma_tf32(d, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    umma_commit(&b_empty[sb]);
+                    if (i == nkb - 1) umma_commit(&acc_full[buf]);
+                    if (++sa == SA) { sa = 0; pha ^= 1u; }
+                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                }
+                buf ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (wid < 2 + PP_CONV_WARPS) {
+        // ------------------------------ converters: 2 groups x 4 warps on alternating stages -----
+        // One group converts a whole 128 x 16 stage (4 pieces per thread); the per-stage chain of a group (wait raw ->
+        // LDS -> wait free stage -> split -> STS -> proxy fence -> arrive) is latency-bound, so two groups in flight
+        // double the conversion rate (one group of 8 warps: 2 000 cycles per stage against 1 026 of MMA work).
+        const int grp = (wid - 2) >> 2;                       // 0 / 1
+        const int ct = tid - 64 - grp * 128;                  // 0..127 inside the group
+        int raw_off[4], toff[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = ct + 128 * q;
+            const int c = idx >> 7, r = idx & 127;           // 512 pieces = 4 chunks x 128 rows
+            raw_off[q] = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+            toff[q] = (c * PK_AR + r) * 4;
+        }
+        const int mask_act = g.amask_act;
+        // ring positions of this group's FIRST stage (global stage index = grp), then +2 per iteration
+        int sa = grp % SA, dr = grp % RD;
+        uint32_t pha = 1u ^ (uint32_t)((grp / SA) & 1), phr = (uint32_t)((grp / RD) & 1);
+        int64_t my_tiles = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) ++my_tiles;
+        const int64_t total_stages = my_tiles * nkb;
+        for (int64_t gs = grp; gs < total_stages; gs += 2) {
+            mbar_wait(&raw_full[dr], phr);
+            const unsigned char* base = ringR + (size_t)dr * raw_item;
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = *reinterpret_cast<const float4*>(base + raw_off[q]);
+                if (p.has_mask) v[q] = pk_mask4(v[q], *reinterpret_cast<const float4*>(base + PK_AR * 64u + raw_off[q]), mask_act);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[dr]);
+            dr += 2;
+            if (dr >= RD) { dr -= RD; phr ^= 1u; }
+            mbar_wait(&a_empty[sa], pha);
+            float* tile = reinterpret_cast<float*>(ringA + (size_t)sa * a_stage);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_store(tile, toff[q], PK_AR * 16, v[q]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[sa]);
+            sa += 2;
+            if (sa >= SA) { sa -= SA; pha ^= 1u; }
+        }
+    } else {
+        // ------------------------------ epilogue warps -------------------------------------------
+        const int ew = wid - 10;                               // 0..7; TMEM quadrant = wid & 3 = (ew + 2) & 3
+        const int ewq = ((wid & 3)) | ((ew >> 2) << 2);        // quadrant in the low bits, column group above
+        float* stg_base = reinterpret_cast<float*>(smem_raw + p.off_stg);
+        int buf = 0;
+        uint32_t phf[2] = {0, 0};
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int64_t mblk = t / p.gn, nblk = t - mblk * p.gn;
+            mbar_wait(&acc_full[buf], phf[buf]);
+            phf[buf] ^= 1u;
+            tc_fence_after();
+            pp_tile_epilogue<EPI>(g, tmem_base + (uint32_t)(buf * BN), stg_base, ewq, lane, mblk * PK_AR, BN, nblk * BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            buf ^= 1;
+        }
+    }
+    __syncthreads();
+    if (wid == 1) {
+        tc_fence_after();
+        tmem_dealloc_warp(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TSW engine (round 2): the weight-gradient GEMM   dW[n, k] (+)= sum_b dZ[b, n] * X[b, k]
 // (reference: autograd of nn.Linear inside DNN, layers/core.py:120-134) with BOTH operands streamed from
 // the batch-major activations and the contraction over the BATCH:
@@ -1864,7 +2108,93 @@ int launch_gemm_tsw(const GemmArgs& g, float* db, cudaStream_t st) {
     return 0;
 }
 
+// PP engine launcher: returns -3 when the shape / layout does not qualify (caller continues with the SS engine)
+static int launch_gemm_pp(const GemmArgs& g, cudaStream_t st) {
+    // Default: short contractions only (K <= 256), where the exposed prologue / epilogue of the one-tile-per-CTA kernel
+    // is a third of a tile: input gradient L1 117.7 -> 98.8 us, L2 48.3 -> 43.6 us.  For longer K the 128-row tiles
+    // fetch every weight stage twice as often as the 256-row tiles of the SS engine and the weight ring paces the loop
+    // (forward L1 96.5 vs 94.7 us): CTR_GEMM_PP=1 forces the engine for any K, =0 disables it.
+    const char* e = getenv("CTR_GEMM_PP");
+    if (e && e[0] == '0') return -3;
+    if (!(e && e[0] == '1') && g.K > 256) return -3;
+    const int64_t sms = ctr_sm_count();
+    if (g.bmask || g.K < 32 || g.N < 16 || g.M < 2 * sms * PK_AR) return -3;       // >= 2 tiles per SM: no split-K needed
+    if (g.M > 0x7fffffff || g.K > 0x7fffffff || !tensor_map_encoder()) return -3;
+    if (stream_mode(g.A, g.sam, g.sak, g.amask, g.smm, g.smk) != OP_KVEC) return -3;
+    PpParams p{};
+    p.g = g;
+    const int64_t ntn = ceil_div64(g.N, 256);
+    p.BN = (int)(ceil_div64(ceil_div64(g.N, ntn), 16) * 16);
+    p.gn = ceil_div64(g.N, p.BN);
+    p.gm = ceil_div64(g.M, PK_AR);
+    p.nkb = ceil_div64(g.K, PK_KB);
+    p.has_mask = g.amask ? 1 : 0;
+    p.fast = ctr_gemm_passes() == 1 ? 1 : 0;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
+    if (p.tmem_cols > 512) return -3;
+    const int64_t b_bytes = p.gn * p.nkb * (int64_t)p.BN * 128;
+    if (b_bytes > kStreamThresholdBytes) return -3;    // weights only
+    void* scratch = gemm_scratch_ptr(b_bytes);
+    if (!scratch) return -3;
+    // shared-memory plan: [A ring | B ring | raw ring (1 KB aligned) | epilogue staging | barriers]
+    const int64_t a_stage = (int64_t)PK_AR * 128, b_stage = (int64_t)p.BN * 128, raw_item = (int64_t)PK_AR * 64 * (p.has_mask ? 2 : 1);
+    const int64_t stg = (int64_t)PP_EPI_WARPS * 32 * PK_STG_PITCH * 4;
+    const int64_t budget = 232448 - 1024;
+    p.SA = 0;
+    const int opts[4][3] = {{4, 4, 4}, {3, 3, 4}, {3, 3, 3}, {3, 2, 3}};
+    for (int i = 0; i < 4 && !p.SA; ++i) {
+        const int64_t rings = (opts[i][0] * a_stage + opts[i][1] * b_stage + 1023) / 1024 * 1024;
+        if (rings + opts[i][2] * raw_item + stg <= budget) {
+            p.SA = opts[i][0];
+            p.SB = opts[i][1];
+            p.RD = opts[i][2];
+        }
+    }
+    if (!p.SA) return -3;
+    p.off_b = (uint32_t)(p.SA * a_stage);
+    p.off_raw = (uint32_t)((p.SA * a_stage + p.SB * b_stage + 1023) / 1024 * 1024);
+    p.off_stg = (uint32_t)(p.off_raw + p.RD * raw_item);
+    p.off_bar = (uint32_t)(p.off_stg + stg);
+    const size_t smem = p.off_bar + (size_t)(2 * p.SA + 2 * p.SB + 2 * p.RD + 4) * sizeof(uint64_t) + 16;
+    if (smem > 232448) return -3;
+    CUtensorMap map_a{}, map_am{};
+    bool ok = make_tile_map(&map_a, g.A, g.M, g.K, g.sam, PK_KB, PK_AR, true);
+    if (ok && g.amask) ok = make_tile_map(&map_am, g.amask, g.M, g.K, g.smm, PK_KB, PK_AR, true);
+    if (!ok) return -3;
+    float* Bp = reinterpret_cast<float*>(scratch);
+    PackArgs pb{g.B, g.sbn, g.sbk, nullptr, 0, 0, 0, g.N, g.K, p.BN, p.gn, p.nkb, Bp};
+    int rc;
+    if ((rc = launch_pack(pb, st)) != 0) return rc;
+    p.Bp = Bp;
+    static bool configured = false;
+    if (!configured) {
+        const int max_smem = 232448;
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pp_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pp_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pp_kernel<EPI_MUL_ACTGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pp_kernel<EPI_CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CTR_CUDA(cudaFuncSetAttribute(gemm_pp_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        configured = true;
+    }
+    const int64_t tiles = p.gm * p.gn;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    switch (g.epilogue) {
+        case EPI_BIAS_ACT: gemm_pp_kernel<EPI_BIAS_ACT><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_MUL_ACTGRAD: gemm_pp_kernel<EPI_MUL_ACTGRAD><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_CROSS: gemm_pp_kernel<EPI_CROSS><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        case EPI_MUL: gemm_pp_kernel<EPI_MUL><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+        default: gemm_pp_kernel<EPI_STORE><<<grid, PK_THREADS, smem, st>>>(p, map_a, map_am); break;
+    }
+    CTR_LAUNCH_OK("gemm_pp_kernel");
+    return 0;
+}
+
 int launch_gemm_pk(const GemmArgs& g, cudaStream_t st) {
+    {
+        const int rc_pp = launch_gemm_pp(g, st);
+        if (rc_pp != -3) return rc_pp;
+    }
     {
         const int rc_ts = launch_gemm_ts(g, st);
         if (rc_ts != -3) return rc_ts;

@@ -228,3 +228,29 @@ def test_fast_mode_is_single_pass_and_restorable():
     assert e_exact <= 5e-6
     assert 1e-5 < e_fast < 5e-3, e_fast
     assert torch.equal(exact, again)
+
+
+@pytest.mark.parametrize("M,N,K,kind", [(65536, 432, 256, "nn"), (65536, 256, 128, "nn"), (66000, 128, 256, "nt"),
+                                        (40000, 300, 64, "nt"), (70001, 130, 100, "nt"), (65536, 256, 432, "nt")])
+def test_pp_engine_matches_ss_engine(M, N, K, kind, monkeypatch):
+    """The persistent tile-pipelined engine (gemm_pp_kernel: double-buffered accumulators, epilogue of tile t under the
+    main loop of tile t+1) against the one-tile-per-CTA SS engine and fp64: same arithmetic order, so bit-identical.
+    CTR_GEMM_PP is read at every launch: 1 forces the engine (any K), 0 disables it."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    K4 = (K + 3) // 4 * 4
+    A = torch.randn(M, K4, device="cuda", generator=g)
+    Bm = torch.randn(N, K4, device="cuda", generator=g) if kind == "nt" else torch.randn(K, N, device="cuda", generator=g)
+    ops.ensure_gemm_scratch(torch.device("cuda:0"), M, K, N)
+    outs = {}
+    for pp in ("1", "0"):
+        monkeypatch.setenv("CTR_GEMM_PP", pp)
+        C = torch.full((M, N), float("nan"), device="cuda")
+        if kind == "nt":
+            _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), K4, 1, ops._ptr(Bm), K4, 1, ops._ptr(C), N, 0, ops._stream())
+        else:
+            _lib.call("ctr_sgemm", M, N, K, ops._ptr(A), K4, 1, ops._ptr(Bm), 1, N, ops._ptr(C), N, 0, ops._stream())
+        torch.cuda.synchronize()
+        outs[pp] = C
+    ref = A[:, :K].double() @ (Bm[:, :K].double().t() if kind == "nt" else Bm.double())
+    assert float((outs["1"].double() - ref).abs().max() / ref.abs().max()) <= 5e-6
+    assert torch.equal(outs["1"], outs["0"])
