@@ -2116,7 +2116,9 @@ static int launch_gemm_pp(const GemmArgs& g, cudaStream_t st) {
     // (forward L1 96.5 vs 94.7 us): CTR_GEMM_PP=1 forces the engine for any K, =0 disables it.
     const char* e = getenv("CTR_GEMM_PP");
     if (e && e[0] == '0') return -3;
-    if (!(e && e[0] == '1') && g.K > 256) return -3;
+    // masked A (act'(Y) prologue: a second raw tile per stage) leaves room for only two weight stages: 104 us against
+    // 82 us of the SS engine on the top layer's input gradient (profiles/r02_final_deepfm_kernels.md) — SS keeps it
+    if (!(e && e[0] == '1') && (g.K > 256 || g.amask)) return -3;
     const int64_t sms = ctr_sm_count();
     if (g.bmask || g.K < 32 || g.N < 16 || g.M < 2 * sms * PK_AR) return -3;       // >= 2 tiles per SM: no split-K needed
     if (g.M > 0x7fffffff || g.K > 0x7fffffff || !tensor_map_encoder()) return -3;
