@@ -28,7 +28,7 @@ class DNN(nn.Module):
         self.use_bn = use_bn
         if len(hidden_units) == 0:
             raise ValueError("hidden_units is empty!!")
-        if not isinstance(activation, str) or activation.lower() not in tuple(ops.ACT_CODES) + ("prelu",):
+        if not isinstance(activation, str) or activation.lower() not in tuple(ops.ACT_CODES) + ("prelu", "dice"):
             raise NotImplementedError("DNN activation %r is not implemented by the CUDA tower" % (activation,))
         self.activation = activation.lower()
         units = [inputs_dim] + list(hidden_units)
@@ -38,6 +38,11 @@ class DNN(nn.Module):
         if self.activation == "prelu":
             # same container and key names as the reference (`activation_layers.<i>.weight`, core.py:110-111)
             self.activation_layers = nn.ModuleList([nn.PReLU() for _ in range(len(units) - 1)])
+        if self.activation == "dice":
+            # batch-normalising activation (reference activation.py:6-45): torch CUDA ops between the fused linears,
+            # keys `activation_layers.<i>.bn.*` / `.alpha` as in the reference
+            from .activation import Dice
+            self.activation_layers = nn.ModuleList([Dice(units[i + 1], dice_dim) for i in range(len(units) - 1)])
         for name, tensor in self.linears.named_parameters():
             if "weight" in name:
                 nn.init.normal_(tensor, mean=0, std=init_std)
@@ -45,6 +50,15 @@ class DNN(nn.Module):
 
     def forward(self, inputs):
         x = inputs
+        if self.activation == "dice":
+            for i, lin in enumerate(self.linears):
+                x = ops.dnn_layer(x, lin.weight, lin.bias, "linear")
+                if self.use_bn:
+                    x = self.bn[i](x)
+                x = self.activation_layers[i](x)
+                if self.dropout_rate > 0:
+                    x = F.dropout(x, self.dropout_rate, self.training)
+            return x
         if self.activation == "prelu":
             for i, lin in enumerate(self.linears):
                 x = ops.dnn_layer(x, lin.weight, lin.bias, "linear")
