@@ -549,7 +549,7 @@ def measure_workload(workload, args, world, rank, dev, steps, warmup, full=True)
         pipe = {"primed": False}
         out["e2e_mode"] = "copy-then-step"
         ms_e2e = None
-        if use_graph and world == 1 and os.environ.get("CTR_BENCH_PREFETCH", "1") != "0":
+        if use_graph and os.environ.get("CTR_BENCH_PREFETCH", "1") != "0":
             try:                                  # input pipeline: H2D of step i+1 overlaps step i
                 gstep.enable_prefetch()
                 ms_e2e = timed(step_e2e_pipelined, steps, max(3, warmup // 2))

@@ -14,7 +14,55 @@ import torch
 from . import ops
 
 
-class GraphedStep:
+class _PrefetchMixin:
+    """Input pipeline shared by the graphed steps: the next batch travels host -> device on a copy stream while the
+    current step computes.  Needs ``self.X`` / ``self.y`` (the graph's static inputs) and ``self._replay()``."""
+
+    # ---- input pipeline: the next batch travels host -> device while the current step computes ----
+    def enable_prefetch(self):
+        """Two device staging buffers + a copy stream.  ``prefetch(X, y)`` (pinned host tensors) enqueues
+        the H2D copy of a FUTURE step on the copy stream; ``step_prefetched()`` consumes the oldest
+        prefetched batch (device-to-device into the graph's static inputs, ~10 us) and replays."""
+        dev = self.X.device
+        cur = torch.cuda.current_stream(dev)
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [(torch.empty_like(self.X), torch.empty_like(self.y)) for _ in range(2)]
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]    # H2D into staging[k] finished (copy stream)
+        self._free = [torch.cuda.Event(), torch.cuda.Event()]     # staging[k] consumed (compute stream)
+        for e in self._free:
+            e.record(cur)
+        self._pf = 0        # next staging slot to fill
+        self._use = 0       # next staging slot to consume
+        self._pending = 0
+
+    def prefetch(self, X, y):
+        if self._pending >= 2:
+            raise RuntimeError("GraphedStep.prefetch: both staging buffers are full")
+        k = self._pf
+        self._pf ^= 1
+        self._pending += 1
+        cs = self._copy_stream
+        cs.wait_event(self._free[k])
+        with torch.cuda.stream(cs):
+            self._stage[k][0].copy_(X, non_blocking=True)
+            self._stage[k][1].copy_(y.reshape(-1), non_blocking=True)
+            self._ready[k].record(cs)
+
+    def step_prefetched(self):
+        if self._pending <= 0:
+            raise RuntimeError("GraphedStep.step_prefetched: nothing was prefetched")
+        k = self._use
+        self._use ^= 1
+        self._pending -= 1
+        cur = torch.cuda.current_stream(self.X.device)
+        cur.wait_event(self._ready[k])
+        self.X.copy_(self._stage[k][0], non_blocking=True)
+        self.y.copy_(self._stage[k][1], non_blocking=True)
+        self._free[k].record(cur)
+        return self._replay()
+
+
+class GraphedStep(_PrefetchMixin):
     def __init__(self, model, batch_size, loss_fn=None, warmup=3, with_reg=False):
         self.model = model
         dev = torch.device(model.device)
@@ -64,62 +112,16 @@ class GraphedStep:
         """Copy one batch in (host or device tensors) and replay; returns the (device) loss tensor."""
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y.reshape(-1), non_blocking=True)
+        return self._replay()
+
+    def _replay(self):
         self.graph.replay()
         self.replays += 1
         if self._parked:
             self.model._plan.pending[:] = self._parked
         return self.loss
 
-    # ---- input pipeline: the next batch travels host -> device while the current step computes ----
-    def enable_prefetch(self):
-        """Two device staging buffers + a copy stream.  ``prefetch(X, y)`` (pinned host tensors) enqueues
-        the H2D copy of a FUTURE step on the copy stream; ``step_prefetched()`` consumes the oldest
-        prefetched batch (device-to-device into the graph's static inputs, ~10 us) and replays."""
-        dev = self.X.device
-        cur = torch.cuda.current_stream(dev)
-        self._copy_stream = torch.cuda.Stream(device=dev)
-        self._stage = [(torch.empty_like(self.X), torch.empty_like(self.y)) for _ in range(2)]
-        self._ready = [torch.cuda.Event(), torch.cuda.Event()]    # H2D into staging[k] finished (copy stream)
-        self._free = [torch.cuda.Event(), torch.cuda.Event()]     # staging[k] consumed (compute stream)
-        for e in self._free:
-            e.record(cur)
-        self._pf = 0        # next staging slot to fill
-        self._use = 0       # next staging slot to consume
-        self._pending = 0
-
-    def prefetch(self, X, y):
-        if self._pending >= 2:
-            raise RuntimeError("GraphedStep.prefetch: both staging buffers are full")
-        k = self._pf
-        self._pf ^= 1
-        self._pending += 1
-        cs = self._copy_stream
-        cs.wait_event(self._free[k])
-        with torch.cuda.stream(cs):
-            self._stage[k][0].copy_(X, non_blocking=True)
-            self._stage[k][1].copy_(y.reshape(-1), non_blocking=True)
-            self._ready[k].record(cs)
-
-    def step_prefetched(self):
-        if self._pending <= 0:
-            raise RuntimeError("GraphedStep.step_prefetched: nothing was prefetched")
-        k = self._use
-        self._use ^= 1
-        self._pending -= 1
-        cur = torch.cuda.current_stream(self.X.device)
-        cur.wait_event(self._ready[k])
-        self.X.copy_(self._stage[k][0], non_blocking=True)
-        self.y.copy_(self._stage[k][1], non_blocking=True)
-        self._free[k].record(cur)
-        self.graph.replay()
-        self.replays += 1
-        if self._parked:
-            self.model._plan.pending[:] = self._parked
-        return self.loss
-
-
-
-class ShardedGraphedStep:
+class ShardedGraphedStep(_PrefetchMixin):
     """The row-sharded multi-GPU step (forward with the row exchange, loss, backward with the row-gradient
     push, dense-gradient all-reduce, receive-list bookkeeping) as TWO alternating CUDA graphs — one per
     step parity, because the receive lists are double-buffered by parity.  NCCL collectives are captured
@@ -172,6 +174,9 @@ class ShardedGraphedStep:
     def __call__(self, X, y):
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y.reshape(-1), non_blocking=True)
+        return self._replay()
+
+    def _replay(self):
         i = self.replays & 1
         self.graphs[i].replay()
         self.replays += 1
