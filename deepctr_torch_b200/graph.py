@@ -121,6 +121,7 @@ class GraphedStep(_PrefetchMixin):
             self.model._plan.pending[:] = self._parked
         return self.loss
 
+
 class ShardedGraphedStep(_PrefetchMixin):
     """The row-sharded multi-GPU step (forward with the row exchange, loss, backward with the row-gradient
     push, dense-gradient all-reduce, receive-list bookkeeping) as TWO alternating CUDA graphs — one per
